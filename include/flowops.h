@@ -1,0 +1,112 @@
+/*
+ * flowops.h -- C ABI of libflowops.so: the B200 (sm_100a) flow hot path of ir2rgb / vid2vid.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one pybind11/ATen entry point (or one
+ * ATen call) of the reference; paths are relative to
+ * /root/reference/models/flownet2_pytorch/networks/ unless they start with models/.
+ *
+ * Conventions
+ *   - every tensor is fp32, contiguous NCHW, resident on the device the stream belongs to;
+ *   - the library never allocates, frees or retains a pointer; scratch space is passed in as
+ *     `workspace` (query the size first), outputs are fully written (callers need not zero them);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ *     stream), performs no host synchronisation and is CUDA-graph capturable;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative FLOWOPS_E* code;
+ *     flowops_last_error() returns a thread-local message for the last non-zero return.
+ */
+#ifndef FLOWOPS_H
+#define FLOWOPS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOWOPS_VERSION 1
+
+#define FLOWOPS_EINVAL (-1)        /* bad argument (null pointer, non-positive size, ...)            */
+#define FLOWOPS_EUNSUPPORTED (-2)  /* parameter combination the reference never defines/uses        */
+#define FLOWOPS_EWORKSPACE (-3)    /* workspace missing, misaligned or too small                    */
+
+/* warp coordinate conventions */
+#define FLOWOPS_WARP_RESAMPLE2D 0  /* resample2d_package: sample at (x+dx, y+dy), clamp corners      */
+#define FLOWOPS_WARP_GRIDSAMPLE 1  /* models/networks.py:93-100: vid2vid grid + F.grid_sample
+                                      (bilinear, border, align_corners=False)                       */
+
+int flowops_version(void);
+const char *flowops_last_error(void);
+
+/* ---- ChannelNorm --------------------------------------------------------------------------- */
+
+/* Replaces channelnorm_cuda.forward (channelnorm_cuda.cc:6-15 -> channelnorm_kernel.cu:98-127).
+ * y[b,0,h,w] = sqrt(sum_c x[b,c,h,w]^2); x is [B,C,H,W], y is [B,1,H,W].  Bit-identical to the
+ * reference kernel (FFMA chain in channel order, IEEE sqrt).  norm_deg is ignored there too. */
+int flowops_cnorm_fwd(const float *x, float *y, int B, int C, int H, int W, void *stream);
+
+/* Replaces channelnorm_cuda.backward (channelnorm_cuda.cc:17-25 -> channelnorm_kernel.cu:129-177).
+ * gx[b,c,h,w] = gy[b,0,h,w] * x[b,c,h,w] / (y[b,0,h,w] + 1e-9), divide in fp64. */
+int flowops_cnorm_bwd(const float *x, const float *y, const float *gy, float *gx,
+                      int B, int C, int H, int W, void *stream);
+
+/* ---- Flow warp ----------------------------------------------------------------------------- */
+
+/* Replaces resample2d_cuda.forward (resample2d_cuda.cc:6-14 -> resample2d_kernel.cu:192-233) for
+ * mode RESAMPLE2D (kernel_size 1), and the get_grid + normalise + F.grid_sample chain of
+ * models/networks.py:15-28,89-100 (== models/base_model.py:123-136) for mode GRIDSAMPLE.
+ * img, out: [B,C,H,W]; flow: [B,2,H,W] in pixels (ch0 = dx, ch1 = dy).
+ * lin_x[W], lin_y[H]: torch.linspace(-1,1,W|H) tables (device), required for GRIDSAMPLE only. */
+int flowops_warp_fwd(const float *img, const float *flow, float *out,
+                     int B, int C, int H, int W, int mode,
+                     const float *lin_x, const float *lin_y, void *stream);
+
+/* Replaces resample2d_cuda.backward (resample2d_cuda.cc:16-26 -> resample2d_kernel.cu:235-310) and
+ * autograd through the models/networks.py chain.  gimg ([B,C,H,W]) and gflow ([B,2,H,W]) may each
+ * be NULL when that gradient is not needed (discriminator.py:120,137).  gimg is zero-filled by the
+ * callee and then accumulated with warp-aggregated atomics. */
+int flowops_warp_bwd(const float *img, const float *flow, const float *gout,
+                     float *gimg, float *gflow,
+                     int B, int C, int H, int W, int mode,
+                     const float *lin_x, const float *lin_y, void *stream);
+
+/* ---- Correlation --------------------------------------------------------------------------- */
+
+/* Output shape, correlation_cuda.cc:19-34. */
+int flowops_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2,
+                           int *oC, int *oH, int *oW);
+
+/* Scratch the fast path needs (the role of rInput1/rInput2 in correlation.py:16-17); 0 when the
+ * generic kernel is used.  Alignment requirement on `workspace`: 256 bytes. */
+size_t flowops_corr_fwd_workspace_bytes(int B, int C, int H, int W,
+                                        int pad, int k, int md, int s1, int s2);
+size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W,
+                                        int pad, int k, int md, int s1, int s2);
+
+/* Replaces correlation_cuda.forward (correlation_cuda.cc:10-87 -> correlation_cuda_kernel.cu:336-427).
+ * in1, in2: [B,C,H,W]; out: [B,oC,oH,oW].  corr_multiply is ignored by the reference kernels and is
+ * not part of this ABI. */
+int flowops_corr_fwd(const float *in1, const float *in2, float *out,
+                     int B, int C, int H, int W,
+                     int pad, int k, int md, int s1, int s2,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).
+ * gout: [B,oC,oH,oW]; gin1, gin2: [B,C,H,W] (either may be NULL). */
+int flowops_corr_bwd(const float *in1, const float *in2, const float *gout,
+                     float *gin1, float *gin2,
+                     int B, int C, int H, int W,
+                     int pad, int k, int md, int s1, int s2,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Measurement helper (not part of the reference surface) -------------------------------- */
+
+/* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent
+ * FFMAs per thread.  Returns (through *flops) the FLOP count of one launch so that the caller can
+ * time it with CUDA events and derive the FP32-FMA pipe peak the Correlation roofline is quoted
+ * against.  sink: device buffer of at least 4 bytes. */
+int flowops_bench_ffma(float *sink, int iters, double *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWOPS_H */

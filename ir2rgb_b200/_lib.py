@@ -1,0 +1,70 @@
+"""ctypes binding of libflowops.so (include/flowops.h).  No torch C++ extension, no dispatch layer.
+
+The library is built in-tree by ``python -m ir2rgb_b200.build`` (``__graft_entry__.build()`` does it).
+If it is missing, loading fails loudly: there is no CPU or PyTorch fallback for the hot path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflowops.so")
+
+WARP_RESAMPLE2D = 0
+WARP_GRIDSAMPLE = 1
+
+_c_float_p = ctypes.c_void_p   # device pointers travel as plain addresses
+_int = ctypes.c_int
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); every symbol include/flowops.h declares
+SIGNATURES = {
+    "flowops_version": (_int, []),
+    "flowops_last_error": (ctypes.c_char_p, []),
+    "flowops_cnorm_fwd": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
+    "flowops_cnorm_bwd": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "flowops_warp_fwd": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "flowops_warp_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "flowops_corr_out_shape": (_int, [_int] * 7 + [ctypes.POINTER(_int)] * 3),
+    "flowops_corr_fwd_workspace_bytes": (_sz, [_int] * 9),
+    "flowops_corr_bwd_workspace_bytes": (_sz, [_int] * 9),
+    "flowops_corr_fwd": (_int, [_vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_bench_ffma": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), _vp]),
+}
+
+_lib = None
+
+
+class FlowopsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libflowops.so once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlowopsError(
+            "libflowops.so not found at %s -- build it with `python -m ir2rgb_b200.build` "
+            "(needs nvcc; there is no CPU fallback for the flow hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.flowops_version() != 1:
+        raise FlowopsError("libflowops.so version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    """Turn a non-zero return into a RuntimeError, like the reference's AT_ERROR
+    (correlation_cuda.cc:81-83)."""
+    if rc != 0:
+        msg = load().flowops_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise NotImplementedError("%s: %s" % (what, msg))
+        raise FlowopsError("%s failed (%d): %s" % (what, rc, msg))

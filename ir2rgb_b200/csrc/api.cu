@@ -1,0 +1,73 @@
+// api.cu -- error plumbing, version, and the FFMA-peak measurement helper of libflowops.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace flowops {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// Launch-time errors only (cudaPeekAtLastError does not synchronise, so calls stay async and
+// CUDA-graph capturable).  The reference does the same with cudaGetLastError
+// (correlation_cuda_kernel.cu:417-424) and turns it into a RuntimeError; the Python layer here
+// does likewise.
+int check_launch(const char *what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// 64 independent accumulators per thread, 2 FFMA sources from registers: the pattern a register-
+// tiled FP32 kernel issues.  8 warps x 2 CTAs per SM.
+__global__ void __launch_bounds__(256, 2) ffma_peak_kernel(float *sink, int iters, float a, float b)
+{
+    float acc[8][8], u[8], v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u[i] = a + (threadIdx.x + i) * 1e-7f;
+        v[i] = b + (threadIdx.x * 8 + i) * 1e-7f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = (float)(i - j);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(u[i], v[j], acc[i][j]);   // 8x8 outer product
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    if (s == 123.456f) *sink = s;   // never true in practice; keeps the chain alive
+}
+
+}  // namespace flowops
+
+using namespace flowops;
+
+extern "C" int flowops_version(void) { return FLOWOPS_VERSION; }
+
+extern "C" const char *flowops_last_error(void) { return g_err; }
+
+extern "C" int flowops_bench_ffma(float *sink, int iters, double *flops, void *stream)
+{
+    FLOWOPS_REQUIRE(sink && iters > 0, FLOWOPS_EINVAL, "bench_ffma: bad arguments");
+    const int grid = kNumSMs * 2 * 4;
+    ffma_peak_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.999f, 0.001f);
+    if (flops) *flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+    return check_launch("bench_ffma");
+}

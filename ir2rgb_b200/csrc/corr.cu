@@ -1,0 +1,89 @@
+// corr.cu -- C-ABI entry points of the Correlation operator and the fast/generic dispatch.
+#include <math.h>
+
+#include "corr.cuh"
+
+namespace flowops {
+
+int corr_geometry(CorrGeom &g, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2)
+{
+    FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "corr: bad shape %dx%dx%dx%d", B, C, H, W);
+    FLOWOPS_REQUIRE(k >= 1 && (k & 1) && s1 >= 1 && s2 >= 1 && md >= 0 && pad >= 0, FLOWOPS_EINVAL,
+                    "corr: bad parameters pad=%d k=%d md=%d s1=%d s2=%d", pad, k, md, s1, s2);
+    g.B = B; g.C = C; g.H = H; g.W = W;
+    g.pad = pad; g.k = k; g.md = md; g.s1 = s1; g.s2 = s2;
+    g.kr = (k - 1) / 2;
+    g.dr = md / s2;
+    g.D = 2 * g.dr + 1;
+    const int br = g.kr + md;
+    g.oC = g.D * g.D;
+    // correlation_cuda.cc:31-32 (float ceil of a float quotient)
+    g.oH = (int)ceilf((float)(H + 2 * pad - 2 * br) / (float)s1);
+    g.oW = (int)ceilf((float)(W + 2 * pad - 2 * br) / (float)s1);
+    FLOWOPS_REQUIRE(g.oH > 0 && g.oW > 0, FLOWOPS_EINVAL, "corr: empty output (%d x %d)", g.oH, g.oW);
+    FLOWOPS_REQUIRE((size_t)B * g.oC * g.oH * g.oW < (1ull << 40) && (size_t)C * H * W < (1ull << 31),
+                    FLOWOPS_EUNSUPPORTED, "corr: tensor too large");
+    return 0;
+}
+
+}  // namespace flowops
+
+using namespace flowops;
+
+extern "C" int flowops_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2,
+                                      int *oC, int *oH, int *oW)
+{
+    CorrGeom g;
+    const int rc = corr_geometry(g, 1, 1, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    if (oC) *oC = g.oC;
+    if (oH) *oH = g.oH;
+    if (oW) *oW = g.oW;
+    return 0;
+}
+
+extern "C" size_t flowops_corr_fwd_workspace_bytes(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2)
+{
+    CorrGeom g;
+    if (corr_geometry(g, B, C, H, W, pad, k, md, s1, s2)) return 0;
+    return corr_fast_supported(g) ? corr_fast_fwd_workspace(g) : 0;
+}
+
+extern "C" size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2)
+{
+    CorrGeom g;
+    if (corr_geometry(g, B, C, H, W, pad, k, md, s1, s2)) return 0;
+    return corr_fast_supported(g) ? corr_fast_bwd_workspace(g) : 0;
+}
+
+extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
+                                int pad, int k, int md, int s1, int s2,
+                                void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(in1 && in2 && out, FLOWOPS_EINVAL, "corr_fwd: null pointer");
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(pad >= md + g.kr || k == 1, FLOWOPS_EUNSUPPORTED,
+                    "corr_fwd: pad_size < max_displacement + kernel_radius reads outside the padded scratch in the reference");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (corr_fast_supported(g)) return corr_fast_fwd_launch(in1, in2, out, g, workspace, workspace_bytes, st);
+    return corr_fwd_generic_launch(in1, in2, out, g, st);
+}
+
+extern "C" int flowops_corr_bwd(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                                int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(in1 && in2 && gout, FLOWOPS_EINVAL, "corr_bwd: null pointer");
+    FLOWOPS_REQUIRE(gin1 || gin2, FLOWOPS_EINVAL, "corr_bwd: both gradient outputs are null");
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    // the reference backward indexes gradInput with blockIdx * stride1 and writes out of bounds for
+    // stride1 > 1 (correlation_cuda_kernel.cu:164-165,238); it is never used that way.
+    FLOWOPS_REQUIRE(s1 == 1, FLOWOPS_EUNSUPPORTED, "corr_bwd: stride1 != 1 is not defined by the reference backward");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (corr_fast_supported(g)) return corr_fast_bwd_launch(in1, in2, gout, gin1, gin2, g, workspace, workspace_bytes, st);
+    return corr_bwd_generic_launch(in1, in2, gout, gin1, gin2, g, st);
+}

@@ -1,0 +1,32 @@
+// corr.cuh -- geometry shared by the Correlation kernels.
+#pragma once
+#include "common.cuh"
+
+namespace flowops {
+
+struct CorrGeom {
+    int B, C, H, W;          // inputs  [B,C,H,W]
+    int pad, k, md, s1, s2;  // reference parameters (correlation.py:43)
+    int kr, dr, D;           // kernel radius, displacement radius (md / s2), D = 2*dr + 1
+    int oC, oH, oW;          // output [B,oC,oH,oW], correlation_cuda.cc:19-34
+};
+
+// Fills g; returns 0 or a FLOWOPS_E* code (message set).
+int corr_geometry(CorrGeom &g, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2);
+
+// FlowNetC configuration the fast path is specialised for (FlowNetC.py:31):
+// k = 1, s1 = 1, s2 = 2, pad == md == 20  (D = 21, 441 output channels).
+bool corr_fast_supported(const CorrGeom &g);
+
+int corr_fwd_generic_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, cudaStream_t st);
+int corr_bwd_generic_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                            const CorrGeom &g, cudaStream_t st);
+
+size_t corr_fast_fwd_workspace(const CorrGeom &g);
+size_t corr_fast_bwd_workspace(const CorrGeom &g);
+int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g,
+                         void *ws, size_t ws_bytes, cudaStream_t st);
+int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                         const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace flowops

@@ -1,0 +1,362 @@
+// corr_fast.cu -- FlowNetC Correlation (pad 20, k 1, md 20, s1 1, s2 2 -> 21x21 = 441 channels)
+// for sm_100a: TMA-staged, register-tiled FP32-FMA kernel.
+//
+//   out[n, tj*21+ti, y, x] = (1/C) * sum_c f1[n,c,y,x] * f2pad[n,c, y + 2(tj-10), x + 2(ti-10)]
+//   (reference correlation_cuda_kernel.cu:74-147; tj = vertical = slow index)
+//
+// Structure
+//   stride2 = 2 means a pixel only ever meets pixels of its own (row, column) parity, so the
+//   problem splits into four independent "parity planes" in which the displacement is a dense
+//   +-10 x +-10 window.  A pre-pass (corr_planarize) de-interleaves both inputs into planes
+//   P[n][plane][c][H/2][W/2] in the caller-provided workspace (this replaces the reference's
+//   zero-padded NHWC scratch copies rInput1/rInput2 -- same size, no padding: TMA's out-of-bounds
+//   zero fill supplies it).  The main kernel then runs, per CTA, a tile of 3 plane-rows x 32 plane-
+//   columns x all 441 displacements:
+//     * per pipeline stage TMA brings 8 channels of the f1 tile (3 x 36) and of the displaced f2
+//       window (23 x 52) into shared memory, 4 stages deep, completion on mbarriers;
+//     * 252 threads each own a register tile of 8 pixels x 21 horizontal displacements for one
+//       (row, vertical displacement) pair: per channel 2 + 7 LDS.128 feed 168 FFMAs
+//       (sliding-window reuse of the f2 row inside registers);
+//     * a warp holds 32 (row, tj) pairs that touch only 13 distinct f2 rows and 3 f1 rows, so its
+//       shared-memory loads are mostly broadcasts (about 16 wavefronts per 168 FFMA issue slots);
+//     * the epilogue transposes the accumulators through shared memory so that every global store
+//       instruction writes one 32-pixel output row segment.
+//
+// Roofline: FP32-FMA pipe.  Algorithmic work 2*B*H*W*441*C FLOP (dense count, taps that fall in
+// the zero padding included -- the kernel does not skip them).
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is resolved at run time (no libcuda link)
+
+#include "corr.cuh"
+
+namespace flowops {
+
+constexpr int kD = 21;                       // displacements per axis
+constexpr int kR = 10;                       // displacement radius in plane coordinates
+constexpr int kTY = 3;                       // plane rows per CTA tile
+constexpr int kTX = 32;                      // plane columns per CTA tile
+constexpr int kPX = 8;                       // pixels per thread
+constexpr int kCK = 8;                       // channels per pipeline stage
+constexpr int kStages = 4;
+constexpr int kF2W = kTX + 2 * kR;           // 52
+constexpr int kF2H = kTY + 2 * kR;           // 23
+constexpr int kF1W = kTX + 4;                // 36: +4 columns so the 3 f1 rows sit in different banks
+constexpr int kF2Floats = kCK * kF2H * kF2W; // 9568
+constexpr int kF1Floats = kCK * kTY * kF1W;  // 864
+constexpr int kStageBytes = (kF2Floats + kF1Floats) * 4;   // 41728 (multiple of 128)
+constexpr int kPairs = kTY * kD;             // 63 (row, tj) pairs per tile column block
+constexpr int kEpiPitch = 36;                // floats per staged output row
+constexpr int kEpiGroup = 7;                 // tj values staged per epilogue pass
+constexpr int kEpiRows = kEpiGroup * kD * kTY;              // 441
+constexpr int kSmemBytes = kStages * kStageBytes;           // 166912
+static_assert(kEpiRows * kEpiPitch * 4 <= kSmemBytes, "epilogue staging must fit in the pipeline buffers");
+static_assert(kStageBytes % 128 == 0 && (kF2Floats * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+struct PlaneGeom {
+    int Hp, Wp, pitch;    // plane rows, valid plane columns (ceil), row pitch in floats (multiple of 4)
+    size_t plane_elems;   // Hp * pitch
+};
+
+static inline PlaneGeom plane_geom(const CorrGeom &g)
+{
+    PlaneGeom p;
+    p.Hp = (g.H + 1) / 2;
+    p.Wp = (g.W + 1) / 2;
+    p.pitch = (p.Wp + 3) & ~3;
+    p.plane_elems = (size_t)p.Hp * p.pitch;
+    return p;
+}
+
+bool corr_fast_supported(const CorrGeom &g)
+{
+    return g.k == 1 && g.s1 == 1 && g.s2 == 2 && g.pad == g.md && g.md == 2 * kR && g.D == kD;
+}
+
+size_t corr_fast_fwd_workspace(const CorrGeom &g)
+{
+    const PlaneGeom p = plane_geom(g);
+    return 2 * sizeof(float) * (size_t)g.B * 4 * g.C * p.plane_elems;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass: NCHW -> parity planes  P[n][py*2+px][c][Hp][pitch]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ in1, const float *__restrict__ in2,
+                                                      float *__restrict__ P1, float *__restrict__ P2,
+                                                      int B, int C, int H, int W, int Hp, int pitch, int vec_ok)
+{
+    const float *__restrict__ in = blockIdx.y ? in2 : in1;
+    float *__restrict__ P = blockIdx.y ? P2 : P1;
+    const int W4 = (W + 3) >> 2;
+    const size_t total = (size_t)B * C * H * W4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W4) * 4;
+        size_t r = idx / W4;
+        const int y = (int)(r % H); r /= H;
+        const int c = (int)(r % C);
+        const int n = (int)(r / C);
+        const float *src = in + (((size_t)n * C + c) * H + y) * W + x;
+        float4 v;
+        if (vec_ok) {
+            v = ldg_stream4(src);
+        } else {
+            v.x = src[0];
+            v.y = x + 1 < W ? src[1] : 0.f;
+            v.z = x + 2 < W ? src[2] : 0.f;
+            v.w = x + 3 < W ? src[3] : 0.f;
+        }
+        const int py = y & 1, yy = y >> 1, xx = x >> 1;
+        float *d0 = P + ((((size_t)n * 4 + py * 2 + 0) * C + c) * Hp + yy) * pitch + xx;
+        float *d1 = P + ((((size_t)n * 4 + py * 2 + 1) * C + c) * Hp + yy) * pitch + xx;
+        // pitch is a multiple of 4 and xx is even: 8-byte aligned pairs (padding columns get zeros)
+        *reinterpret_cast<float2 *>(d0) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2 *>(d1) = make_float2(v.y, v.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+              float *__restrict__ out, int C, int H, int W, int row_tiles, int x_tiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+
+    // tile decode: plane fastest so the two column parities of a row segment are written close in time
+    int bid = blockIdx.x;
+    const int plane = bid & 3; bid >>= 2;
+    const int xt = bid % x_tiles; bid /= x_tiles;
+    const int rt = bid % row_tiles;
+    const int n = bid / row_tiles;
+    const int py = plane >> 1, px = plane & 1;
+    const int y0 = rt * kTY, x0 = xt * kTX;          // plane coordinates of the tile origin
+    const int np = n * 4 + plane;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int xb = warp >> 1;                         // 8-pixel column block 0..3
+    const int pair = (warp & 1) * 32 + lane;          // 0..63, 63 is a spare lane
+    const bool live = pair < kPairs;
+    const int pp = live ? pair : kPairs - 1;
+    const int tj = pp / kTY, yi = pp - tj * kTY;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(full_bar);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_it = (C + kCK - 1) / kCK;
+    auto issue = [&](int it, int slot) {
+        const uint32_t bar = bar_base + 8 * slot;
+        const uint32_t dst = smem_base + slot * kStageBytes;
+        mbar_expect_tx(bar, kStageBytes);
+        tma_load_4d(dst, &tm2, x0 - kR, y0 - kR, it * kCK, np, bar);
+        tma_load_4d(dst + kF2Floats * 4, &tm1, x0, y0, it * kCK, np, bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages && s < n_it; ++s) issue(s, s);
+    }
+
+    float acc[kD][kPX];
+#pragma unroll
+    for (int i = 0; i < kD; ++i)
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) acc[i][k] = 0.f;
+
+    const int f2_off = (yi + tj) * kF2W + xb * kPX;
+    const int f1_off = yi * kF1W + xb * kPX;
+
+    for (int it = 0; it < n_it; ++it) {
+        const int slot = it % kStages;
+        mbar_wait(bar_base + 8 * slot, (it / kStages) & 1);
+        const float *f2s = reinterpret_cast<const float *>(smem + slot * kStageBytes) + f2_off;
+        const float *f1s = reinterpret_cast<const float *>(smem + slot * kStageBytes) + kF2Floats + f1_off;
+#pragma unroll 2
+        for (int ck = 0; ck < kCK; ++ck) {
+            float a[kPX], w[kPX + kD - 1];
+            const float4 *pa = reinterpret_cast<const float4 *>(f1s + ck * (kTY * kF1W));
+            const float4 *pw = reinterpret_cast<const float4 *>(f2s + ck * (kF2H * kF2W));
+#pragma unroll
+            for (int q = 0; q < kPX / 4; ++q) {
+                const float4 v = pa[q];
+                a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < (kPX + kD - 1) / 4; ++q) {
+                const float4 v = pw[q];
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kD; ++i)
+#pragma unroll
+                for (int k = 0; k < kPX; ++k) acc[i][k] = __fmaf_rn(a[k], w[i + k], acc[i][k]);
+        }
+        __syncthreads();                              // every warp is done with this slot
+        if (tid == 0 && it + kStages < n_it) issue(it + kStages, slot);
+    }
+
+    // ---- epilogue: registers -> shared (row-major 32-pixel segments) -> global ----
+    // (the last loop iteration ended with __syncthreads and no TMA is in flight)
+    float *stage = reinterpret_cast<float *>(smem);
+    const float nelems = (float)C;
+    const size_t hw = (size_t)H * W;
+    float *out_n = out + (size_t)n * (kD * kD) * hw;
+#pragma unroll 1
+    for (int grp = 0; grp < kD / kEpiGroup; ++grp) {
+        if (live && tj >= grp * kEpiGroup && tj < (grp + 1) * kEpiGroup) {
+            float *dst = stage + ((tj - grp * kEpiGroup) * kD * kTY + yi) * kEpiPitch + xb * kPX;
+#pragma unroll
+            for (int i = 0; i < kD; ++i) {
+                float4 lo, hi;
+                lo.x = __fdiv_rn(acc[i][0], nelems); lo.y = __fdiv_rn(acc[i][1], nelems);
+                lo.z = __fdiv_rn(acc[i][2], nelems); lo.w = __fdiv_rn(acc[i][3], nelems);
+                hi.x = __fdiv_rn(acc[i][4], nelems); hi.y = __fdiv_rn(acc[i][5], nelems);
+                hi.z = __fdiv_rn(acc[i][6], nelems); hi.w = __fdiv_rn(acc[i][7], nelems);
+                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch)) = lo;
+                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch) + 4) = hi;
+            }
+        }
+        __syncthreads();
+        const int x = 2 * (x0 + lane) + px;
+        for (int row = warp; row < kEpiRows; row += 8) {
+            const int tjl = row / (kD * kTY);
+            const int rem = row - tjl * (kD * kTY);
+            const int ti = rem / kTY, ry = rem - ti * kTY;
+            const int y = 2 * (y0 + ry) + py;
+            if (y < H && x < W) {
+                const int tc = (grp * kEpiGroup + tjl) * kD + ti;
+                out_n[(size_t)tc * hw + (size_t)y * W + x] = stage[row * kEpiPitch + lane];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, const PlaneGeom &p, int box_w, int box_h)
+{
+    EncodeTiledFn enc = get_encoder();
+    FLOWOPS_REQUIRE(enc, FLOWOPS_EUNSUPPORTED, "corr: cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)p.pitch, (cuuint64_t)p.Hp, (cuuint64_t)g.C, (cuuint64_t)g.B * 4};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.pitch * 4, (cuuint64_t)p.plane_elems * 4,
+                                   (cuuint64_t)p.plane_elems * 4 * g.C};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)kCK, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLOWOPS_REQUIRE(r == CUDA_SUCCESS, FLOWOPS_EINVAL, "corr: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g,
+                         void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const PlaneGeom p = plane_geom(g);
+    const size_t need = corr_fast_fwd_workspace(g);
+    FLOWOPS_REQUIRE(ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0, FLOWOPS_EWORKSPACE,
+                    "corr_fwd: workspace of %zu bytes (256-byte aligned) required, got %zu", need, ws_bytes);
+    float *P1 = reinterpret_cast<float *>(ws);
+    float *P2 = P1 + need / (2 * sizeof(float));
+
+    // planes have zero padding only when W is not a multiple of 8 or H is odd
+    if ((g.W & 7) || (g.H & 1)) {
+        cudaError_t e = cudaMemsetAsync(ws, 0, need, st);
+        if (e != cudaSuccess) { set_error("corr_fwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    {
+        const int vec_ok = (g.W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
+        size_t blocks = (total + 255) / 256;
+        if (blocks > (size_t)kNumSMs * 8 * 8) blocks = (size_t)kNumSMs * 8 * 8;
+        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch, vec_ok);
+        const int rc = check_launch("corr_planarize");
+        if (rc) return rc;
+    }
+
+    CUtensorMap tm1, tm2;
+    int rc = make_plane_map(&tm1, P1, g, p, kF1W, kTY);
+    if (rc) return rc;
+    rc = make_plane_map(&tm2, P2, g, p, kF2W, kF2H);
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    const int row_tiles = (p.Hp + kTY - 1) / kTY, x_tiles = (p.Wp + kTX - 1) / kTX;
+    const size_t grid = (size_t)g.B * row_tiles * x_tiles * 4;
+    FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
+    corr_fwd_fast<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
+    return check_launch("corr_fwd_fast");
+}
+
+// The backward still runs the generic gather kernels (corr_generic.cu); a tiled version is the next
+// step for this file.
+size_t corr_fast_bwd_workspace(const CorrGeom &) { return 0; }
+
+int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                         const CorrGeom &g, void *, size_t, cudaStream_t st)
+{
+    return corr_bwd_generic_launch(in1, in2, gout, gin1, gin2, g, st);
+}
+
+}  // namespace flowops

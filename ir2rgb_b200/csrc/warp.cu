@@ -1,0 +1,399 @@
+// warp.cu -- bilinear flow warp, forward and backward, for sm_100a.
+//
+// One kernel family serves both warps on the hot path:
+//   mode RESAMPLE2D : FlowNet2's Resample2d (reference resample2d_package/resample2d_kernel.cu:16-190)
+//   mode GRIDSAMPLE : vid2vid's `resample` (reference models/networks.py:15-28,89-100 ==
+//                     models/base_model.py:123-136), i.e. get_grid + flow normalisation +
+//                     F.grid_sample(bilinear, border, align_corners=False), without ever
+//                     materialising the normalised grid.
+//
+// Design (HBM-bound op; algorithmic bytes per pixel: fwd 4*(2C+2), bwd 4*(3C+4) + gimg memset):
+//   * one thread per pixel handles ALL channels: the flow is read once (coalesced, L1-bypassing),
+//     the bilinear weights are computed once, the 4*C corner gathers go through L1 (neighbouring
+//     lanes hit the same 128-byte lines), the C stores are coalesced and L1-bypassing;
+//   * the reference runs one thread per output ELEMENT and re-reads the flow / recomputes the
+//     weights C times;
+//   * backward: the flow gradient is a gather (deterministic); the image gradient is a scatter whose
+//     atomics are aggregated inside the warp before they are issued -- lane i's right-hand corners
+//     usually coincide with lane i+1's left-hand corners, and clamped corners coincide within a
+//     lane -- so a smooth flow costs ~2 RED.ADD per element instead of the reference's 4.
+//
+// Arithmetic: RESAMPLE2D forward reproduces the reference's mixed precision exactly (three weight
+// products in fp64, the fourth in fp32, fp32 adds in TL,TR,BL,BR order) and is bit-identical to it.
+// GRIDSAMPLE reproduces ATen's fp32 op chain (GridSampler.cuh: unnormalize -> clip -> floor ->
+// weights as differences -> nw,ne,sw,se FFMA chain).
+#include "common.cuh"
+
+namespace flowops {
+
+struct Corners {
+    int o_tl, o_tr, o_bl, o_br;   // offsets inside one H*W plane
+};
+
+// ---------------------------------------------------------------------------------------------
+// coordinate conventions
+// ---------------------------------------------------------------------------------------------
+
+// resample2d_kernel.cu:40-51
+__device__ __forceinline__ void r2d_coords(int x, int y, float dx, float dy, int H, int W,
+                                           float &xf, float &yf, Corners &k)
+{
+    xf = __fadd_rn((float)x, dx);
+    yf = __fadd_rn((float)y, dy);
+    const float fx = floorf(xf), fy = floorf(yf);
+    const int xL = max(min((int)fx, W - 1), 0);
+    const int xR = max(min((int)(__fadd_rn(fx, 1.f)), W - 1), 0);
+    const int yT = max(min((int)fy, H - 1), 0);
+    const int yB = max(min((int)(__fadd_rn(fy, 1.f)), H - 1), 0);
+    k.o_tl = yT * W + xL; k.o_tr = yT * W + xR; k.o_bl = yB * W + xL; k.o_br = yB * W + xR;
+}
+
+// models/networks.py:97-98 + ATen grid_sampler_compute_source_index (align_corners=False, border)
+struct GsCoord {
+    float ix, iy;        // clipped source coordinates
+    int ix_nw, iy_nw;    // floor
+    float gmx, gmy;      // d(ix)/d(flow_x), d(iy)/d(flow_y) incl. the clip mask (backward only)
+};
+__device__ __forceinline__ GsCoord gs_coords(int x, int y, float dx, float dy, int H, int W,
+                                             const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                             float invx, float invy)
+{
+    GsCoord g;
+    const float gx = __fadd_rn(__ldg(lin_x + x), __fmul_rn(dx, invx));
+    const float gy = __fadd_rn(__ldg(lin_y + y), __fmul_rn(dy, invy));
+    // ((coord + 1) * size - 1) / 2 ; nvcc contracts the multiply-subtract in ATen's build
+    float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), (float)W, -1.f), 0.5f);
+    float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), (float)H, -1.f), 0.5f);
+    // clip_coordinates_set_grad: gradient is zero at and beyond both borders
+    g.gmx = (ix <= 0.f || ix >= (float)(W - 1)) ? 0.f : 1.f;
+    g.gmy = (iy <= 0.f || iy >= (float)(H - 1)) ? 0.f : 1.f;
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+    g.ix = ix; g.iy = iy;
+    g.ix_nw = (int)floorf(ix);
+    g.iy_nw = (int)floorf(iy);
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int CT>
+__global__ void __launch_bounds__(256) warp_fwd_kernel(const float *__restrict__ img, const float *__restrict__ flow,
+                                                       float *__restrict__ out, int B, int C, int H, int W,
+                                                       const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                                       float invx, float invy)
+{
+    const int c_n = CT > 0 ? CT : C;
+    const size_t hw = (size_t)H * W;
+    const size_t total = (size_t)B * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw;
+        const int p = (int)(i - b * hw);
+        const int y = p / W, x = p - y * W;
+        const float dx = ldg_stream(flow + (b * 2) * hw + p);
+        const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
+        const float *src = img + b * c_n * hw;
+        float *dst = out + b * c_n * hw + p;
+
+        if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
+            float xf, yf; Corners k;
+            r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
+            const float alpha = __fsub_rn(xf, floorf(xf));
+            const float beta = __fsub_rn(yf, floorf(yf));
+            // resample2d_kernel.cu:55-58: `1.` literals promote the first three products to fp64
+            const double wa = 1. - (double)alpha, wb = 1. - (double)beta;
+            const double w_tl = wa * wb, w_tr = (double)alpha * wb, w_bl = wa * (double)beta;
+            const float w_br = __fmul_rn(alpha, beta);
+#pragma unroll
+            for (int c = 0; c < c_n; ++c) {
+                const float *pl = src + (size_t)c * hw;
+                const float tl = __ldg(pl + k.o_tl), tr = __ldg(pl + k.o_tr);
+                const float bl = __ldg(pl + k.o_bl), br = __ldg(pl + k.o_br);
+                float val = 0.0f;
+                val = __fadd_rn(val, (float)(w_tl * (double)tl));
+                val = __fadd_rn(val, (float)(w_tr * (double)tr));
+                val = __fadd_rn(val, (float)(w_bl * (double)bl));
+                val = __fmaf_rn(w_br, br, val);
+                stg_stream(dst + (size_t)c * hw, val);
+            }
+        } else {
+            const GsCoord g = gs_coords(x, y, dx, dy, H, W, lin_x, lin_y, invx, invy);
+            const int ix_nw = g.ix_nw, iy_nw = g.iy_nw;
+            const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
+            const float nw = __fmul_rn(__fsub_rn((float)ix_se, g.ix), __fsub_rn((float)iy_se, g.iy));
+            const float ne = __fmul_rn(__fsub_rn(g.ix, (float)ix_nw), __fsub_rn((float)iy_se, g.iy));
+            const float sw = __fmul_rn(__fsub_rn((float)ix_se, g.ix), __fsub_rn(g.iy, (float)iy_nw));
+            const float se = __fmul_rn(__fsub_rn(g.ix, (float)ix_nw), __fsub_rn(g.iy, (float)iy_nw));
+            // after the border clip (ix_nw, iy_nw) is always inside; the +1 neighbours may be one past
+            const bool in_e = ix_se < W, in_s = iy_se < H;
+            const int o_nw = iy_nw * W + ix_nw;
+#pragma unroll
+            for (int c = 0; c < c_n; ++c) {
+                const float *pl = src + (size_t)c * hw + o_nw;
+                float acc = 0.f;
+                acc = __fmaf_rn(__ldg(pl), nw, acc);
+                if (in_e) acc = __fmaf_rn(__ldg(pl + 1), ne, acc);
+                if (in_s) acc = __fmaf_rn(__ldg(pl + W), sw, acc);
+                if (in_e && in_s) acc = __fmaf_rn(__ldg(pl + W + 1), se, acc);
+                stg_stream(dst + (size_t)c * hw, acc);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+
+// Warp-aggregated scatter of the four corner contributions of one channel.
+// Lanes hold horizontally adjacent pixels.  `m` holds the per-pixel merge plan computed once
+// (addresses are the same for every channel).
+struct MergePlan {
+    bool take_tr_from_left;   // lane-1's TR lands on my TL  -> I add it to my TL
+    bool take_br_from_left;   // lane-1's BR lands on my BL
+    bool give_tr_to_right;    // my TR is taken by lane+1    -> I do not issue it
+    bool give_br_to_right;
+    bool fold_x;              // xL == xR : TL/TR (and BL/BR) are the same address
+    bool fold_y;              // yT == yB
+};
+
+__device__ __forceinline__ MergePlan make_plan(const Corners &k, bool valid, size_t plane_key)
+{
+    // keys compare plane (batch) and in-plane offset; invalid lanes never match
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long base = valid ? (long long)plane_key : -(long long)(lane + 2);
+    const long long k_tl = valid ? base + k.o_tl : -1 - lane * 4;
+    const long long k_tr = valid ? base + k.o_tr : -2 - lane * 4;
+    const long long k_bl = valid ? base + k.o_bl : -3 - lane * 4;
+    const long long k_br = valid ? base + k.o_br : -4 - lane * 4;
+    const long long left_tr = __shfl_up_sync(full, k_tr, 1);
+    const long long left_br = __shfl_up_sync(full, k_br, 1);
+    const long long right_tl = __shfl_down_sync(full, k_tl, 1);
+    const long long right_bl = __shfl_down_sync(full, k_bl, 1);
+    MergePlan m;
+    m.fold_x = (k.o_tl == k.o_tr);
+    m.fold_y = (k.o_tl == k.o_bl);
+    // only merge the regular pattern (both rows shift together); anything else goes out unmerged
+    const bool l_ok = valid && lane > 0 && left_tr == k_tl && left_br == k_bl;
+    const bool r_ok = valid && lane < 31 && right_tl == k_tr && right_bl == k_br;
+    m.take_tr_from_left = l_ok; m.take_br_from_left = l_ok;
+    m.give_tr_to_right = r_ok;  m.give_br_to_right = r_ok;
+    return m;
+}
+
+__device__ __forceinline__ void scatter4(float *__restrict__ plane, const Corners &k, const MergePlan &m,
+                                         bool valid, float v_tl, float v_tr, float v_bl, float v_br)
+{
+    const unsigned full = 0xffffffffu;
+    if (m.fold_x) { v_tl += v_tr; v_bl += v_br; v_tr = 0.f; v_br = 0.f; }
+    if (m.fold_y) { v_tl += v_bl; v_tr += v_br; v_bl = 0.f; v_br = 0.f; }
+    const float in_tr = __shfl_up_sync(full, v_tr, 1);
+    const float in_br = __shfl_up_sync(full, v_br, 1);
+    if (m.take_tr_from_left) v_tl += in_tr;
+    if (m.take_br_from_left) v_bl += in_br;
+    if (!valid) return;
+    red_add(plane + k.o_tl, v_tl);
+    if (!m.fold_y) red_add(plane + k.o_bl, v_bl);
+    if (!m.fold_x && !m.give_tr_to_right) {
+        red_add(plane + k.o_tr, v_tr);
+        if (!m.fold_y) red_add(plane + k.o_br, v_br);
+    }
+}
+
+template <int MODE, int CT, bool NEED_IMG, bool NEED_FLOW>
+__global__ void __launch_bounds__(256) warp_bwd_kernel(const float *__restrict__ img, const float *__restrict__ flow,
+                                                       const float *__restrict__ gout, float *__restrict__ gimg,
+                                                       float *__restrict__ gflow, int B, int C, int H, int W,
+                                                       const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                                       float invx, float invy, float mulx, float muly)
+{
+    const int c_n = CT > 0 ? CT : C;
+    const size_t hw = (size_t)H * W;
+    const size_t total = (size_t)B * hw;
+    const size_t rounded = (total + 31) & ~(size_t)31;   // whole warps stay in the loop (shuffles)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rounded;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const bool valid = i < total;
+        const size_t ii = valid ? i : total - 1;
+        const size_t b = ii / hw;
+        const int p = (int)(ii - b * hw);
+        const int y = p / W, x = p - y * W;
+        const float dx = ldg_stream(flow + (b * 2) * hw + p);
+        const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
+        const float *src = img + b * c_n * hw;
+        const float *go = gout + b * c_n * hw + p;
+        float *gi = NEED_IMG ? gimg + b * c_n * hw : nullptr;
+
+        Corners k;
+        float w_tl, w_tr, w_bl, w_br;      // image-gradient weights
+        float gam_x = 0.f, gam_y = 0.f;    // RESAMPLE2D flow-gradient weights
+        float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;   // GRIDSAMPLE: (ix_se-ix),(iy_se-iy),(ix-ix_nw),(iy-iy_nw)
+        float gmx = 0.f, gmy = 0.f;
+        if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
+            float xf, yf;
+            r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
+            // resample2d_kernel.cu:97-98: truncation, not floor, in the image-gradient kernel
+            const float alpha = __fsub_rn(xf, (float)(int)xf);
+            const float beta = __fsub_rn(yf, (float)(int)yf);
+            w_tl = (1 - alpha) * (1 - beta); w_tr = alpha * (1 - beta);
+            w_bl = (1 - alpha) * beta;       w_br = alpha * beta;
+            gam_x = 1 - __fsub_rn(xf, floorf(xf));     // :160 (used for d/d dy)
+            gam_y = 1 - __fsub_rn(yf, floorf(yf));     // :172 (used for d/d dx)
+        } else {
+            const GsCoord g = gs_coords(x, y, dx, dy, H, W, lin_x, lin_y, invx, invy);
+            const int xe = min(g.ix_nw + 1, W - 1), ys = min(g.iy_nw + 1, H - 1);   // weight is 0 when clamped
+            k.o_tl = g.iy_nw * W + g.ix_nw; k.o_tr = g.iy_nw * W + xe;
+            k.o_bl = ys * W + g.ix_nw;      k.o_br = ys * W + xe;
+            ax = (float)(g.ix_nw + 1) - g.ix; ay = (float)(g.iy_nw + 1) - g.iy;
+            bx = g.ix - (float)g.ix_nw;       by = g.iy - (float)g.iy_nw;
+            w_tl = ax * ay; w_tr = bx * ay; w_bl = ax * by; w_br = bx * by;
+            gmx = g.gmx; gmy = g.gmy;
+        }
+
+        MergePlan m;
+        if (NEED_IMG) m = make_plan(k, valid, b * (size_t)c_n * hw);
+
+        float gfx = 0.f, gfy = 0.f;
+#pragma unroll
+        for (int c = 0; c < c_n; ++c) {
+            const float g = valid ? ldg_stream(go + (size_t)c * hw) : 0.f;
+            if (NEED_FLOW) {
+                const float *pl = src + (size_t)c * hw;
+                const float tl = __ldg(pl + k.o_tl), tr = __ldg(pl + k.o_tr);
+                const float bl = __ldg(pl + k.o_bl), br = __ldg(pl + k.o_br);
+                if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
+                    // resample2d_kernel.cu:159-184, same operation order
+                    gfy = __fmaf_rn(gam_x * g, bl, gfy);
+                    gfy = __fmaf_rn(-(gam_x * g), tl, gfy);
+                    gfy = __fmaf_rn((1 - gam_x) * g, br, gfy);
+                    gfy = __fmaf_rn(-((1 - gam_x) * g), tr, gfy);
+                    gfx = __fmaf_rn(gam_y * g, tr, gfx);
+                    gfx = __fmaf_rn(-(gam_y * g), tl, gfx);
+                    gfx = __fmaf_rn((1 - gam_y) * g, br, gfx);
+                    gfx = __fmaf_rn(-((1 - gam_y) * g), bl, gfx);
+                } else {
+                    // ATen grid_sampler_2d_backward_kernel, bilinear branch
+                    gfx -= tl * ay * g; gfy -= tl * ax * g;
+                    gfx += tr * ay * g; gfy -= tr * bx * g;
+                    gfx -= bl * by * g; gfy += bl * ax * g;
+                    gfx += br * by * g; gfy += br * bx * g;
+                }
+            }
+            if (NEED_IMG)
+                scatter4(gi + (size_t)c * hw, k, m, valid, w_tl * g, w_tr * g, w_bl * g, w_br * g);
+        }
+        if (NEED_FLOW && valid) {
+            if (MODE == FLOWOPS_WARP_GRIDSAMPLE) { gfx *= gmx * mulx; gfy *= gmy * muly; }
+            stg_stream(gflow + (b * 2) * hw + p, gfx);
+            stg_stream(gflow + (b * 2 + 1) * hw + p, gfy);
+        }
+    }
+}
+
+static inline unsigned warp_grid(size_t total)
+{
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+template <int MODE>
+static int launch_fwd(const float *img, const float *flow, float *out, int B, int C, int H, int W,
+                      const float *lx, const float *ly, float invx, float invy, cudaStream_t st)
+{
+    const unsigned grid = warp_grid((size_t)B * H * W);
+    if (C == 3) warp_fwd_kernel<MODE, 3><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else if (C == 2) warp_fwd_kernel<MODE, 2><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else if (C == 1) warp_fwd_kernel<MODE, 1><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else warp_fwd_kernel<MODE, 0><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    return check_launch("warp_fwd");
+}
+
+template <int MODE, bool NI, bool NF>
+static void launch_bwd_c(const float *img, const float *flow, const float *gout, float *gimg, float *gflow,
+                         int B, int C, int H, int W, const float *lx, const float *ly,
+                         float invx, float invy, float mulx, float muly, cudaStream_t st)
+{
+    const unsigned grid = warp_grid((size_t)B * H * W);
+    if (C == 3) warp_bwd_kernel<MODE, 3, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
+    else if (C == 1) warp_bwd_kernel<MODE, 1, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
+    else warp_bwd_kernel<MODE, 0, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
+}
+
+template <int MODE>
+static int launch_bwd(const float *img, const float *flow, const float *gout, float *gimg, float *gflow,
+                      int B, int C, int H, int W, const float *lx, const float *ly,
+                      float invx, float invy, float mulx, float muly, cudaStream_t st)
+{
+    if (gimg) {
+        cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, st);
+        if (e != cudaSuccess) { set_error("warp_bwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    if (gimg && gflow) launch_bwd_c<MODE, true, true>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
+    else if (gimg) launch_bwd_c<MODE, true, false>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
+    else launch_bwd_c<MODE, false, true>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
+    return check_launch("warp_bwd");
+}
+
+// fp32 constants of the models/networks.py:97 normalisation: flow / ((W-1)/2) runs on CUDA as a
+// multiply by the fp32 reciprocal of the fp32 scalar.
+static inline void gs_scales(int H, int W, float &invx, float &invy, float &mulx, float &muly)
+{
+    const float sx = (float)((W - 1.0) / 2.0), sy = (float)((H - 1.0) / 2.0);
+    invx = 1.0f / sx; invy = 1.0f / sy;
+    // d(ix)/d(flow_x) = (W/2) * invx  (unnormalize gradient times the reciprocal above)
+    mulx = ((float)W * 0.5f) * invx;
+    muly = ((float)H * 0.5f) * invy;
+}
+
+}  // namespace flowops
+
+using namespace flowops;
+
+static int warp_check(const char *who, const void *img, const void *flow, int B, int C, int H, int W, int mode,
+                      const float *lin_x, const float *lin_y)
+{
+    FLOWOPS_REQUIRE(img && flow, FLOWOPS_EINVAL, "%s: null pointer", who);
+    FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "%s: bad shape %dx%dx%dx%d", who, B, C, H, W);
+    FLOWOPS_REQUIRE((size_t)C * H * W < (1ull << 31), FLOWOPS_EUNSUPPORTED, "%s: C*H*W exceeds int32 indexing", who);
+    FLOWOPS_REQUIRE(mode == FLOWOPS_WARP_RESAMPLE2D || mode == FLOWOPS_WARP_GRIDSAMPLE, FLOWOPS_EINVAL, "%s: unknown mode %d", who, mode);
+    if (mode == FLOWOPS_WARP_GRIDSAMPLE) {
+        FLOWOPS_REQUIRE(lin_x && lin_y, FLOWOPS_EINVAL, "%s: GRIDSAMPLE mode needs the linspace tables", who);
+        FLOWOPS_REQUIRE(H > 1 && W > 1, FLOWOPS_EUNSUPPORTED, "%s: GRIDSAMPLE mode needs H, W > 1", who);
+    }
+    return 0;
+}
+
+extern "C" int flowops_warp_fwd(const float *img, const float *flow, float *out, int B, int C, int H, int W,
+                                int mode, const float *lin_x, const float *lin_y, void *stream)
+{
+    int rc = warp_check("warp_fwd", img, flow, B, C, H, W, mode, lin_x, lin_y);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(out, FLOWOPS_EINVAL, "warp_fwd: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == FLOWOPS_WARP_RESAMPLE2D)
+        return launch_fwd<FLOWOPS_WARP_RESAMPLE2D>(img, flow, out, B, C, H, W, nullptr, nullptr, 0.f, 0.f, st);
+    float invx, invy, mulx, muly;
+    gs_scales(H, W, invx, invy, mulx, muly);
+    return launch_fwd<FLOWOPS_WARP_GRIDSAMPLE>(img, flow, out, B, C, H, W, lin_x, lin_y, invx, invy, st);
+}
+
+extern "C" int flowops_warp_bwd(const float *img, const float *flow, const float *gout, float *gimg, float *gflow,
+                                int B, int C, int H, int W, int mode,
+                                const float *lin_x, const float *lin_y, void *stream)
+{
+    int rc = warp_check("warp_bwd", img, flow, B, C, H, W, mode, lin_x, lin_y);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(gout, FLOWOPS_EINVAL, "warp_bwd: null grad_output");
+    FLOWOPS_REQUIRE(gimg || gflow, FLOWOPS_EINVAL, "warp_bwd: both gradient outputs are null");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == FLOWOPS_WARP_RESAMPLE2D)
+        return launch_bwd<FLOWOPS_WARP_RESAMPLE2D>(img, flow, gout, gimg, gflow, B, C, H, W, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
+    float invx, invy, mulx, muly;
+    gs_scales(H, W, invx, invy, mulx, muly);
+    return launch_bwd<FLOWOPS_WARP_GRIDSAMPLE>(img, flow, gout, gimg, gflow, B, C, H, W, lin_x, lin_y, invx, invy, mulx, muly, st);
+}

@@ -1,0 +1,189 @@
+"""Tensor-level calls into libflowops.so: argument checking, output allocation, stream and device
+handling.  PyTorch is plumbing here (device memory, streams); all arithmetic happens in the library.
+
+Every function requires CUDA fp32 tensors and raises otherwise -- by design there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import WARP_GRIDSAMPLE, WARP_RESAMPLE2D, check
+
+
+def _require(t, name, ndim=4):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the flow hot path has no CPU implementation "
+                           "(got device %s)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (the reference ops are fp32-only on this path; cast like "
+                        "FlowNetC.py:86-87 does), got %s" % (name, t.dtype))
+    if t.dim() != ndim:
+        raise ValueError("%s must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# ChannelNorm
+# ---------------------------------------------------------------------------------------------
+def channelnorm_forward(x):
+    x = _require(x, "input1").contiguous()
+    B, C, H, W = x.shape
+    with torch.cuda.device_of(x):
+        y = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+        if x.numel():
+            check(_lib.load().flowops_cnorm_fwd(_p(x), _p(y), B, C, H, W, _stream()), "cnorm_fwd")
+    return y
+
+
+def channelnorm_backward(x, y, gy):
+    x = _require(x, "input1").contiguous()
+    y = _require(y, "output").contiguous()
+    gy = _require(gy, "grad_output").contiguous()
+    B, C, H, W = x.shape
+    with torch.cuda.device_of(x):
+        gx = torch.empty_like(x)
+        if x.numel():
+            check(_lib.load().flowops_cnorm_bwd(_p(x), _p(y), _p(gy), _p(gx), B, C, H, W, _stream()), "cnorm_bwd")
+    return gx
+
+
+# ---------------------------------------------------------------------------------------------
+# warps
+# ---------------------------------------------------------------------------------------------
+_LIN_CACHE = {}
+
+
+def _lin_tables(H, W, device):
+    """torch.linspace(-1, 1, n) on the host in fp32, moved to the device: exactly the values
+    get_grid produces (reference models/networks.py:15-28).  Cached per (H, W, device) -- the
+    counterpart of the reference's `self.grid` cache (networks.py:95-96), 4*(H+W) bytes instead
+    of a [b,2,h,w] tensor."""
+    key = (H, W, device)
+    t = _LIN_CACHE.get(key)
+    if t is None:
+        t = (torch.linspace(-1.0, 1.0, W).to(device), torch.linspace(-1.0, 1.0, H).to(device))
+        _LIN_CACHE[key] = t
+    return t
+
+
+def _warp_args(img, flow, mode):
+    img = _require(img, "image")
+    flow = _require(flow, "flow")
+    B, C, H, W = img.shape
+    if flow.shape != (B, 2, H, W):
+        raise ValueError("flow must be [B,2,H,W] matching the image %s, got %s" % (tuple(img.shape), tuple(flow.shape)))
+    if flow.device != img.device:
+        raise RuntimeError("image and flow must be on the same device")
+    if mode == WARP_GRIDSAMPLE:
+        lx, ly = _lin_tables(H, W, img.device)
+    else:
+        lx = ly = None
+    return img.contiguous(), flow.contiguous(), B, C, H, W, lx, ly
+
+
+def warp_forward(img, flow, mode=WARP_RESAMPLE2D):
+    img, flow, B, C, H, W, lx, ly = _warp_args(img, flow, mode)
+    with torch.cuda.device_of(img):
+        out = torch.empty_like(img)
+        if img.numel():
+            check(_lib.load().flowops_warp_fwd(_p(img), _p(flow), _p(out), B, C, H, W, mode, _p(lx), _p(ly), _stream()),
+                  "warp_fwd")
+    return out
+
+
+def warp_backward(img, flow, gout, need_img=True, need_flow=True, mode=WARP_RESAMPLE2D):
+    img, flow, B, C, H, W, lx, ly = _warp_args(img, flow, mode)
+    gout = _require(gout, "grad_output").contiguous()
+    if gout.shape != img.shape:
+        raise ValueError("grad_output shape %s does not match the image %s" % (tuple(gout.shape), tuple(img.shape)))
+    with torch.cuda.device_of(img):
+        gimg = torch.empty_like(img) if need_img else None
+        gflow = torch.empty_like(flow) if need_flow else None
+        if img.numel() and (need_img or need_flow):
+            check(_lib.load().flowops_warp_bwd(_p(img), _p(flow), _p(gout), _p(gimg), _p(gflow), B, C, H, W, mode,
+                                               _p(lx), _p(ly), _stream()), "warp_bwd")
+    return gimg, gflow
+
+
+# ---------------------------------------------------------------------------------------------
+# Correlation
+# ---------------------------------------------------------------------------------------------
+def correlation_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
+    oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(_lib.load().flowops_corr_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                             ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)), "corr_out_shape")
+    return oc.value, oh.value, ow.value
+
+
+def _workspace(nbytes, device):
+    # torch.empty on CUDA is 512-byte aligned; the library asks for 256
+    return torch.empty((max(nbytes, 1),), device=device, dtype=torch.uint8)
+
+
+def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
+    in1 = _require(in1, "input1").contiguous()
+    in2 = _require(in2, "input2").contiguous()
+    if in1.shape != in2.shape or in1.device != in2.device:
+        raise ValueError("input1 %s and input2 %s must have the same shape and device" % (tuple(in1.shape), tuple(in2.shape)))
+    B, C, H, W = in1.shape
+    params = (int(pad_size), int(kernel_size), int(max_displacement), int(stride1), int(stride2))
+    lib = _lib.load()
+    oc, oh, ow = correlation_out_shape(H, W, *params)
+    with torch.cuda.device_of(in1):
+        out = torch.empty((B, oc, oh, ow), device=in1.device, dtype=torch.float32)
+        nbytes = lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *params)
+        ws = _workspace(nbytes, in1.device)       # the role of rbot1/rbot2 (correlation.py:16-17)
+        if in1.numel():
+            check(lib.flowops_corr_fwd(_p(in1), _p(in2), _p(out), B, C, H, W, *params, _p(ws), nbytes, _stream()), "corr_fwd")
+    return out
+
+
+def correlation_backward(in1, in2, gout, pad_size, kernel_size, max_displacement, stride1, stride2,
+                         need1=True, need2=True):
+    in1 = _require(in1, "input1").contiguous()
+    in2 = _require(in2, "input2").contiguous()
+    gout = _require(gout, "grad_output").contiguous()
+    B, C, H, W = in1.shape
+    params = (int(pad_size), int(kernel_size), int(max_displacement), int(stride1), int(stride2))
+    lib = _lib.load()
+    if tuple(gout.shape) != (B,) + correlation_out_shape(H, W, *params):
+        raise ValueError("grad_output has shape %s" % (tuple(gout.shape),))
+    with torch.cuda.device_of(in1):
+        g1 = torch.empty_like(in1) if need1 else None
+        g2 = torch.empty_like(in2) if need2 else None
+        nbytes = lib.flowops_corr_bwd_workspace_bytes(B, C, H, W, *params)
+        ws = _workspace(nbytes, in1.device)
+        if in1.numel() and (need1 or need2):
+            check(lib.flowops_corr_bwd(_p(in1), _p(in2), _p(gout), _p(g1), _p(g2), B, C, H, W, *params,
+                                       _p(ws), nbytes, _stream()), "corr_bwd")
+    return g1, g2
+
+
+# ---------------------------------------------------------------------------------------------
+# measurement helper
+# ---------------------------------------------------------------------------------------------
+def ffma_peak_tflops(iters=4096, reps=5):
+    """Measured FP32-FMA pipe throughput of this GPU (TFLOP/s): the Correlation roofline denominator."""
+    lib = _lib.load()
+    sink = torch.zeros(4, device="cuda")
+    flops = ctypes.c_double()
+    best = 0.0
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.flowops_bench_ffma(_p(sink), iters, ctypes.byref(flops), _stream()), "bench_ffma")
+        e1.record()
+        e1.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

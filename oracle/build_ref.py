@@ -1,0 +1,72 @@
+"""Build the reference's own CUDA extensions for sm_100 into oracle/_ref/ (git-ignored).
+
+Test infrastructure only: the resulting modules are the GPU-side oracle (and the reference arm of
+bench.py).  Sources are compiled from where they lie in /root/reference -- they are staged into a
+throw-away directory under /tmp because two mechanical patches are needed:
+
+  1. the gencode list (sm_37 ... sm_70 in */setup.py is rejected by CUDA 12) is replaced by
+     -gencode arch=compute_100,code=sm_100 (passed here on the command line; setup.py is not used);
+  2. `.type()` -> `.scalar_type()` inside the AT_DISPATCH_* calls (removed API in torch >= 2.x).
+
+Only the built .so files are written into the repo tree (oracle/_ref/), never the sources.
+Run:  python oracle/build_ref.py          (needs /root/reference; ~2-5 min on 8 cores, no GPU needed)
+"""
+import glob
+import os
+import re
+import shutil
+import sys
+import tempfile
+
+REF_ROOT = os.environ.get("IR2RGB_REFERENCE", "/root/reference")
+NETS = os.path.join(REF_ROOT, "models", "flownet2_pytorch", "networks")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+EXTS = {
+    "correlation_cuda": ("correlation_package", ["correlation_cuda.cc", "correlation_cuda_kernel.cu"]),
+    "resample2d_cuda": ("resample2d_package", ["resample2d_cuda.cc", "resample2d_kernel.cu"]),
+    "channelnorm_cuda": ("channelnorm_package", ["channelnorm_cuda.cc", "channelnorm_kernel.cu"]),
+}
+
+
+def available():
+    return os.path.isdir(NETS)
+
+
+def built():
+    return all(glob.glob(os.path.join(OUT, name + "*.so")) for name in EXTS)
+
+
+def build(force=False, verbose=False):
+    if not available():
+        raise RuntimeError("reference sources not found under %s" % NETS)
+    if built() and not force:
+        return OUT
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
+    from torch.utils.cpp_extension import load
+    os.makedirs(OUT, exist_ok=True)
+    for name, (pkg, sources) in EXTS.items():
+        stage = tempfile.mkdtemp(prefix="ir2rgb_ref_%s_" % name)
+        for fn in os.listdir(os.path.join(NETS, pkg)):
+            if fn.endswith((".cc", ".cu", ".cuh", ".h")):
+                with open(os.path.join(NETS, pkg, fn)) as f:
+                    text = f.read()
+                text = re.sub(r"\.type\(\),", ".scalar_type(),", text)       # patch 2
+                with open(os.path.join(stage, fn), "w") as f:
+                    f.write(text)
+        build_dir = os.path.join(stage, "build")
+        os.makedirs(build_dir)
+        load(name=name, sources=[os.path.join(stage, s) for s in sources],
+             extra_cflags=["-O2", "-std=c++17"],
+             extra_cuda_cflags=["-gencode", "arch=compute_100,code=sm_100", "-std=c++17"],   # patch 1
+             build_directory=build_dir, verbose=verbose, is_python_module=False)
+        so = glob.glob(os.path.join(build_dir, name + "*.so"))[0]
+        shutil.copy(so, os.path.join(OUT, name + ".so"))
+        shutil.rmtree(stage, ignore_errors=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", sorted(os.listdir(OUT)))

@@ -1,0 +1,78 @@
+"""CPU tests of the host-side mirror of the reference interface: same names, import paths, argument
+order and defaults; loud failure (never a silent CPU path) when asked to run off-GPU."""
+import inspect
+
+import pytest
+import torch
+
+from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm, ChannelNormFunction
+from ir2rgb_b200.models.flownet2_pytorch.networks.correlation_package.correlation import Correlation, CorrelationFunction
+from ir2rgb_b200.models.flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d, Resample2dFunction
+from ir2rgb_b200.models import networks
+
+
+def defaults(fn):
+    sig = inspect.signature(fn)
+    return [(n, p.default) for n, p in sig.parameters.items() if n not in ("self", "ctx")]
+
+
+def test_constructor_signatures_match_reference():
+    # reference correlation.py:43, resample2d.py:40, channelnorm.py:33
+    assert defaults(Correlation.__init__) == [("pad_size", 0), ("kernel_size", 0), ("max_displacement", 0),
+                                              ("stride1", 1), ("stride2", 2), ("corr_multiply", 1)]
+    assert defaults(Resample2d.__init__) == [("kernel_size", 1)]
+    assert defaults(ChannelNorm.__init__) == [("norm_deg", 2)]
+
+
+def test_function_signatures_match_reference():
+    # reference correlation.py:10-12, resample2d.py:8, channelnorm.py:8
+    assert defaults(CorrelationFunction.forward) == [("input1", inspect._empty), ("input2", inspect._empty),
+                                                     ("pad_size", 3), ("kernel_size", 3), ("max_displacement", 20),
+                                                     ("stride1", 1), ("stride2", 2), ("corr_multiply", 1)]
+    assert defaults(Resample2dFunction.forward) == [("input1", inspect._empty), ("input2", inspect._empty), ("kernel_size", 1)]
+    assert defaults(ChannelNormFunction.forward) == [("input1", inspect._empty), ("norm_deg", 2)]
+    assert defaults(networks.get_grid) == [("batch_size", inspect._empty), ("rows", inspect._empty), ("cols", inspect._empty),
+                                           ("device", "cuda:0"), ("dtype", torch.float32)]
+
+
+def test_modules_hold_no_parameters_and_keep_attribute_names():
+    c = Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)
+    assert (c.pad_size, c.kernel_size, c.max_displacement, c.stride1, c.stride2, c.corr_multiply) == (20, 1, 20, 1, 2, 1)
+    for m in (c, Resample2d(), ChannelNorm()):
+        assert list(m.state_dict().keys()) == []        # checkpoints of the reference load unchanged
+
+
+def test_get_grid_values_match_reference_formula():
+    g = networks.get_grid(2, 5, 7, device="cpu")
+    assert g.shape == (2, 2, 5, 7)
+    assert torch.equal(g[0, 0, 0], torch.linspace(-1.0, 1.0, 7))
+    assert torch.equal(g[1, 1, :, 3], torch.linspace(-1.0, 1.0, 5))
+
+
+@pytest.mark.parametrize("call", [
+    lambda: ChannelNorm()(torch.zeros(1, 3, 4, 4)),
+    lambda: Resample2d()(torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)),
+    lambda: Correlation(20, 1, 20, 1, 2, 1)(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8)),
+    lambda: networks.resample(torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)),
+])
+def test_no_cpu_fallback(call):
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        call()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from ir2rgb_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libflowops.so"))
+    with pytest.raises(_lib.FlowopsError, match="not found"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ir2rgb_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)

@@ -1,0 +1,365 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the public drop-in
+modules -> ctypes -> the C ABI of libflowops.so; the oracle (C restatement, PyTorch fp64 closed
+forms, the reference's rebuilt extensions when oracle/_ref is present) is only the checker.
+
+Tolerances (BASELINE.json north_star): fp32 forward max-relative error <= 1e-5, backward <= 1e-4,
+where max-relative = max|a-b| / max|b|.  Where the arithmetic can be reproduced exactly the tests
+ask for bit-identity instead.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_ref as tr
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, BWD_TOL = 1e-5, 1e-4
+
+
+def maxrel(a, b):
+    a = a.detach().double().cpu() if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a)).double()
+    b = b.detach().double().cpu() if isinstance(b, torch.Tensor) else torch.from_numpy(np.asarray(b)).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops(flowops_lib):
+    assert torch.cuda.is_available()
+    from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm
+    from ir2rgb_b200.models.flownet2_pytorch.networks.correlation_package.correlation import Correlation
+    from ir2rgb_b200.models.flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d
+    from ir2rgb_b200.models import networks
+
+    class Ops:
+        pass
+    o = Ops()
+    o.ChannelNorm, o.Correlation, o.Resample2d, o.networks = ChannelNorm, Correlation, Resample2d, networks
+    return o
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_ext
+
+
+# =============================================================================================
+# ChannelNorm
+# =============================================================================================
+@pytest.mark.parametrize("shape", [(2, 3, 16, 24), (1, 2, 13, 19), (1, 5, 8, 8), (3, 3, 64, 128), (1, 1, 1, 1),
+                                   (2, 2, 31, 33), (1, 12, 20, 36)])
+def test_cnorm_vs_oracle_bitexact(ops, c_oracle, shape):
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal(shape).astype(np.float32)
+    x[0, :, 0, 0] = 0.0
+    xt = cu(x).requires_grad_()
+    y = ops.ChannelNorm()(xt)
+    y_ref = c_oracle.cnorm_fwd(x)
+    assert np.array_equal(y.detach().cpu().numpy(), y_ref)
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    y.backward(cu(gy))
+    gx_ref = c_oracle.cnorm_bwd(x, y_ref, gy)
+    gx = xt.grad.cpu().numpy()
+    assert maxrel(gx, gx_ref) <= 1e-7
+    assert (gx == gx_ref).mean() >= 0.9999       # reciprocal + correction reproduces the fp64 divide
+
+
+def test_cnorm_golden(ops, golden_native):
+    g = golden_native
+    for name in ["cn3", "cn2", "cn5"]:
+        xt = cu(g[name + "_x"]).requires_grad_()
+        y = ops.ChannelNorm()(xt)
+        assert np.array_equal(y.detach().cpu().numpy(), g[name + "_y"])
+        y.backward(cu(g[name + "_gy"]))
+        assert maxrel(xt.grad, g[name + "_gx"]) <= 1e-7
+
+
+def test_cnorm_vs_reference_ext_full_size(ops, ref):
+    torch.manual_seed(0)
+    x = (2 * torch.rand(4, 3, 512, 1024, device="cuda") - 1)
+    y = ops.ChannelNorm()(x)
+    assert torch.equal(y, ref.channelnorm_forward(x))
+    gy = torch.randn_like(y)
+    from ir2rgb_b200 import functional as F
+    gx = F.channelnorm_backward(x, y, gy)
+    gx_ref = ref.channelnorm_backward(x, y, gy)
+    assert maxrel(gx, gx_ref) <= 1e-7
+    # properties at full size: norm of a scaled input scales, gradient is parallel to x
+    assert torch.allclose(ops.ChannelNorm()(2 * x), 2 * y, rtol=1e-6)
+
+
+def test_cnorm_empty_and_errors(ops):
+    y = ops.ChannelNorm()(torch.empty(0, 3, 4, 4, device="cuda"))
+    assert y.shape == (0, 1, 4, 4)
+    with pytest.raises(RuntimeError):
+        ops.ChannelNorm()(torch.zeros(1, 3, 4, 4))              # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        ops.ChannelNorm()(torch.zeros(1, 3, 4, 4, device="cuda", dtype=torch.float16))
+
+
+# =============================================================================================
+# Resample2d
+# =============================================================================================
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 16, 24), 3.0), ((1, 2, 13, 19), 6.0), ((1, 3, 12, 20), 40.0),
+                                         ((1, 1, 5, 7), 1.0), ((2, 4, 33, 65), 2.0), ((1, 3, 64, 128), 0.0)])
+def test_resample2d_vs_oracle(ops, c_oracle, shape, sigma):
+    rng = np.random.default_rng(11)
+    B, C, H, W = shape
+    img = rng.standard_normal(shape).astype(np.float32)
+    flow = (sigma * rng.standard_normal((B, 2, H, W))).astype(np.float32)
+    it, ft = cu(img).requires_grad_(), cu(flow).requires_grad_()
+    out = ops.Resample2d()(it, ft)
+    out_ref = c_oracle.resample2d_fwd(img, flow)
+    assert np.array_equal(out.detach().cpu().numpy(), out_ref), "forward is bit-identical to the reference arithmetic"
+    if sigma == 0.0:
+        assert torch.equal(out.detach(), it.detach())
+    go = rng.standard_normal(shape).astype(np.float32)
+    out.backward(cu(go))
+    gi_ref, gf_ref = c_oracle.resample2d_bwd(img, flow, go)
+    assert maxrel(it.grad, gi_ref) <= BWD_TOL and maxrel(it.grad, gi_ref) <= 1e-5
+    assert maxrel(ft.grad, gf_ref) <= 1e-6
+
+
+def test_resample2d_golden(ops, golden_native):
+    g = golden_native
+    for name in ["res_small", "res_odd", "res_far"]:
+        it, ft = cu(g[name + "_img"]).requires_grad_(), cu(g[name + "_flow"]).requires_grad_()
+        out = ops.Resample2d()(it, ft)
+        assert np.array_equal(out.detach().cpu().numpy(), g[name + "_out"])
+        out.backward(cu(g[name + "_gout"]))
+        assert maxrel(it.grad, g[name + "_gimg"]) <= 1e-5
+        assert maxrel(ft.grad, g[name + "_gflow"]) <= 1e-6
+
+
+def test_resample2d_integer_flow_is_shift(ops):
+    img = torch.randn(1, 3, 20, 30, device="cuda")
+    flow = torch.zeros(1, 2, 20, 30, device="cuda")
+    flow[:, 0] = 3.0
+    flow[:, 1] = -2.0
+    out = ops.Resample2d()(img, flow)
+    assert torch.equal(out[:, :, 2:, :27], img[:, :, :18, 3:])
+    # border clamping: rows that would read above the image repeat row 0
+    assert torch.equal(out[:, :, 0, :27], img[:, :, 0, 3:])
+
+
+def test_resample2d_grad_flags(ops):
+    img = torch.randn(1, 3, 8, 8, device="cuda", requires_grad=True)
+    flow = torch.randn(1, 2, 8, 8, device="cuda")
+    ops.Resample2d()(img, flow).sum().backward()
+    assert img.grad is not None
+    img2 = torch.randn(1, 3, 8, 8, device="cuda")
+    flow2 = torch.randn(1, 2, 8, 8, device="cuda", requires_grad=True)
+    ops.Resample2d()(img2, flow2).sum().backward()
+    assert flow2.grad is not None
+    with pytest.raises(NotImplementedError):
+        ops.Resample2d(kernel_size=3)(img2, flow2)
+
+
+@pytest.mark.parametrize("flavour", ["randn", "bilinear_up", "nearest_up"])
+def test_resample2d_vs_reference_ext_full_size(ops, ref, flavour):
+    """SURVEY 8d C3 shapes (batch 4 of the 16 to bound test time), the three flow flavours."""
+    torch.manual_seed(0)
+    B, H, W = 4, 512, 1024
+    img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
+    if flavour == "randn":
+        flow = 4 * torch.randn(B, 2, H, W, device="cuda")
+    else:
+        low = 20 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
+        flow = torch.nn.functional.interpolate(low, scale_factor=4, mode="bilinear" if flavour == "bilinear_up" else "nearest")
+    flow = flow.contiguous()
+    it, ft = img.clone().requires_grad_(), flow.clone().requires_grad_()
+    out = ops.Resample2d()(it, ft)
+    assert torch.equal(out.detach(), ref.resample2d_forward(img, flow))
+    go = torch.randn_like(out)
+    out.backward(go)
+    gi_ref, gf_ref = ref.resample2d_backward(img, flow, go)
+    assert maxrel(ft.grad, gf_ref) <= 1e-6
+    assert maxrel(it.grad, gi_ref) <= BWD_TOL
+    # conservation: the scatter distributes exactly the incoming gradient mass
+    assert abs(it.grad.double().sum().item() - go.double().sum().item()) <= 1e-3 * go.abs().double().sum().item() ** 0.5 + 1e-2
+
+
+# =============================================================================================
+# networks.resample (grid_sample path)
+# =============================================================================================
+@pytest.mark.parametrize("name", ["small", "odd", "border"])
+def test_networks_resample_golden(ops, golden_resample, name):
+    """Against outputs of the reference's own Python code path (CPU)."""
+    g = golden_resample
+    it, ft = cu(g[name + "_img"]).requires_grad_(), cu(g[name + "_flow"]).requires_grad_()
+    out = ops.networks.resample(it, ft)
+    # fp32 coordinate normalisation costs ~3e-5 px; CPU and CUDA ATen differ from each other by that
+    assert maxrel(out, g[name + "_out"]) <= 2e-5
+    out.backward(cu(g[name + "_gout"]))
+    assert maxrel(it.grad, g[name + "_gimg"]) <= BWD_TOL
+    assert maxrel(ft.grad, g[name + "_gflow"]) <= 2e-4
+
+
+@pytest.mark.parametrize("shape,sigma", [((1, 3, 256, 512), 5.0), ((2, 3, 64, 96), 40.0), ((1, 3, 17, 23), 3.0)])
+def test_networks_resample_vs_torch_cuda(ops, shape, sigma):
+    """Against the reference code path run on this GPU (ATen grid_sampler_2d) and against fp64 truth."""
+    torch.manual_seed(0)
+    B, C, H, W = shape
+    img = torch.randn(shape, device="cuda")
+    flow = sigma * torch.randn(B, 2, H, W, device="cuda")
+    it, ft = img.clone().requires_grad_(), flow.clone().requires_grad_()
+    out = ops.networks.resample(it, ft)
+    ir, fr = img.clone().requires_grad_(), flow.clone().requires_grad_()
+    out_ref = tr.networks_resample(ir, fr)
+    truth = tr.networks_resample(img.double(), flow.double())
+    err_new, err_ref = maxrel(out, truth), maxrel(out_ref, truth)
+    frac_equal = (out == out_ref).float().mean().item()
+    print("resample %s: new-vs-fp64 %.2e  aten-vs-fp64 %.2e  new-vs-aten %.2e  bit-equal %.4f"
+          % (shape, err_new, err_ref, maxrel(out, out_ref), frac_equal))
+    assert err_new <= max(1.5 * err_ref, FWD_TOL)        # no less accurate than the reference path
+    go = torch.randn_like(out)
+    out.backward(go)
+    out_ref.backward(go)
+    i64, f64 = img.double().requires_grad_(), flow.double().requires_grad_()
+    tr.networks_resample(i64, f64).backward(go.double())
+    assert maxrel(it.grad, i64.grad) <= max(1.5 * maxrel(ir.grad, i64.grad), BWD_TOL)
+    assert maxrel(ft.grad, f64.grad) <= max(1.5 * maxrel(fr.grad, f64.grad), BWD_TOL)
+
+
+def test_networks_resample_smooth_frame_meets_1e5(ops):
+    """On band-limited frames (what the generator warps) the 1e-5 forward target is met outright."""
+    torch.manual_seed(1)
+    H, W = 256, 512
+    low = torch.randn(1, 3, H // 16, W // 16, device="cuda")
+    img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)
+    flow = 5 * torch.randn(1, 2, H, W, device="cuda")
+    out = ops.networks.resample(img, flow)
+    truth = tr.networks_resample(img.double(), flow.double())
+    assert maxrel(out, truth) <= FWD_TOL
+
+
+# =============================================================================================
+# Correlation
+# =============================================================================================
+FLOWNETC = (20, 1, 20, 1, 2)
+
+
+@pytest.mark.parametrize("shape,params", [
+    ((2, 16, 8, 12), FLOWNETC), ((1, 40, 6, 40), FLOWNETC), ((1, 8, 9, 11), (4, 1, 4, 1, 1)),
+    ((1, 3, 5, 70), FLOWNETC), ((1, 9, 7, 5), FLOWNETC), ((2, 64, 24, 32), FLOWNETC),
+    ((1, 8, 6, 6), (6, 1, 6, 1, 2)), ((1, 4, 6, 7), (3, 3, 2, 1, 1)),
+])
+def test_correlation_vs_oracle(ops, c_oracle, shape, params):
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal(shape).astype(np.float32)
+    b = rng.standard_normal(shape).astype(np.float32)
+    at, bt = cu(a).requires_grad_(), cu(b).requires_grad_()
+    out = ops.Correlation(*params, 1)(at, bt)
+    out_ref = c_oracle.corr_fwd(a, b, *params)
+    assert tuple(out.shape) == out_ref.shape
+    assert maxrel(out, out_ref) <= FWD_TOL
+    go = rng.standard_normal(out_ref.shape).astype(np.float32)
+    out.backward(cu(go))
+    ga_ref, gb_ref = c_oracle.corr_bwd(a, b, go, *params)
+    assert maxrel(at.grad, ga_ref) <= BWD_TOL
+    assert maxrel(bt.grad, gb_ref) <= BWD_TOL
+
+
+def test_correlation_stride1_forward_only(ops, c_oracle):
+    rng = np.random.default_rng(13)
+    a = rng.standard_normal((1, 8, 10, 10)).astype(np.float32)
+    b = rng.standard_normal((1, 8, 10, 10)).astype(np.float32)
+    out = ops.Correlation(4, 1, 4, 2, 2, 1)(cu(a), cu(b))
+    assert maxrel(out, c_oracle.corr_fwd(a, b, 4, 1, 4, 2, 2)) <= FWD_TOL
+    at = cu(a).requires_grad_()
+    with pytest.raises(NotImplementedError):
+        ops.Correlation(4, 1, 4, 2, 2, 1)(at, cu(b)).sum().backward()
+
+
+def test_correlation_golden(ops, golden_native):
+    g = golden_native
+    for name in ["corr_c", "corr_wide", "corr_s1", "corr_s2"]:
+        p = [int(v) for v in g[name + "_params"]]
+        at, bt = cu(g[name + "_a"]).requires_grad_(), cu(g[name + "_b"]).requires_grad_()
+        out = ops.Correlation(*p, 1)(at, bt)
+        assert maxrel(out, g[name + "_out"]) <= FWD_TOL
+        if name + "_gout" in g:
+            out.backward(cu(g[name + "_gout"]))
+            assert maxrel(at.grad, g[name + "_ga"]) <= BWD_TOL
+            assert maxrel(bt.grad, g[name + "_gb"]) <= BWD_TOL
+
+
+def test_correlation_config2_vs_reference_ext_and_fp64(ops, ref):
+    """BASELINE config 2: 8x256x48x64, FlowNetC parameters, fwd + bwd."""
+    torch.manual_seed(0)
+    a = torch.randn(8, 256, 48, 64, device="cuda")
+    b = torch.randn(8, 256, 48, 64, device="cuda")
+    at, bt = a.clone().requires_grad_(), b.clone().requires_grad_()
+    out = ops.Correlation(*FLOWNETC, 1)(at, bt)
+    out_ref = ref.correlation_forward(a, b, *FLOWNETC)
+    assert maxrel(out, out_ref) <= FWD_TOL
+    # fp64 truth on one batch item: the new kernel is no further from it than the reference kernel
+    truth = tr.correlation(a[:1].double(), b[:1].double(), *FLOWNETC)
+    assert maxrel(out[:1], truth) <= max(1.5 * maxrel(out_ref[:1], truth), 1e-6)
+    go = torch.randn_like(out)
+    out.backward(go)
+    ga_ref, gb_ref = ref.correlation_backward(a, b, go, *FLOWNETC)
+    assert maxrel(at.grad, ga_ref) <= BWD_TOL
+    assert maxrel(bt.grad, gb_ref) <= BWD_TOL
+
+
+def test_correlation_properties_full_size(ops):
+    """Size-independent properties at the FlowNet2 512x1024 feature size (B x 256 x 64 x 128)."""
+    torch.manual_seed(1)
+    a = torch.randn(2, 256, 64, 128, device="cuda")
+    b = torch.randn(2, 256, 64, 128, device="cuda")
+    corr = ops.Correlation(*FLOWNETC, 1)
+    out = corr(a, b)
+    assert out.shape == (2, 441, 64, 128)
+    # centre channel (tj = ti = 0) is the per-pixel mean of a*b
+    assert maxrel(out[:, 220], (a * b).mean(1)) <= FWD_TOL
+    # bilinearity
+    assert maxrel(corr(2 * a, b), 2 * out) <= FWD_TOL
+    assert maxrel(corr(a, b + a), out + corr(a, a)) <= 2e-5
+    # displacement structure: channel (tj, ti) equals mean_c a * shift(b); spot-check three taps incl. padding
+    for tj, ti in [(-10, -10), (3, -7), (10, 10)]:
+        sh = torch.zeros_like(b)
+        dy, dx = 2 * tj, 2 * ti
+        ys, ye = max(0, -dy), min(64, 64 - dy)
+        xs, xe = max(0, -dx), min(128, 128 - dx)
+        sh[:, :, ys:ye, xs:xe] = b[:, :, ys + dy:ye + dy, xs + dx:xe + dx]
+        assert maxrel(out[:, (tj + 10) * 21 + ti + 10], (a * sh).mean(1)) <= FWD_TOL
+
+
+def test_correlation_errors(ops):
+    a = torch.randn(1, 4, 8, 8, device="cuda")
+    with pytest.raises(ValueError):
+        ops.Correlation(*FLOWNETC, 1)(a, torch.randn(1, 4, 8, 9, device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.Correlation(*FLOWNETC, 1)(a.cpu(), a.cpu())
+    out = ops.Correlation(*FLOWNETC, 1)(torch.empty(0, 4, 8, 8, device="cuda"), torch.empty(0, 4, 8, 8, device="cuda"))
+    assert out.shape == (0, 441, 8, 8)
+
+
+def test_ops_are_graph_capturable_and_stream_ordered(ops):
+    """No allocation-free guarantee is needed from torch here: the library calls themselves must not
+    synchronise or touch the default stream."""
+    a = torch.randn(1, 16, 16, 16, device="cuda")
+    b = torch.randn(1, 16, 16, 16, device="cuda")
+    corr = ops.Correlation(*FLOWNETC, 1)
+    expect = corr(a, b)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            corr(a, b)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = corr(a, b)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, expect)

@@ -1,5 +1,6 @@
 // api.cu -- error plumbing, version, and the FFMA-peak measurement helper of libflowops.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,7 +22,11 @@ void set_error(const char *fmt, ...)
 // does likewise.
 int check_launch(const char *what)
 {
-    const cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    // FLOWOPS_DEBUG_SYNC=1: synchronise after every launch so that an execution error is attributed
+    // to the kernel that caused it (development aid; never set in production or under graph capture)
+    static const bool debug_sync = getenv("FLOWOPS_DEBUG_SYNC") != nullptr;
+    if (e == cudaSuccess && debug_sync) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return (int)e;

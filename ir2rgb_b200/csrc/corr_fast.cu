@@ -51,9 +51,16 @@ constexpr int kSmemBytes = kStages * kStageBytes;           // 166912
 static_assert(kEpiRows * kEpiPitch * 4 <= kSmemBytes, "epilogue staging must fit in the pipeline buffers");
 static_assert(kStageBytes % 128 == 0 && (kF2Floats * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 
+// TMA needs the innermost start coordinate of a box to be 16-byte aligned (measured on B200: a box
+// starting at x = -10 or 2 raises "illegal instruction", -8 / 0 / -12 are fine).  The f2 window starts
+// kR = 10 columns left of the tile, so the f2 planes are stored shifted right by kShift = 2 columns
+// (two explicit zero columns in front): the window then starts at x0 - 8.
+constexpr int kShift = 2;
+
 struct PlaneGeom {
-    int Hp, Wp, pitch;    // plane rows, valid plane columns (ceil), row pitch in floats (multiple of 4)
-    size_t plane_elems;   // Hp * pitch
+    int Hp, Wp;             // plane rows / valid plane columns (ceil)
+    int pitch1, pitch2;     // row pitch in floats of the f1 / f2 planes (multiples of 4)
+    size_t elems1, elems2;  // floats per (n, plane, c) image
 };
 
 static inline PlaneGeom plane_geom(const CorrGeom &g)
@@ -61,8 +68,10 @@ static inline PlaneGeom plane_geom(const CorrGeom &g)
     PlaneGeom p;
     p.Hp = (g.H + 1) / 2;
     p.Wp = (g.W + 1) / 2;
-    p.pitch = (p.Wp + 3) & ~3;
-    p.plane_elems = (size_t)p.Hp * p.pitch;
+    p.pitch1 = (p.Wp + 3) & ~3;
+    p.pitch2 = (p.Wp + kShift + 3) & ~3;
+    p.elems1 = (size_t)p.Hp * p.pitch1;
+    p.elems2 = (size_t)p.Hp * p.pitch2;
     return p;
 }
 
@@ -74,7 +83,7 @@ bool corr_fast_supported(const CorrGeom &g)
 size_t corr_fast_fwd_workspace(const CorrGeom &g)
 {
     const PlaneGeom p = plane_geom(g);
-    return 2 * sizeof(float) * (size_t)g.B * 4 * g.C * p.plane_elems;
+    return sizeof(float) * (size_t)g.B * 4 * g.C * (p.elems1 + p.elems2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -82,10 +91,13 @@ size_t corr_fast_fwd_workspace(const CorrGeom &g)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ in1, const float *__restrict__ in2,
                                                       float *__restrict__ P1, float *__restrict__ P2,
-                                                      int B, int C, int H, int W, int Hp, int pitch, int vec_ok)
+                                                      int B, int C, int H, int W, int Hp, int pitch1, int pitch2, int vec_ok)
 {
-    const float *__restrict__ in = blockIdx.y ? in2 : in1;
-    float *__restrict__ P = blockIdx.y ? P2 : P1;
+    const bool second = blockIdx.y != 0;
+    const float *__restrict__ in = second ? in2 : in1;
+    float *__restrict__ P = second ? P2 : P1;
+    const int pitch = second ? pitch2 : pitch1;
+    const int shift = second ? kShift : 0;
     const int W4 = (W + 3) >> 2;
     const size_t total = (size_t)B * C * H * W4;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
@@ -105,12 +117,23 @@ __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ 
             v.z = x + 2 < W ? src[2] : 0.f;
             v.w = x + 3 < W ? src[3] : 0.f;
         }
-        const int py = y & 1, yy = y >> 1, xx = x >> 1;
-        float *d0 = P + ((((size_t)n * 4 + py * 2 + 0) * C + c) * Hp + yy) * pitch + xx;
-        float *d1 = P + ((((size_t)n * 4 + py * 2 + 1) * C + c) * Hp + yy) * pitch + xx;
-        // pitch is a multiple of 4 and xx is even: 8-byte aligned pairs (padding columns get zeros)
-        *reinterpret_cast<float2 *>(d0) = make_float2(v.x, v.z);
-        *reinterpret_cast<float2 *>(d1) = make_float2(v.y, v.w);
+        const int py = y & 1, yy = y >> 1, xx = (x >> 1) + shift;
+        float *row0 = P + ((((size_t)n * 4 + py * 2 + 0) * C + c) * Hp + yy) * pitch;
+        float *row1 = P + ((((size_t)n * 4 + py * 2 + 1) * C + c) * Hp + yy) * pitch;
+        // pitch is a multiple of 4 and xx is even: 8-byte aligned pairs
+        *reinterpret_cast<float2 *>(row0 + xx) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2 *>(row1 + xx) = make_float2(v.y, v.w);
+        if (second) {   // explicit zero columns in front of and behind the shifted row
+            if (x == 0) {
+                *reinterpret_cast<float2 *>(row0) = make_float2(0.f, 0.f);
+                *reinterpret_cast<float2 *>(row1) = make_float2(0.f, 0.f);
+            }
+            if (x + 4 >= W)
+                for (int q = xx + 2; q < pitch; q += 2) {
+                    *reinterpret_cast<float2 *>(row0 + q) = make_float2(0.f, 0.f);
+                    *reinterpret_cast<float2 *>(row1 + q) = make_float2(0.f, 0.f);
+                }
+        }
     }
 }
 
@@ -187,7 +210,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
         const uint32_t bar = bar_base + 8 * slot;
         const uint32_t dst = smem_base + slot * kStageBytes;
         mbar_expect_tx(bar, kStageBytes);
-        tma_load_4d(dst, &tm2, x0 - kR, y0 - kR, it * kCK, np, bar);
+        tma_load_4d(dst, &tm2, x0 - kR + kShift, y0 - kR, it * kCK, np, bar);   // x0 - 8: 16-byte aligned
         tma_load_4d(dst + kF2Floats * 4, &tm1, x0, y0, it * kCK, np, bar);
     };
     if (tid == 0) {
@@ -289,13 +312,13 @@ static EncodeTiledFn get_encoder()
     return fn;
 }
 
-static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, const PlaneGeom &p, int box_w, int box_h)
+static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, int Hp, int pitch, int box_w, int box_h)
 {
     EncodeTiledFn enc = get_encoder();
     FLOWOPS_REQUIRE(enc, FLOWOPS_EUNSUPPORTED, "corr: cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t dims[4] = {(cuuint64_t)p.pitch, (cuuint64_t)p.Hp, (cuuint64_t)g.C, (cuuint64_t)g.B * 4};
-    const cuuint64_t strides[3] = {(cuuint64_t)p.pitch * 4, (cuuint64_t)p.plane_elems * 4,
-                                   (cuuint64_t)p.plane_elems * 4 * g.C};
+    const cuuint64_t plane_bytes = (cuuint64_t)Hp * pitch * 4;
+    const cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)Hp, (cuuint64_t)g.C, (cuuint64_t)g.B * 4};
+    const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, plane_bytes, plane_bytes * g.C};
     const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)kCK, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
@@ -313,7 +336,7 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
     FLOWOPS_REQUIRE(ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0, FLOWOPS_EWORKSPACE,
                     "corr_fwd: workspace of %zu bytes (256-byte aligned) required, got %zu", need, ws_bytes);
     float *P1 = reinterpret_cast<float *>(ws);
-    float *P2 = P1 + need / (2 * sizeof(float));
+    float *P2 = P1 + (size_t)g.B * 4 * g.C * p.elems1;
 
     // planes have zero padding only when W is not a multiple of 8 or H is odd
     if ((g.W & 7) || (g.H & 1)) {
@@ -325,15 +348,15 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
         const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
         size_t blocks = (total + 255) / 256;
         if (blocks > (size_t)kNumSMs * 8 * 8) blocks = (size_t)kNumSMs * 8 * 8;
-        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch, vec_ok);
+        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
         const int rc = check_launch("corr_planarize");
         if (rc) return rc;
     }
 
     CUtensorMap tm1, tm2;
-    int rc = make_plane_map(&tm1, P1, g, p, kF1W, kTY);
+    int rc = make_plane_map(&tm1, P1, g, p.Hp, p.pitch1, kF1W, kTY);
     if (rc) return rc;
-    rc = make_plane_map(&tm2, P2, g, p, kF2W, kF2H);
+    rc = make_plane_map(&tm2, P2, g, p.Hp, p.pitch2, kF2W, kF2H);
     if (rc) return rc;
 
     static bool attr_set = false;

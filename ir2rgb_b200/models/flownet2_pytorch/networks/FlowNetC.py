@@ -1,0 +1,56 @@
+"""FlowNetC (reference networks/FlowNetC.py:13-131; 39,175,298 parameters), table-driven.
+
+The one caller of the Correlation operator on the hot path (FlowNetC.py:31,89): both frames go
+through a shared conv1-3 tower, the 256-channel conv3 features are correlated (pad 20, k 1, md 20,
+s1 1, s2 2 -> 441 channels), and the cost volume joins a 32-channel redirect of frame-1 features.
+"""
+import torch
+import torch.nn as nn
+
+from .correlation_package.correlation import Correlation
+from .submodules import add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
+
+TOWER = [("conv1", 3, 64, 7, 2), ("conv2", 64, 128, 5, 2), ("conv3", 128, 256, 5, 2), ("conv_redir", 256, 32, 1, 1)]
+TRUNK = [("conv3_1", 473, 256, 3, 1), ("conv4", 256, 512, 3, 2), ("conv4_1", 512, 512, 3, 1), ("conv5", 512, 512, 3, 2),
+         ("conv5_1", 512, 512, 3, 1), ("conv6", 512, 1024, 3, 2), ("conv6_1", 1024, 1024, 3, 1)]
+DECODER = {5: (1024, 512), 4: (1026, 256), 3: (770, 128), 2: (386, 64)}
+HEADS = {6: 1024, 5: 1026, 4: 770, 3: 386, 2: 194}
+
+
+class FlowNetC(nn.Module):
+    def __init__(self, args, batchNorm=True, div_flow=20):
+        super(FlowNetC, self).__init__()
+        self.fp16 = args.fp16
+        self.batchNorm = batchNorm
+        self.div_flow = div_flow
+        add_layers(self, batchNorm, TOWER)
+        self.corr = Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)
+        self.corr_activation = nn.LeakyReLU(0.1, inplace=True)
+        add_layers(self, batchNorm, TRUNK)
+        for lv, (cin, cout) in DECODER.items():
+            setattr(self, "deconv%d" % lv, deconv(cin, cout))
+        for lv, cin in HEADS.items():
+            setattr(self, "predict_flow%d" % lv, predict_flow(cin))
+        for lv in (5, 4, 3, 2):
+            setattr(self, "upsampled_flow%d_to_%d" % (lv + 1, lv), flow_upsampler(bias=True))
+        reference_init(self)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
+
+    def tower(self, frame):
+        c2 = self.conv2(self.conv1(frame))
+        return c2, self.conv3(c2)
+
+    def forward(self, x):
+        c2a, c3a = self.tower(x[:, 0:3])
+        _, c3b = self.tower(x[:, 3:])
+        if self.fp16:       # the operator is fp32-only, as in the reference (FlowNetC.py:86-87)
+            cost = self.corr(c3a.float(), c3b.float()).half()
+        else:
+            cost = self.corr(c3a, c3b)
+        cost = self.corr_activation(cost)
+        c3 = self.conv3_1(torch.cat((self.conv_redir(c3a), cost), 1))
+        c4 = self.conv4_1(self.conv4(c3))
+        c5 = self.conv5_1(self.conv5(c4))
+        c6 = self.conv6_1(self.conv6(c5))
+        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2a}, c6, (5, 4, 3, 2))
+        return tuple(flows) if self.training else (flows[0],)

@@ -1,0 +1,34 @@
+"""FlowNetS (reference networks/FlowNetS.py:15-95; 38,676,504 parameters), table-driven."""
+import torch.nn as nn
+
+from .submodules import add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
+
+ENCODER = [("conv1", None, 64, 7, 2), ("conv2", 64, 128, 5, 2), ("conv3", 128, 256, 5, 2), ("conv3_1", 256, 256, 3, 1),
+           ("conv4", 256, 512, 3, 2), ("conv4_1", 512, 512, 3, 1), ("conv5", 512, 512, 3, 2), ("conv5_1", 512, 512, 3, 1),
+           ("conv6", 512, 1024, 3, 2), ("conv6_1", 1024, 1024, 3, 1)]
+DECODER = {5: (1024, 512), 4: (1026, 256), 3: (770, 128), 2: (386, 64)}      # level -> deconv (in, out)
+HEADS = {6: 1024, 5: 1026, 4: 770, 3: 386, 2: 194}                           # level -> predict_flow in
+
+
+class FlowNetS(nn.Module):
+    def __init__(self, args, input_channels=12, batchNorm=True):
+        super(FlowNetS, self).__init__()
+        self.batchNorm = batchNorm
+        add_layers(self, batchNorm, [(n, input_channels if i is None else i, o, k, s) for n, i, o, k, s in ENCODER])
+        for lv, (cin, cout) in DECODER.items():
+            setattr(self, "deconv%d" % lv, deconv(cin, cout))
+        for lv, cin in HEADS.items():
+            setattr(self, "predict_flow%d" % lv, predict_flow(cin))
+        for lv in (5, 4, 3, 2):
+            setattr(self, "upsampled_flow%d_to_%d" % (lv + 1, lv), flow_upsampler(bias=False))
+        reference_init(self)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
+
+    def forward(self, x):
+        c2 = self.conv2(self.conv1(x))
+        c3 = self.conv3_1(self.conv3(c2))
+        c4 = self.conv4_1(self.conv4(c3))
+        c5 = self.conv5_1(self.conv5(c4))
+        c6 = self.conv6_1(self.conv6(c5))
+        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2}, c6, (5, 4, 3, 2))
+        return tuple(flows) if self.training else (flows[0],)

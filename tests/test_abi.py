@@ -81,8 +81,9 @@ def test_shapes_and_workspace(flowops_lib):
     assert (oc.value, oh.value, ow.value) == (441, 48, 64)
     assert lib.flowops_corr_out_shape(10, 10, 4, 1, 4, 2, 2, ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)) == 0
     assert (oc.value, oh.value, ow.value) == (25, 5, 5)
-    # FlowNetC configuration: two parity-plane copies, the size of the reference's rbot1/rbot2 minus padding
-    assert lib.flowops_corr_fwd_workspace_bytes(8, 256, 48, 64, 20, 1, 20, 1, 2) == 2 * 8 * 256 * 48 * 64 * 4
+    # FlowNetC configuration: two parity-plane copies (the role of the reference's rbot1/rbot2, without the
+    # 20-pixel padding); the f2 planes carry 4 extra columns per row for TMA start alignment
+    assert lib.flowops_corr_fwd_workspace_bytes(8, 256, 48, 64, 20, 1, 20, 1, 2) == 8 * 4 * 256 * 24 * (32 + 36) * 4
     assert lib.flowops_corr_fwd_workspace_bytes(1, 8, 9, 11, 4, 1, 4, 1, 1) == 0               # generic kernel
 
 

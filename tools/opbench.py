@@ -1,0 +1,143 @@
+"""Per-operator timing on one GPU: new kernels vs the reference's rebuilt extensions (oracle/_ref),
+with roofline fractions.  CUDA events on the current stream, warm-up, L2 flushed between iterations.
+
+    python tools/opbench.py [--iters 20] [--json gpurun_out/opbench.json] [--skip-ref]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ir2rgb_b200 import functional as F  # noqa: E402
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "source": "fallback"}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        m = json.load(open(path))
+        p = {"hbm_gbs": float(m["hbm_gbs"]), "source": "measured"}
+    return p
+
+
+class L2Flusher:
+    def __init__(self):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_op(fn, iters, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    best = 1e30
+    for _ in range(iters):
+        if flush is not None:
+            flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        total += t
+        best = min(best, t)
+    return total / iters * 1e3, best * 1e3      # microseconds (mean, best)
+
+
+def run(iters=20, skip_ref=False, small=False):
+    torch.manual_seed(0)
+    pk = peaks()
+    flush = L2Flusher()
+    ffma = F.ffma_peak_tflops()
+    res = {"peaks": dict(pk, ffma_tflops=ffma, ffma_nominal_tflops=148 * 128 * 2 * 1.965e9 / 1e12), "ops": {}}
+    ref = None
+    if not skip_ref:
+        from oracle import ref_ext
+        if ref_ext.available():
+            ref = ref_ext
+
+    def add(name, new_fn, ref_fn, alg_bytes=None, alg_flop=None, ref_iters=None):
+        mean, best = time_op(new_fn, iters, flush=flush)
+        e = {"us": mean, "us_best": best}
+        if alg_bytes is not None:
+            e.update(bound="hbm", alg_bytes=alg_bytes, achieved_gbs=alg_bytes / mean / 1e3,
+                     frac=alg_bytes / mean / 1e3 / pk["hbm_gbs"], frac_of_8TBs=alg_bytes / mean / 1e3 / 8000.0)
+        if alg_flop is not None:
+            e.update(bound="fp32", alg_flop=alg_flop, achieved_tflops=alg_flop / mean / 1e6,
+                     frac=alg_flop / mean / 1e6 / ffma)
+        if ref is not None and ref_fn is not None:
+            rmean, rbest = time_op(ref_fn, ref_iters or max(3, iters // 4), warmup=1, flush=flush)
+            e.update(ref_us=rmean, speedup_vs_ref=rmean / mean)
+        res["ops"][name] = e
+        print(name, json.dumps(e), flush=True)
+
+    # ---- C2: Correlation 8x256x48x64 ----
+    B, C, H, W = (2, 64, 24, 32) if small else (8, 256, 48, 64)
+    P = (20, 1, 20, 1, 2)
+    a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, 441, H, W, device="cuda")
+    flop = 2.0 * B * H * W * 441 * C
+    add("corr_fwd_c2", lambda: F.correlation_forward(a, b, *P),
+        (lambda: ref.correlation_forward(a, b, *P)) if ref else None,
+        alg_flop=flop)
+    add("corr_bwd_c2", lambda: F.correlation_backward(a, b, go, *P),
+        (lambda: ref.correlation_backward(a, b, go, *P)) if ref else None,
+        alg_flop=2 * flop, ref_iters=2)
+    # ---- C4-shaped correlation (FlowNet2 at 512x1024, per-GPU batch 8) ----
+    if not small:
+        a4, b4 = torch.randn(8, 256, 64, 128, device="cuda"), torch.randn(8, 256, 64, 128, device="cuda")
+        add("corr_fwd_c4_b8", lambda: F.correlation_forward(a4, b4, *P),
+            (lambda: ref.correlation_forward(a4, b4, *P)) if ref else None,
+            alg_flop=2.0 * 8 * 64 * 128 * 441 * 256, ref_iters=2)
+        del a4, b4
+
+    # ---- C3: Resample2d + ChannelNorm on 16x3x512x1024 ----
+    B, H, W = (2, 128, 256) if small else (16, 512, 1024)
+    plane = B * H * W * 4
+    img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
+    gout = torch.randn(B, 3, H, W, device="cuda")
+    low = 20 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
+    flows = {
+        "randn": 4 * torch.randn(B, 2, H, W, device="cuda"),
+        "bilinear": torch.nn.functional.interpolate(low, scale_factor=4, mode="bilinear").contiguous(),
+        "nearest": torch.nn.functional.interpolate(low, scale_factor=4, mode="nearest").contiguous(),
+    }
+    for fl, flow in flows.items():
+        add("resample2d_fwd_" + fl, lambda: F.warp_forward(img, flow, F.WARP_RESAMPLE2D),
+            (lambda: ref.resample2d_forward(img, flow)) if ref else None, alg_bytes=8 * plane)
+        add("resample2d_bwd_" + fl, lambda: F.warp_backward(img, flow, gout, True, True, F.WARP_RESAMPLE2D),
+            (lambda: ref.resample2d_backward(img, flow, gout)) if ref else None, alg_bytes=13 * plane)
+        add("resample2d_bwd_flowonly_" + fl, lambda: F.warp_backward(img, flow, gout, False, True, F.WARP_RESAMPLE2D),
+            None, alg_bytes=10 * plane)
+    flow = flows["bilinear"]
+    add("gridsample_fwd_bilinear", lambda: F.warp_forward(img, flow, F.WARP_GRIDSAMPLE),
+        lambda: __import__("oracle.torch_ref", fromlist=["x"]).networks_resample(img, flow), alg_bytes=8 * plane)
+    y = F.channelnorm_forward(img)
+    gy = torch.randn_like(y)
+    add("cnorm_fwd_c3", lambda: F.channelnorm_forward(img),
+        (lambda: ref.channelnorm_forward(img)) if ref else None, alg_bytes=4 * plane)
+    add("cnorm_bwd_c3", lambda: F.channelnorm_backward(img, y, gy),
+        (lambda: ref.channelnorm_backward(img, y, gy)) if ref else None, alg_bytes=8 * plane)
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--skip-ref", action="store_true")
+    ap.add_argument("--small", action="store_true")
+    args = ap.parse_args()
+    out = run(args.iters, args.skip_ref, args.small)
+    if args.json:
+        os.makedirs(os.path.dirname(args.json) or ".", exist_ok=True)
+        json.dump(out, open(args.json, "w"), indent=1)

@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric: FlowNet2 frame pairs/s at 512x1024, batch 64 sharded over
+N B200s, with the hot-path operators' roofline fractions.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the flow hot path over one batch of synthetic frame pairs: config[3] of
+BASELINE.json -- FlowNet2 (C+S+SD+fusion) forward + confidence mask through the public `FlowNet` wrapper
+(models/flownet.py API) on 2*rand-1 frames of 512x1024, random-init weights, global batch 64 split into
+contiguous chunks of 64/N per rank (strong scaling, no collective on the data path), processed in
+micro-batches.  `value` times the step with the frames already in HBM; `e2e` times the same call with
+the frames in pinned host memory (H2D of both frame batches and D2H of flow + confidence inside the
+timed region).  Rank 0 prints ONE JSON line.
+
+--impl reference runs the same workload with the reference's own operators: the CUDA extensions of
+/root/reference rebuilt for sm_100 (oracle/_ref, see oracle/build_ref.py) plugged into the same FlowNet2
+conv body with the reference's unfused glue; if they cannot be loaded it falls back to the pure-PyTorch
+CPU port on the host cores (a bounded sample).  Nothing of ir2rgb_b200's native code runs in that arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 512, 1024
+GLOBAL_BATCH = 64
+METRIC = "flownet2_frame_pairs_per_s"
+
+
+# ---------------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-operator roofline table")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="keep cuDNN autotuning launches out of ncu launch lists")
+    return ap.parse_args()
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        m = json.load(open(path))
+        p = {"hbm_gbs": float(m["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+class Launches:
+    """Counts this repo's kernel launches and times the dominant operator (Correlation forward) with
+    CUDA events on the launching stream, live inside the timed region."""
+
+    PER_CALL = {"correlation_forward": 2, "warp_diff_norm_forward": 1, "channelnorm_forward": 1,
+                "warp_conf_forward": 1, "warp_forward": 1}
+
+    def __init__(self):
+        self.count = 0
+        self.corr_events = []
+        self.enabled = False
+
+    def install(self):
+        import torch
+        from ir2rgb_b200 import functional as F
+        for name, n in self.PER_CALL.items():
+            orig = getattr(F, name)
+
+            def wrapped(*a, _orig=orig, _n=n, _name=name, **k):
+                if not self.enabled:
+                    return _orig(*a, **k)
+                self.count += _n
+                if _name != "correlation_forward":
+                    return _orig(*a, **k)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = _orig(*a, **k)
+                e1.record()
+                self.corr_events.append((e0, e1, a[0].shape))
+                return out
+            setattr(F, name, wrapped)
+
+
+def build_native(device):
+    from ir2rgb_b200.models.flownet import FlowNet
+    net = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[device.index], checkpoints_dir=".", name="bench")
+    return net.eval()
+
+
+def run_step(net, im1, im2, mb, host_out=None):
+    """One pass over this rank's batch in micro-batches.  im1/im2 on the device, or pinned host tensors
+    (then each micro-batch is copied H2D here and its flow/conf are copied back into host_out)."""
+    import torch
+    B = im1.shape[0]
+    dev = next(net.parameters()).device
+    last = None
+    for s in range(0, B, mb):
+        a, b = im1[s:s + mb], im2[s:s + mb]
+        if not a.is_cuda:
+            a = a.to(dev, non_blocking=True)
+            b = b.to(dev, non_blocking=True)
+        flow, conf = net(a, b)
+        if host_out is not None:
+            host_out[0][s:s + mb].copy_(flow, non_blocking=True)
+            host_out[1][s:s + mb].copy_(conf, non_blocking=True)
+        last = flow
+    return last
+
+
+def timed(fn, steps, warmup, dist, device):
+    import torch
+    for _ in range(warmup):
+        fn()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms / steps
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_pairs_per_s(max_pairs=8, min_seconds=10.0, threads=None):
+    """The pure-PyTorch CPU port (oracle) of the same workload on the host cores: FlowNet2 forward +
+    confidence on `max_pairs` 512x1024 pairs (bounded sample)."""
+    import torch
+    from oracle.harness import OracleFlowNet
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = OracleFlowNet("torch", "cpu")
+    im1, im2 = 2 * torch.rand(1, 3, H, W) - 1, 2 * torch.rand(1, 3, H, W) - 1
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_pairs and (n == 0 or time.perf_counter() - t0 < min_seconds):
+        net(im1, im2)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "%d frame pair(s) of 512x1024 through the pure-PyTorch CPU oracle (FlowNet2 + conf), %.1f s" % (n, dt)}
+
+
+def ops_table(pk, ffma):
+    """Per-operator roofline fractions at BASELINE configs 2 and 3 (outside the timed region)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import opbench
+    res = opbench.run(iters=10, skip_ref=True, quiet=True, ffma=ffma)
+    out = {}
+    for k, v in res["ops"].items():
+        out[k] = {"us": round(v["us"], 2), "bound": v["bound"], "frac": round(v["frac"], 4),
+                  "achieved": round(v.get("achieved_gbs", v.get("achieved_tflops", 0.0)), 2),
+                  "unit": "GB/s" if v["bound"] == "hbm" else "TFLOP/s"}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+
+    import torch
+
+    use_cpu_ref = False
+    if args.impl == "reference":
+        from oracle import ref_ext
+        use_cpu_ref = args.ref_device == "cpu" or (args.ref_device == "auto" and not (ref_ext.available() and torch.cuda.is_available()))
+        if use_cpu_ref and rank != 0:
+            return 0            # the CPU arm runs on rank 0 alone
+
+    if args.impl == "reference" and use_cpu_ref:
+        base = cpu_port_pairs_per_s()
+        line = {"metric": METRIC, "value": base["value"], "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": "flownet2_fwd+conf_512x1024", "global_batch": args.global_batch, "device": "cpu"},
+                "cpu_baseline": base, "gpu_launches": 0,
+                "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the hot path)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark     # True: as the reference does (models/models.py:26)
+
+    from ir2rgb_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(args.global_batch, rank, world)      # contiguous chunk of the global batch
+    B_local = hi - lo
+    mb = min(args.micro_batch, B_local)
+    torch.manual_seed(1234 + rank)
+    im1 = 2 * torch.rand(B_local, 3, H, W, device=device) - 1
+    im2 = 2 * torch.rand(B_local, 3, H, W, device=device) - 1
+    h1, h2 = im1.cpu().pin_memory(), im2.cpu().pin_memory()
+    hflow = torch.empty(B_local, 2, H, W).pin_memory()
+    hconf = torch.empty(B_local, 1, H, W).pin_memory()
+
+    launches = Launches()
+    if args.impl == "native":
+        launches.install()
+        torch.manual_seed(0)
+        net = build_native(device)
+    else:
+        from oracle.harness import OracleFlowNet
+        torch.manual_seed(0)
+        net = OracleFlowNet("ref", device)
+
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+    launches.enabled = True
+    ms_dev = timed(lambda: run_step(net, im1, im2, mb), args.steps, args.warmup, dist, device)
+    n_launch = launches.count * args.steps // max(args.steps + args.warmup, 1)
+    corr_events = launches.corr_events[-(args.steps * ((B_local + mb - 1) // mb)):]
+    launches.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(lambda: run_step(net, h1, h2, mb, host_out=(hflow, hconf)), max(1, args.steps), 1, dist, device)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    line = {"metric": METRIC, "value": args.global_batch / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "flownet2_fwd+conf_512x1024 (BASELINE configs[3])", "global_batch": args.global_batch,
+                       "per_gpu_batch": B_local, "micro_batch": mb, "frame": [H, W], "weights": "random-init",
+                       "conv_math": "cudnn fp32 with TF32 allowed (torch default, same in the reference arm)",
+                       "l2": "inputs larger than L2 (per-rank frames %.0f MB, activations several GB per micro-batch)"
+                             % (2 * B_local * 3 * H * W * 4 / 1e6),
+                       "parallelism": "batch-sharded x%d, no collective on the data path" % world},
+            "clocks": clocks,
+            "e2e": {"value": args.global_batch / (ms_e2e * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": 2 * B_local * 3 * H * W * 4, "d2h_bytes_per_step": B_local * 3 * H * W * 4},
+            "gpu_launches": n_launch}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["gpu_launches"] = 0
+        line["config"]["operators"] = "reference CUDA extensions rebuilt for sm_100 (oracle/_ref), unfused glue"
+        line["cpu_baseline"] = {"value": line["value"], "unit": "pairs/s", "cores": 0, "kind": "reference",
+                                "sample": "reference operators are CUDA-only; this arm ran them on the GPU (see DESIGN.md)"}
+    else:
+        from ir2rgb_b200 import functional as F
+        ffma = F.ffma_peak_tflops()
+        # roofline of the dominant hand-written kernel in the step: Correlation forward (planarize + main)
+        if corr_events:
+            us = [e0.elapsed_time(e1) * 1e3 for e0, e1, _ in corr_events]
+            shp = corr_events[0][2]
+            flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]
+            mean_us = sum(us) / len(us)
+            line["roofline"] = {"kernel": "corr_fwd (corr_planarize + corr_fwd_fast)", "bound": "fp32",
+                                "achieved": flop / mean_us / 1e6, "peak": ffma, "unit": "TFLOP/s",
+                                "frac": flop / mean_us / 1e6 / ffma, "traffic": None,
+                                "peak_source": "flowops_bench_ffma measured on this GPU (nominal 74.4)",
+                                "alg_flop_per_launch": flop, "us_per_launch": mean_us, "launches_timed": len(us),
+                                "share_of_step": sum(us) / args.steps / (ms_dev * 1e3)}
+        line["peaks"] = dict(pk, ffma_tflops=ffma)
+        if not args.no_ops:
+            try:
+                line["ops"] = ops_table(pk, ffma)
+            except Exception as e:      # the table is informative; never lose the headline line over it
+                line["ops"] = {"error": repr(e)}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_port_pairs_per_s()
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

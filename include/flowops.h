@@ -98,6 +98,25 @@ int flowops_corr_bwd(const float *in1, const float *in2, const float *gout,
                      int pad, int k, int md, int s1, int s2,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- Fused FlowNet2 glue (additive; bit-identical to chaining the operators above) ------------ */
+
+/* warped = Resample2d(img1, flow); norm = ChannelNorm(img0 - warped)
+ * (models/flownet2_pytorch/models.py:109-111,121-123,133-137,146-150) in one pass.
+ * img0/img1 are [B,C,H,W] views with a common batch stride (in floats) -- e.g. x[:, :3] and x[:, 3:]
+ * of the 6-channel frame stack, which the reference copies with .contiguous() (resample2d.py:45).
+ * warped ([B,C,H,W], may be NULL when only the error magnitude is needed, models.py:133-137) and
+ * norm ([B,1,H,W]) take their own batch strides so that they can be channel slices of the concat
+ * buffer of models.py:114. */
+int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, size_t img_batch_stride,
+                               const float *flow, float *warped, size_t warped_batch_stride,
+                               float *norm, size_t norm_batch_stride,
+                               int B, int C, int H, int W, void *stream);
+
+/* conf = (sum_c (im1 - Resample2d(im2, flow))^2 < thresh) ? 1 : 0   (models/flownet.py:50,56-57).
+ * im1, im2: [B,C,H,W] contiguous; conf: [B,1,H,W]. */
+int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow, float *conf,
+                          float thresh, int B, int C, int H, int W, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

@@ -1,0 +1,134 @@
+// fused.cu -- FlowNet2 glue kernels: the operator chains that surround
+// the conv body in reference models/flownet2_pytorch/models.py:109-150 and models/flownet.py:50, each
+// collapsed into one pass over HBM.  Additive API: results are bit-identical to running the separate
+// Resample2d / subtract / ChannelNorm operators.
+//
+//   warp_diff_norm : warped = Resample2d(img1, flow); norm = ChannelNorm(img0 - warped)
+//       unfused traffic per pixel (C = 3): warp 8 + .contiguous() copy of the x[:,3:] slice 6 +
+//       subtract 9 + norm 4 = 27 floats;  fused: 3 + 3 + 2 read, 3 + 1 written = 12 floats.
+//       Inputs may be channel slices of a wider tensor (batch stride given), outputs may be channel
+//       slices of the concat buffer the next sub-network reads (models.py:114,126).
+//   warp_conf      : conf = (sum_c (im1 - Resample2d(im2, flow))^2 < thresh) as 0/1 floats
+//       (flownet.py:50,56-57): 3 + 3 + 2 read, 1 written, instead of five elementwise kernels.
+#include "warp.cuh"
+
+namespace flowops {
+
+template <int CT, bool WRITE_WARPED>
+__global__ void __launch_bounds__(256) warp_diff_norm_kernel(const float *__restrict__ img0, const float *__restrict__ img1,
+                                                             size_t img_bs, const float *__restrict__ flow,
+                                                             float *__restrict__ warped, size_t warped_bs,
+                                                             float *__restrict__ norm, size_t norm_bs,
+                                                             int B, int C, int H, int W)
+{
+    const int c_n = CT > 0 ? CT : C;
+    const size_t hw = (size_t)H * W;
+    const size_t total = (size_t)B * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw;
+        const int p = (int)(i - b * hw);
+        const int y = p / W, x = p - y * W;
+        const float dx = ldg_stream(flow + (b * 2) * hw + p);
+        const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
+        float xf, yf; Corners k;
+        r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
+        const R2dWeights w = r2d_weights(xf, yf);
+        const float *src = img1 + b * img_bs;
+        const float *ref = img0 + b * img_bs + p;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < c_n; ++c) {
+            const float *pl = src + (size_t)c * hw;
+            const float val = r2d_blend(w, __ldg(pl + k.o_tl), __ldg(pl + k.o_tr), __ldg(pl + k.o_bl), __ldg(pl + k.o_br));
+            if (WRITE_WARPED) stg_stream(warped + b * warped_bs + (size_t)c * hw + p, val);
+            const float d = __fsub_rn(ldg_stream(ref + (size_t)c * hw), val);   // img0 - warped (models.py:110)
+            acc = __fmaf_rn(d, d, acc);                                        // channelnorm_kernel.cu:55-56
+        }
+        stg_stream(norm + b * norm_bs + p, __fsqrt_rn(acc));
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256) warp_conf_kernel(const float *__restrict__ im1, const float *__restrict__ im2,
+                                                        const float *__restrict__ flow, float *__restrict__ conf,
+                                                        float thresh, int B, int C, int H, int W)
+{
+    const int c_n = CT > 0 ? CT : C;
+    const size_t hw = (size_t)H * W;
+    const size_t total = (size_t)B * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw;
+        const int p = (int)(i - b * hw);
+        const int y = p / W, x = p - y * W;
+        const float dx = ldg_stream(flow + (b * 2) * hw + p);
+        const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
+        float xf, yf; Corners k;
+        r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
+        const R2dWeights w = r2d_weights(xf, yf);
+        const float *src = im2 + b * c_n * hw;
+        const float *ref = im1 + b * c_n * hw + p;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < c_n; ++c) {
+            const float *pl = src + (size_t)c * hw;
+            const float val = r2d_blend(w, __ldg(pl + k.o_tl), __ldg(pl + k.o_tr), __ldg(pl + k.o_bl), __ldg(pl + k.o_br));
+            const float d = __fsub_rn(ldg_stream(ref + (size_t)c * hw), val);
+            // torch.sum(t*t, dim=1): products are rounded before they are added (flownet.py:56-57)
+            acc = c == 0 ? __fmul_rn(d, d) : __fadd_rn(acc, __fmul_rn(d, d));
+        }
+        stg_stream(conf + i, acc < thresh ? 1.f : 0.f);
+    }
+}
+
+static inline unsigned fused_grid(size_t total)
+{
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace flowops
+
+using namespace flowops;
+
+extern "C" int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, size_t img_batch_stride,
+                                          const float *flow, float *warped, size_t warped_batch_stride,
+                                          float *norm, size_t norm_batch_stride,
+                                          int B, int C, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(img0 && img1 && flow && norm, FLOWOPS_EINVAL, "warp_diff_norm_fwd: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "warp_diff_norm_fwd: bad shape %dx%dx%dx%d", B, C, H, W);
+    const size_t hw = (size_t)H * W;
+    FLOWOPS_REQUIRE(img_batch_stride >= (size_t)C * hw && norm_batch_stride >= hw &&
+                    (!warped || warped_batch_stride >= (size_t)C * hw), FLOWOPS_EINVAL,
+                    "warp_diff_norm_fwd: batch stride smaller than one item");
+    FLOWOPS_REQUIRE((size_t)C * hw < (1ull << 31), FLOWOPS_EUNSUPPORTED, "warp_diff_norm_fwd: C*H*W exceeds int32 indexing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = fused_grid((size_t)B * hw);
+#define LAUNCH(CT)                                                                                              \
+    do {                                                                                                        \
+        if (warped) warp_diff_norm_kernel<CT, true><<<grid, 256, 0, st>>>(img0, img1, img_batch_stride, flow,  \
+                        warped, warped_batch_stride, norm, norm_batch_stride, B, C, H, W);                     \
+        else warp_diff_norm_kernel<CT, false><<<grid, 256, 0, st>>>(img0, img1, img_batch_stride, flow,        \
+                        warped, warped_batch_stride, norm, norm_batch_stride, B, C, H, W);                     \
+    } while (0)
+    if (C == 3) LAUNCH(3); else LAUNCH(0);
+#undef LAUNCH
+    return check_launch("warp_diff_norm_fwd");
+}
+
+extern "C" int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow, float *conf,
+                                     float thresh, int B, int C, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(im1 && im2 && flow && conf, FLOWOPS_EINVAL, "warp_conf_fwd: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "warp_conf_fwd: bad shape %dx%dx%dx%d", B, C, H, W);
+    FLOWOPS_REQUIRE((size_t)C * H * W < (1ull << 31), FLOWOPS_EUNSUPPORTED, "warp_conf_fwd: C*H*W exceeds int32 indexing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = fused_grid((size_t)B * H * W);
+    if (C == 3) warp_conf_kernel<3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W);
+    else warp_conf_kernel<0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W);
+    return check_launch("warp_conf_fwd");
+}

@@ -22,31 +22,9 @@
 // products in fp64, the fourth in fp32, fp32 adds in TL,TR,BL,BR order) and is bit-identical to it.
 // GRIDSAMPLE reproduces ATen's fp32 op chain (GridSampler.cuh: unnormalize -> clip -> floor ->
 // weights as differences -> nw,ne,sw,se FFMA chain).
-#include "common.cuh"
+#include "warp.cuh"
 
 namespace flowops {
-
-struct Corners {
-    int o_tl, o_tr, o_bl, o_br;   // offsets inside one H*W plane
-};
-
-// ---------------------------------------------------------------------------------------------
-// coordinate conventions
-// ---------------------------------------------------------------------------------------------
-
-// resample2d_kernel.cu:40-51
-__device__ __forceinline__ void r2d_coords(int x, int y, float dx, float dy, int H, int W,
-                                           float &xf, float &yf, Corners &k)
-{
-    xf = __fadd_rn((float)x, dx);
-    yf = __fadd_rn((float)y, dy);
-    const float fx = floorf(xf), fy = floorf(yf);
-    const int xL = max(min((int)fx, W - 1), 0);
-    const int xR = max(min((int)(__fadd_rn(fx, 1.f)), W - 1), 0);
-    const int yT = max(min((int)fy, H - 1), 0);
-    const int yB = max(min((int)(__fadd_rn(fy, 1.f)), H - 1), 0);
-    k.o_tl = yT * W + xL; k.o_tr = yT * W + xR; k.o_bl = yB * W + xL; k.o_br = yB * W + xR;
-}
 
 // models/networks.py:97-98 + ATen grid_sampler_compute_source_index (align_corners=False, border)
 struct GsCoord {
@@ -100,23 +78,12 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float *__restrict__
         if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
             float xf, yf; Corners k;
             r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
-            const float alpha = __fsub_rn(xf, floorf(xf));
-            const float beta = __fsub_rn(yf, floorf(yf));
-            // resample2d_kernel.cu:55-58: `1.` literals promote the first three products to fp64
-            const double wa = 1. - (double)alpha, wb = 1. - (double)beta;
-            const double w_tl = wa * wb, w_tr = (double)alpha * wb, w_bl = wa * (double)beta;
-            const float w_br = __fmul_rn(alpha, beta);
+            const R2dWeights w = r2d_weights(xf, yf);
 #pragma unroll
             for (int c = 0; c < c_n; ++c) {
                 const float *pl = src + (size_t)c * hw;
-                const float tl = __ldg(pl + k.o_tl), tr = __ldg(pl + k.o_tr);
-                const float bl = __ldg(pl + k.o_bl), br = __ldg(pl + k.o_br);
-                float val = 0.0f;
-                val = __fadd_rn(val, (float)(w_tl * (double)tl));
-                val = __fadd_rn(val, (float)(w_tr * (double)tr));
-                val = __fadd_rn(val, (float)(w_bl * (double)bl));
-                val = __fmaf_rn(w_br, br, val);
-                stg_stream(dst + (size_t)c * hw, val);
+                stg_stream(dst + (size_t)c * hw,
+                           r2d_blend(w, __ldg(pl + k.o_tl), __ldg(pl + k.o_tr), __ldg(pl + k.o_bl), __ldg(pl + k.o_br)));
             }
         } else {
             const GsCoord g = gs_coords(x, y, dx, dy, H, W, lin_x, lin_y, invx, invy);

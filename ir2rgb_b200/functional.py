@@ -117,6 +117,57 @@ def warp_backward(img, flow, gout, need_img=True, need_flow=True, mode=WARP_RESA
 
 
 # ---------------------------------------------------------------------------------------------
+# fused FlowNet2 glue (forward only; used under no_grad)
+# ---------------------------------------------------------------------------------------------
+def _plane_ptr(t, ch):
+    return ctypes.c_void_p(t.data_ptr() + 4 * ch * t.stride(1))
+
+
+def warp_diff_norm_forward(x, flow, out=None, need_warped=True):
+    """x: [B,6,H,W] stack of (frame 0, frame 1), contiguous.  Returns (warped frame 1 or None,
+    |frame 0 - warped| as [B,1,H,W]).  With ``out=(buf, ch_warped, ch_norm)`` the results are written
+    into channels of the preallocated concat buffer ``buf`` instead of fresh tensors."""
+    x = _require(x, "x")
+    flow = _require(flow, "flow").contiguous()
+    B, C6, H, W = x.shape
+    if C6 != 6 or flow.shape != (B, 2, H, W):
+        raise ValueError("expected x [B,6,H,W] and flow [B,2,H,W], got %s and %s" % (tuple(x.shape), tuple(flow.shape)))
+    x = x.contiguous()
+    with torch.cuda.device_of(x):
+        if out is None:
+            warped = torch.empty((B, 3, H, W), device=x.device, dtype=torch.float32) if need_warped else None
+            norm = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+            wp, wbs = _p(warped), 3 * H * W
+            npt, nbs = _p(norm), H * W
+        else:
+            buf, ch_w, ch_n = out
+            assert buf.is_contiguous() and buf.shape[0] == B and tuple(buf.shape[2:]) == (H, W)
+            warped = buf[:, ch_w:ch_w + 3] if need_warped else None
+            norm = buf[:, ch_n:ch_n + 1]
+            wp, wbs = (_plane_ptr(buf, ch_w) if need_warped else _p(None)), buf.stride(0)
+            npt, nbs = _plane_ptr(buf, ch_n), buf.stride(0)
+        if x.numel():
+            check(_lib.load().flowops_warp_diff_norm_fwd(_plane_ptr(x, 0), _plane_ptr(x, 3), x.stride(0), _p(flow),
+                                                         wp, wbs, npt, nbs, B, 3, H, W, _stream()), "warp_diff_norm_fwd")
+    return warped, norm
+
+
+def warp_conf_forward(im1, im2, flow, thresh=0.02):
+    im1 = _require(im1, "im1").contiguous()
+    im2 = _require(im2, "im2").contiguous()
+    flow = _require(flow, "flow").contiguous()
+    B, C, H, W = im1.shape
+    if im2.shape != im1.shape or flow.shape != (B, 2, H, W):
+        raise ValueError("shape mismatch: %s %s %s" % (tuple(im1.shape), tuple(im2.shape), tuple(flow.shape)))
+    with torch.cuda.device_of(im1):
+        conf = torch.empty((B, 1, H, W), device=im1.device, dtype=torch.float32)
+        if im1.numel():
+            check(_lib.load().flowops_warp_conf_fwd(_p(im1), _p(im2), _p(flow), _p(conf), ctypes.c_float(thresh),
+                                                    B, C, H, W, _stream()), "warp_conf_fwd")
+    return conf
+
+
+# ---------------------------------------------------------------------------------------------
 # Correlation
 # ---------------------------------------------------------------------------------------------
 def correlation_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):

@@ -1,0 +1,81 @@
+"""Drop-in for the reference's models/flownet.py (flownet.py:9-60): the vid2vid-side FlowNet2 wrapper
+that turns two frame batches into (flow, confidence).
+
+``FlowNet(**kwargs)`` takes the same keys (fp16, flownet_checkpoint_path, gpu_ids, checkpoints_dir,
+name).  ``flownet_checkpoint_path=None`` gives a random-init FlowNet2 (the 620 MB checkpoint is not
+shipped with the reference; benchmarks run on random weights).  Unlike the reference it does not import
+``flownet2_pytorch.utils.tools`` (which needs ``pytz``).
+
+The confidence mask ``(sum_c (im1 - warp(im2, flow))^2 < 0.02)`` (flownet.py:50) is one libflowops
+kernel (warp + squared error + threshold) instead of a warp, a subtraction, a square, a reduction and
+a comparison.
+"""
+from abc import ABC
+
+import torch
+
+from .. import functional as _F
+from .base_model import Model
+from .flownet2_pytorch import models as flownet2_models
+from .flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d
+
+
+class FlowNet(Model, ABC):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        gpu_ids = self.opt.get('gpu_ids') or [0]
+        self.flowNet = flownet2_models.FlowNet2(fp16=kwargs.get('fp16', False)).cuda(gpu_ids[0])
+        path = kwargs.get('flownet_checkpoint_path')
+        if path:
+            checkpoint = torch.load(path, map_location='cuda:%d' % gpu_ids[0])
+            self.flowNet.load_state_dict(checkpoint['state_dict'])
+        self.flowNet.eval()
+        self.resample = Resample2d()
+        self.downsample = torch.nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+        self.fuse_conf = True
+
+    def forward(self, input_A, input_B, dummy_bs=0):
+        with torch.no_grad():
+            gpu0 = (self.opt.get('gpu_ids') or [0])[0]
+            if input_A.get_device() == gpu0:
+                input_A, input_B = input_A[dummy_bs:], input_B[dummy_bs:]
+                if input_A.size(0) == 0:
+                    b, n, c, h, w = input_A.size()
+                    return self.Tensor(1, n, 2, h, w), self.Tensor(1, n, 1, h, w)
+            size = input_A.size()
+            assert (len(size) == 4 or len(size) == 5)
+            if len(size) == 5:
+                b, n, c, h, w = size
+                input_A = input_A.contiguous().view(-1, c, h, w)
+                input_B = input_B.contiguous().view(-1, c, h, w)
+                flow, conf = self.compute_flow_and_conf(input_A, input_B)
+                return flow.view(b, n, 2, h, w), conf.view(b, n, 1, h, w)
+            else:
+                return self.compute_flow_and_conf(input_A, input_B)
+
+    def compute_flow_and_conf(self, im1, im2):
+        assert (im1.size()[1] == 3)
+        assert (im1.size() == im2.size())
+        old_h, old_w = im1.size()[2], im1.size()[3]
+        new_h, new_w = old_h // 64 * 64, old_w // 64 * 64
+        if old_h != new_h:
+            downsample = torch.nn.Upsample(size=(new_h, new_w), mode='bilinear')
+            upsample = torch.nn.Upsample(size=(old_h, old_w), mode='bilinear')
+            im1 = downsample(im1)
+            im2 = downsample(im2)
+        data1 = torch.cat([im1.unsqueeze(2), im2.unsqueeze(2)], dim=2)
+        flow1 = self.flowNet(data1)
+        if self.fuse_conf and flow1.dtype == torch.float32 and im1.dtype == torch.float32:
+            conf = _F.warp_conf_forward(im1, im2, flow1, 0.02)
+        else:
+            conf = (self.norm(im1 - self.resample(im2, flow1)) < 0.02).float()
+        if old_h != new_h:
+            flow1 = upsample(flow1) * old_h / new_h
+            conf = upsample(conf)
+        return flow1.detach(), conf.detach()
+
+    def norm(self, t):
+        return torch.sum(t * t, dim=1, keepdim=True)
+
+    def save(self, label):
+        pass

@@ -1,0 +1,110 @@
+"""FlowNet2 (reference models/flownet2_pytorch/models.py:30-161; 162,518,834 parameters): the caller
+that fixes how often the hot-path operators run per frame pair -- 1 Correlation (inside FlowNetC),
+4 Resample2d, 6 ChannelNorm (models.py:105-156).
+
+Same constructor (``FlowNet2(args=None, batchNorm=False, div_flow=20., fp16=False)``), same attribute
+names (a reference checkpoint loads with ``load_state_dict``), same arithmetic.  The conv/deconv body
+is stock cuDNN; what is new is the glue between the sub-networks:
+
+  * ``warp -> img0 - warped -> ChannelNorm`` (models.py:109-111,121-123,133-137,146-150) is one
+    libflowops kernel (``flowops_warp_diff_norm_fwd``) that reads frame 0, frame 1 and the flow once
+    and writes the warped frame and the brightness-error magnitude -- instead of three kernels, a
+    ``.contiguous()`` copy of the ``x[:,3:]`` slice (resample2d.py:45) and two intermediate tensors.
+    It is used when no gradient is required (how vid2vid runs FlowNet2, flownet.py:21); with
+    autograd the three separate drop-in operators run, exactly as in the reference.
+"""
+import torch
+import torch.nn as nn
+
+from ... import functional as _F
+from .networks import FlowNetC, FlowNetFusion, FlowNetS, FlowNetSD
+from .networks.channelnorm_package.channelnorm import ChannelNorm
+from .networks.resample2d_package.resample2d import Resample2d
+from .networks.submodules import reference_init
+
+'Parameter count = 162,518,834'
+
+
+class MyDict(dict):
+    pass
+
+
+class fp16_resample2d(nn.Module):
+    def __init__(self):
+        super(fp16_resample2d, self).__init__()
+        self.resample = Resample2d()
+
+    def forward(self, input1, input2):
+        return self.resample(input1.float(), input2.float()).half()
+
+
+class FlowNet2(nn.Module):
+
+    def __init__(self, args=None, batchNorm=False, div_flow=20., fp16=False):
+        super(FlowNet2, self).__init__()
+        if args is None:
+            args = MyDict()
+            args.rgb_max = 1
+            args.fp16 = fp16
+            args.grads = {}
+        self.fp16 = fp16
+        self.batchNorm = batchNorm
+        self.div_flow = div_flow
+        self.rgb_max = args.rgb_max
+        self.args = args
+        self.fuse_glue = True          # use the fused warp/diff/norm kernel when autograd is off
+
+        self.channelnorm = ChannelNorm()
+        self.flownetc = FlowNetC.FlowNetC(args, batchNorm=self.batchNorm)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
+        self.flownets_1 = FlowNetS.FlowNetS(args, batchNorm=self.batchNorm)
+        self.upsample2 = nn.Upsample(scale_factor=4, mode='bilinear')
+        self.flownets_2 = FlowNetS.FlowNetS(args, batchNorm=self.batchNorm)
+        self.flownets_d = FlowNetSD.FlowNetSD(args, batchNorm=self.batchNorm)
+        self.upsample3 = nn.Upsample(scale_factor=4, mode='nearest')
+        self.upsample4 = nn.Upsample(scale_factor=4, mode='nearest')
+        self.resample = Resample2d() if not args.fp16 else fp16_resample2d()
+        self.flownetfusion = FlowNetFusion.FlowNetFusion(args, batchNorm=self.batchNorm)
+        reference_init(self)
+
+    # -- glue ------------------------------------------------------------------------------------
+    def warp_error(self, x, flow):
+        """(warped frame 1, |frame 0 - warped frame 1|) for the 6-channel stack x = [frame0, frame1]."""
+        fusable = (self.fuse_glue and not torch.is_grad_enabled() and x.dtype == torch.float32
+                   and flow.dtype == torch.float32 and x.is_cuda)
+        if fusable:
+            return _F.warp_diff_norm_forward(x, flow)
+        warped = self.resample(x[:, 3:, :, :], flow)
+        return warped, self.channelnorm(x[:, :3, :, :] - warped)
+
+    def forward(self, inputs):
+        rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1).view(inputs.size()[:2] + (1, 1, 1,))
+        x = (inputs - rgb_mean) / self.rgb_max
+        x = torch.cat((x[:, :, 0, :, :], x[:, :, 1, :, :]), dim=1)
+
+        # FlowNetC -> warp -> FlowNetS1 -> warp -> FlowNetS2 (models.py:104-137)
+        flownetc_flow = self.upsample1(self.flownetc(x)[0] * self.div_flow)
+        resampled_img1, norm_diff_img0 = self.warp_error(x, flownetc_flow)
+        concat1 = torch.cat((x, resampled_img1, flownetc_flow / self.div_flow, norm_diff_img0), dim=1)
+
+        flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
+        resampled_img1, norm_diff_img0 = self.warp_error(x, flownets1_flow)
+        concat2 = torch.cat((x, resampled_img1, flownets1_flow / self.div_flow, norm_diff_img0), dim=1)
+
+        flownets2_flow = self.upsample4(self.flownets_2(concat2)[0] * self.div_flow)
+        norm_flownets2_flow = self.channelnorm(flownets2_flow)
+        _, diff_flownets2_img1 = self.warp_error(x, flownets2_flow)
+
+        # FlowNetSD branch (models.py:141-150; note the division by div_flow, reproduced as is)
+        flownetsd_flow = self.upsample3(self.flownets_d(x)[0] / self.div_flow)
+        norm_flownetsd_flow = self.channelnorm(flownetsd_flow)
+        _, diff_flownetsd_img1 = self.warp_error(x, flownetsd_flow)
+
+        concat3 = torch.cat((x[:, :3, :, :], flownetsd_flow, flownets2_flow, norm_flownetsd_flow, norm_flownets2_flow,
+                             diff_flownetsd_img1, diff_flownets2_img1), dim=1)
+        return self.flownetfusion(concat3)
+
+
+class FlowNet2C(FlowNetC.FlowNetC):
+    def __init__(self, args, batchNorm=False, div_flow=20):
+        super(FlowNet2C, self).__init__(args, batchNorm=batchNorm, div_flow=20)

@@ -1,0 +1,83 @@
+"""GPU integration tests: FlowNet2 / FlowNet wrapper with the new operators against the same network with
+(a) the reference's rebuilt CUDA extensions and (b) the pure-PyTorch oracle, same random weights."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def maxrel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def nets(flowops_lib):
+    from ir2rgb_b200.models.flownet import FlowNet
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = False          # remove conv-algorithm noise from the comparison
+    new = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[0], checkpoints_dir=".", name="t").eval()
+    yield new
+    torch.backends.cudnn.allow_tf32 = True
+
+
+def test_state_dict_matches_reference_architecture(nets):
+    arch = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "flownet2_arch.json")))
+    sd = nets.flowNet.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == arch["state_dict"]
+    assert sum(v.numel() for v in sd.values()) == arch["n_params"] == 162518834
+
+
+@pytest.mark.parametrize("kind", ["ref", "torch"])
+def test_flownet_matches_oracle_network(nets, kind):
+    from oracle import ref_ext
+    from oracle.harness import OracleFlowNet
+    if kind == "ref" and not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    torch.manual_seed(3)
+    im1 = 2 * torch.rand(2, 3, 128, 192, device="cuda") - 1
+    im2 = (im1 + 0.05 * torch.randn_like(im1)).clamp(-1, 1)
+    other = OracleFlowNet(kind, "cuda", state_dict=nets.flowNet.state_dict())
+    flow_new, conf_new = nets(im1, im2)
+    flow_ref, conf_ref = other(im1, im2)
+    assert flow_new.shape == (2, 2, 128, 192) and conf_new.shape == (2, 1, 128, 192)
+    # operators agree to ~1e-7; a 100+-layer conv stack amplifies that somewhat
+    assert maxrel(flow_new, flow_ref) <= 1e-3
+    assert (conf_new != conf_ref).float().mean().item() <= 0.01      # hard threshold: compare by flip fraction
+    assert set(conf_new.unique().tolist()) <= {0.0, 1.0}
+
+
+def test_fused_glue_is_bit_identical_to_operator_chain(nets):
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm
+    from ir2rgb_b200.models.flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d
+    torch.manual_seed(4)
+    x = 2 * torch.rand(2, 6, 64, 96, device="cuda") - 1
+    flow = 6 * torch.randn(2, 2, 64, 96, device="cuda")
+    warped, norm = F.warp_diff_norm_forward(x, flow)
+    w_ref = Resample2d()(x[:, 3:], flow)
+    n_ref = ChannelNorm()((x[:, :3] - w_ref).contiguous())
+    assert torch.equal(warped, w_ref) and torch.equal(norm, n_ref)
+    # writing straight into a concat buffer
+    buf = torch.zeros(2, 12, 64, 96, device="cuda")
+    F.warp_diff_norm_forward(x, flow, out=(buf, 6, 11))
+    assert torch.equal(buf[:, 6:9], w_ref) and torch.equal(buf[:, 11:12], n_ref) and buf[:, :6].abs().sum() == 0
+    _, norm_only = F.warp_diff_norm_forward(x, flow, need_warped=False)
+    assert torch.equal(norm_only, n_ref)
+    # confidence mask
+    conf = F.warp_conf_forward(x[:, :3].contiguous(), x[:, 3:].contiguous(), flow, 0.02)
+    t = x[:, :3] - w_ref
+    conf_ref = (torch.sum(t * t, dim=1, keepdim=True) < 0.02).float()
+    assert (conf != conf_ref).float().mean().item() <= 1e-4
+
+
+def test_flownet_wrapper_shapes_and_resize_path(nets):
+    # 5-D input (b, n, c, h, w) and a height that is not a multiple of 64 (flownet.py:27-33,41-47,51-53)
+    a = 2 * torch.rand(1, 2, 3, 96, 128, device="cuda") - 1
+    b = 2 * torch.rand(1, 2, 3, 96, 128, device="cuda") - 1
+    flow, conf = nets(a, b)
+    assert flow.shape == (1, 2, 2, 96, 128) and conf.shape == (1, 2, 1, 96, 128)
+    assert torch.isfinite(flow).all()

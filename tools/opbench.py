@@ -53,11 +53,11 @@ def time_op(fn, iters, warmup=3, flush=None):
     return total / iters * 1e3, best * 1e3      # microseconds (mean, best)
 
 
-def run(iters=20, skip_ref=False, small=False):
+def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
     torch.manual_seed(0)
     pk = peaks()
     flush = L2Flusher()
-    ffma = F.ffma_peak_tflops()
+    ffma = ffma or F.ffma_peak_tflops()
     res = {"peaks": dict(pk, ffma_tflops=ffma, ffma_nominal_tflops=148 * 128 * 2 * 1.965e9 / 1e12), "ops": {}}
     ref = None
     if not skip_ref:
@@ -78,7 +78,8 @@ def run(iters=20, skip_ref=False, small=False):
             rmean, rbest = time_op(ref_fn, ref_iters or max(3, iters // 4), warmup=1, flush=flush)
             e.update(ref_us=rmean, speedup_vs_ref=rmean / mean)
         res["ops"][name] = e
-        print(name, json.dumps(e), flush=True)
+        if not quiet:
+            print(name, json.dumps(e), flush=True)
 
     # ---- C2: Correlation 8x256x48x64 ----
     B, C, H, W = (2, 64, 24, 32) if small else (8, 256, 48, 64)

@@ -1,0 +1,47 @@
+"""Tiny launcher for ncu: runs ONE operator a few times at its BASELINE config.
+    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ir2rgb_b200 import functional as F  # noqa: E402
+
+op = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+torch.manual_seed(0)
+P = (20, 1, 20, 1, 2)
+if op in ("corr_fwd", "corr_bwd"):
+    a, b = torch.randn(8, 256, 48, 64, device="cuda"), torch.randn(8, 256, 48, 64, device="cuda")
+    go = torch.randn(8, 441, 48, 64, device="cuda")
+    fn = (lambda: F.correlation_forward(a, b, *P)) if op == "corr_fwd" else (lambda: F.correlation_backward(a, b, go, *P))
+elif op == "corr_fwd_c4":
+    a, b = torch.randn(8, 256, 64, 128, device="cuda"), torch.randn(8, 256, 64, 128, device="cuda")
+    fn = lambda: F.correlation_forward(a, b, *P)
+else:
+    B, H, W = 16, 512, 1024
+    img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
+    low = 20 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
+    flow = torch.nn.functional.interpolate(low, scale_factor=4, mode="bilinear").contiguous()
+    gout = torch.randn(B, 3, H, W, device="cuda")
+    if op == "warp_fwd":
+        fn = lambda: F.warp_forward(img, flow, F.WARP_RESAMPLE2D)
+    elif op == "warp_bwd":
+        fn = lambda: F.warp_backward(img, flow, gout, True, True, F.WARP_RESAMPLE2D)
+    elif op == "cnorm_fwd":
+        fn = lambda: F.channelnorm_forward(img)
+    elif op == "cnorm_bwd":
+        y = F.channelnorm_forward(img)
+        gy = torch.randn_like(y)
+        fn = lambda: F.channelnorm_backward(img, y, gy)
+    elif op == "fused":
+        x = torch.cat([img, img.flip(0)], 1).contiguous()
+        fn = lambda: F.warp_diff_norm_forward(x, flow)
+    else:
+        raise SystemExit("unknown op " + op)
+for _ in range(reps):
+    fn()
+torch.cuda.synchronize()
+print("ok", op)

@@ -24,6 +24,8 @@
 //
 // Roofline: FP32-FMA pipe.  Algorithmic work 2*B*H*W*441*C FLOP (dense count, taps that fall in
 // the zero padding included -- the kernel does not skip them).
+#include <stdlib.h>
+
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is resolved at run time (no libcuda link)
 
 #include "corr.cuh"
@@ -169,9 +171,30 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm,
         :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
+// acc / nelems (reference correlation_cuda_kernel.cu:143) without the call-based divide sequence, which
+// would spill the 168 live accumulators: q = t * (1/n), one residual correction.  Exact for a power-of-
+// two channel count (FlowNetC: 256) and correctly rounded otherwise up to rare last-bit cases.
+__device__ __forceinline__ float div_nelems(float t, float n, float inv_n)
+{
+    const float q = t * inv_n;
+    return __fmaf_rn(__fmaf_rn(-q, n, t), inv_n, q);
+}
+
+// packed FP32 FMA (Blackwell FFMA2): d = a * b + c on both halves, round-to-nearest each
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+template <int UNROLL>
 __global__ void __launch_bounds__(256, 1)
 corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
               float *__restrict__ out, int C, int H, int W, int row_tiles, int x_tiles)
@@ -217,11 +240,20 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
         for (int s = 0; s < kStages && s < n_it; ++s) issue(s, s);
     }
 
-    float acc[kD][kPX];
+    // Accumulators.  The FP32 pipe only sustains its rate when register-file traffic is low: a scalar
+    // FFMA with three distinct source registers runs this sliding-window pattern at 54 % of peak on B200
+    // (register-bank conflicts), the packed fma.rn.f32x2 form at 87 % (tools/ffma_probe.cu).  So the
+    // 21 x 8 tile is held as 64-bit pairs over the displacement index i, paired where i + k is even so
+    // that (w[i+k], w[i+k+1]) is an aligned register pair straight out of an LDS.128:
+    //   even k: pairs (i = 2p, 2p+1), p = 0..9, single i = 20;   odd k: single i = 0, pairs (i = 2p+1, 2p+2)
+    float2 accp[kPX][10];
+    float accs[kPX];
 #pragma unroll
-    for (int i = 0; i < kD; ++i)
+    for (int k = 0; k < kPX; ++k) {
+        accs[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < kPX; ++k) acc[i][k] = 0.f;
+        for (int p = 0; p < 10; ++p) accp[k][p] = make_float2(0.f, 0.f);
+    }
 
     const int f2_off = (yi + tj) * kF2W + xb * kPX;
     const int f1_off = yi * kF1W + xb * kPX;
@@ -231,9 +263,10 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
         mbar_wait(bar_base + 8 * slot, (it / kStages) & 1);
         const float *f2s = reinterpret_cast<const float *>(smem + slot * kStageBytes) + f2_off;
         const float *f1s = reinterpret_cast<const float *>(smem + slot * kStageBytes) + kF2Floats + f1_off;
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int ck = 0; ck < kCK; ++ck) {
-            float a[kPX], w[kPX + kD - 1];
+            float a[kPX];
+            float2 w2[(kPX + kD - 1) / 2];       // w2[j] = (w[2j], w[2j+1])
             const float4 *pa = reinterpret_cast<const float4 *>(f1s + ck * (kTY * kF1W));
             const float4 *pw = reinterpret_cast<const float4 *>(f2s + ck * (kF2H * kF2W));
 #pragma unroll
@@ -244,12 +277,19 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
 #pragma unroll
             for (int q = 0; q < (kPX + kD - 1) / 4; ++q) {
                 const float4 v = pw[q];
-                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                w2[2 * q] = make_float2(v.x, v.y); w2[2 * q + 1] = make_float2(v.z, v.w);
             }
 #pragma unroll
-            for (int i = 0; i < kD; ++i)
+            for (int k = 0; k < kPX; ++k) {
+                const float2 ad = make_float2(a[k], a[k]);
 #pragma unroll
-                for (int k = 0; k < kPX; ++k) acc[i][k] = __fmaf_rn(a[k], w[i + k], acc[i][k]);
+                for (int p = 0; p < 10; ++p) {
+                    const int j = (k & 1) ? (2 * p + 1 + k) / 2 : (2 * p + k) / 2;
+                    accp[k][p] = fma2(ad, w2[j], accp[k][p]);
+                }
+                accs[k] = (k & 1) ? __fmaf_rn(a[k], w2[k / 2].y, accs[k])
+                                  : __fmaf_rn(a[k], w2[(kD - 1 + k) / 2].x, accs[k]);
+            }
         }
         __syncthreads();                              // every warp is done with this slot
         if (tid == 0 && it + kStages < n_it) issue(it + kStages, slot);
@@ -259,6 +299,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
     // (the last loop iteration ended with __syncthreads and no TMA is in flight)
     float *stage = reinterpret_cast<float *>(smem);
     const float nelems = (float)C;
+    const float inv_nelems = 1.0f / nelems;
     const size_t hw = (size_t)H * W;
     float *out_n = out + (size_t)n * (kD * kD) * hw;
 #pragma unroll 1
@@ -267,25 +308,30 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
             float *dst = stage + ((tj - grp * kEpiGroup) * kD * kTY + yi) * kEpiPitch + xb * kPX;
 #pragma unroll
             for (int i = 0; i < kD; ++i) {
-                float4 lo, hi;
-                lo.x = __fdiv_rn(acc[i][0], nelems); lo.y = __fdiv_rn(acc[i][1], nelems);
-                lo.z = __fdiv_rn(acc[i][2], nelems); lo.w = __fdiv_rn(acc[i][3], nelems);
-                hi.x = __fdiv_rn(acc[i][4], nelems); hi.y = __fdiv_rn(acc[i][5], nelems);
-                hi.z = __fdiv_rn(acc[i][6], nelems); hi.w = __fdiv_rn(acc[i][7], nelems);
-                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch)) = lo;
-                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch) + 4) = hi;
+                float v[kPX];
+#pragma unroll
+                for (int k = 0; k < kPX; ++k) {
+                    float t;
+                    if (k & 1) t = (i == 0) ? accs[k] : (((i - 1) & 1) ? accp[k][(i - 1) / 2].y : accp[k][(i - 1) / 2].x);
+                    else       t = (i == kD - 1) ? accs[k] : ((i & 1) ? accp[k][i / 2].y : accp[k][i / 2].x);
+                    v[k] = div_nelems(t, nelems, inv_nelems);
+                }
+                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch)) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(dst + i * (kTY * kEpiPitch) + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
         __syncthreads();
+        // each warp takes (tj-in-group, row) pairs and walks the 21 horizontal displacements with
+        // constant strides: one LDS + one STG per output row segment
         const int x = 2 * (x0 + lane) + px;
-        for (int row = warp; row < kEpiRows; row += 8) {
-            const int tjl = row / (kD * kTY);
-            const int rem = row - tjl * (kD * kTY);
-            const int ti = rem / kTY, ry = rem - ti * kTY;
+        for (int pr = warp; pr < kEpiGroup * kTY; pr += 8) {
+            const int tjl = pr / kTY, ry = pr - tjl * kTY;
             const int y = 2 * (y0 + ry) + py;
             if (y < H && x < W) {
-                const int tc = (grp * kEpiGroup + tjl) * kD + ti;
-                out_n[(size_t)tc * hw + (size_t)y * W + x] = stage[row * kEpiPitch + lane];
+                const float *src = stage + (tjl * (kD * kTY) + ry) * kEpiPitch + lane;
+                float *dst = out_n + (size_t)((grp * kEpiGroup + tjl) * kD) * hw + (size_t)y * W + x;
+#pragma unroll
+                for (int ti = 0; ti < kD; ++ti) dst[(size_t)ti * hw] = src[ti * (kTY * kEpiPitch)];
             }
         }
         __syncthreads();
@@ -359,16 +405,19 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
     rc = make_plane_map(&tm2, P2, g, p.Hp, p.pitch2, kF2W, kF2H);
     if (rc) return rc;
 
+    static const int unroll = getenv("FLOWOPS_CORR_UNROLL") ? atoi(getenv("FLOWOPS_CORR_UNROLL")) : 2;   // dev knob
+    auto kernel = unroll == 1 ? corr_fwd_fast<1> : corr_fwd_fast<2>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
     const int row_tiles = (p.Hp + kTY - 1) / kTY, x_tiles = (p.Wp + kTX - 1) / kTX;
     const size_t grid = (size_t)g.B * row_tiles * x_tiles * 4;
     FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
-    corr_fwd_fast<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
+    kernel<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
     return check_launch("corr_fwd_fast");
 }
 

@@ -224,7 +224,7 @@ def correlation_backward(in1, in2, gout, pad_size, kernel_size, max_displacement
 # ---------------------------------------------------------------------------------------------
 # measurement helper
 # ---------------------------------------------------------------------------------------------
-def ffma_peak_tflops(iters=4096, reps=5):
+def ffma_peak_tflops(iters=20000, reps=5):
     """Measured FP32-FMA pipe throughput of this GPU (TFLOP/s): the Correlation roofline denominator."""
     lib = _lib.load()
     sink = torch.zeros(4, device="cuda")

@@ -26,9 +26,8 @@
 // the zero padding included -- the kernel does not skip them).
 #include <stdlib.h>
 
-#include <cuda.h>   // CUtensorMap + enums only; the encoder is resolved at run time (no libcuda link)
-
 #include "corr.cuh"
+#include "tma.cuh"
 
 namespace flowops {
 
@@ -137,58 +136,6 @@ __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ 
                 }
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA / mbarrier primitives
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
-
-// acc / nelems (reference correlation_cuda_kernel.cu:143) without the call-based divide sequence, which
-// would spill the 168 live accumulators: q = t * (1/n), one residual correction.  Exact for a power-of-
-// two channel count (FlowNetC: 256) and correctly rounded otherwise up to rare last-bit cases.
-__device__ __forceinline__ float div_nelems(float t, float n, float inv_n)
-{
-    const float q = t * inv_n;
-    return __fmaf_rn(__fmaf_rn(-q, n, t), inv_n, q);
-}
-
-// packed FP32 FMA (Blackwell FFMA2): d = a * b + c on both halves, round-to-nearest each
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
-{
-    float2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(*reinterpret_cast<unsigned long long *>(&d))
-        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
-          "l"(*reinterpret_cast<unsigned long long *>(&c)));
-    return d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,37 +288,13 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encoder()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, int Hp, int pitch, int box_w, int box_h)
 {
-    EncodeTiledFn enc = get_encoder();
-    FLOWOPS_REQUIRE(enc, FLOWOPS_EUNSUPPORTED, "corr: cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t plane_bytes = (cuuint64_t)Hp * pitch * 4;
     const cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)Hp, (cuuint64_t)g.C, (cuuint64_t)g.B * 4};
     const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, plane_bytes, plane_bytes * g.C};
     const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)kCK, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FLOWOPS_REQUIRE(r == CUDA_SUCCESS, FLOWOPS_EINVAL, "corr: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return 0;
+    return encode_map4(tm, base, dims, strides, box, "corr_fwd");
 }
 
 int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g,
@@ -419,16 +342,6 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
     FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
     kernel<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
     return check_launch("corr_fwd_fast");
-}
-
-// The backward still runs the generic gather kernels (corr_generic.cu); a tiled version is the next
-// step for this file.
-size_t corr_fast_bwd_workspace(const CorrGeom &) { return 0; }
-
-int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
-                         const CorrGeom &g, void *, size_t, cudaStream_t st)
-{
-    return corr_bwd_generic_launch(in1, in2, gout, gin1, gin2, g, st);
 }
 
 }  // namespace flowops

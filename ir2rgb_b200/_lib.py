@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflowops.so")
+LIB_PATH = os.environ.get("FLOWOPS_LIB") or os.path.join(_HERE, "libflowops.so")   # env override: development builds
 
 WARP_RESAMPLE2D = 0
 WARP_GRIDSAMPLE = 1

@@ -107,7 +107,10 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
     img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
     gout = torch.randn(B, 3, H, W, device="cuda")
     low = 20 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
+    coarse = 20 * torch.randn(B, 2, max(H // 64, 2), max(W // 64, 2), device="cuda")
     flows = {
+        # realistic optical flow: smooth field, |flow| ~ 20 px, gradient well below 1 px/px
+        "smooth": torch.nn.functional.interpolate(coarse, size=(H, W), mode="bicubic", align_corners=False).contiguous(),
         "randn": 4 * torch.randn(B, 2, H, W, device="cuda"),
         "bilinear": torch.nn.functional.interpolate(low, scale_factor=4, mode="bilinear").contiguous(),
         "nearest": torch.nn.functional.interpolate(low, scale_factor=4, mode="nearest").contiguous(),

@@ -23,8 +23,8 @@ elif op == "corr_fwd_c4":
 else:
     B, H, W = 16, 512, 1024
     img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
-    low = 20 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
-    flow = torch.nn.functional.interpolate(low, scale_factor=4, mode="bilinear").contiguous()
+    coarse = 20 * torch.randn(B, 2, H // 64, W // 64, device="cuda")      # smooth, realistic flow field
+    flow = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bicubic", align_corners=False).contiguous()
     gout = torch.randn(B, 3, H, W, device="cuda")
     if op == "warp_fwd":
         fn = lambda: F.warp_forward(img, flow, F.WARP_RESAMPLE2D)

@@ -44,11 +44,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-ops", action="store_true", help="skip the per-operator roofline table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
+    ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
+                    help="layout of the FlowNet2 conv body in the native arm (the reference arm keeps the stock NCHW)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="keep cuDNN autotuning launches out of ncu launch lists")
     return ap.parse_args()
 
@@ -138,9 +140,14 @@ class Launches:
             setattr(F, name, wrapped)
 
 
-def build_native(device):
+def build_native(device, memory_format="channels_last"):
+    import torch
     from ir2rgb_b200.models.flownet import FlowNet
     net = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[device.index], checkpoints_dir=".", name="bench")
+    if memory_format == "channels_last":
+        # conv body tuning: NHWC weights/activations let cuDNN run its tensor-op kernels
+        # without the NCHW<->NHWC transposes that take ~30 % of the stock forward (profiles/launches_r01_*)
+        net.flowNet = net.flowNet.to(memory_format=torch.channels_last)
     return net.eval()
 
 
@@ -274,7 +281,7 @@ def main():
     if args.impl == "native":
         launches.install()
         torch.manual_seed(0)
-        net = build_native(device)
+        net = build_native(device, args.memory_format)
     else:
         from oracle.harness import OracleFlowNet
         torch.manual_seed(0)
@@ -303,6 +310,7 @@ def main():
             "config": {"workload": "flownet2_fwd+conf_512x1024 (BASELINE configs[3])", "global_batch": args.global_batch,
                        "per_gpu_batch": B_local, "micro_batch": mb, "frame": [H, W], "weights": "random-init",
                        "conv_math": "cudnn fp32 with TF32 allowed (torch default, same in the reference arm)",
+                       "conv_layout": args.memory_format if args.impl == "native" else "contiguous",
                        "l2": "inputs larger than L2 (per-rank frames %.0f MB, activations several GB per micro-batch)"
                              % (2 * B_local * 3 * H * W * 4 / 1e6),
                        "parallelism": "batch-sharded x%d, no collective on the data path" % world},

@@ -117,6 +117,14 @@ int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, size_t img_
 int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow, float *conf,
                           float thresh, int B, int C, int H, int W, void *stream);
 
+/* ---- Conv-body epilogue (FlowNet2 inference glue, not an operator of the reference's native surface) ---- */
+
+/* In place: t = y + bias[c]; y = t > 0 ? t : t * slope.  Replaces the separate bias-add and LeakyReLU kernels
+ * that follow every convolution built by submodules.py:7-38 (conv / deconv).  y is [N,C,H,W] stored NCHW
+ * (channels_last = 0) or NHWC (channels_last = 1); HW = H*W. */
+int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int HW, int channels_last,
+                       float slope, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

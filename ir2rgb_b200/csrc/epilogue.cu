@@ -1,0 +1,75 @@
+// epilogue.cu -- conv-body glue for FlowNet2 inference: per-channel bias add
+// + LeakyReLU in ONE in-place pass over the convolution output.
+//
+// The stock path (reference submodules.py:7-38 -> cuDNN) runs three kernels per conv layer: the
+// convolution, an elementwise bias add and an in-place LeakyReLU -- 19 % + 7 % of a channels_last FlowNet2
+// forward on B200 (profiles/torchprof_flownet_cl_r01.txt).  This kernel does `t = y + b[c];
+// y = t > 0 ? t : t * slope` with 128-bit accesses, bit-identical to the two torch kernels it replaces.
+// HBM-bound: 8 bytes per element (one read, one write).
+#include "common.cuh"
+
+namespace flowops {
+
+__device__ __forceinline__ float lrelu(float t, float slope) { return t > 0.f ? t : __fmul_rn(t, slope); }
+
+// channels-last: y[n][hw][c], C % 4 == 0
+__global__ void __launch_bounds__(256) bias_lrelu_nhwc(float *__restrict__ y, const float *__restrict__ bias,
+                                                       size_t total4, unsigned c4n, float slope)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned c4 = (unsigned)(i % c4n);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+        float4 v = *reinterpret_cast<float4 *>(y + i * 4);
+        v.x = lrelu(__fadd_rn(v.x, b.x), slope); v.y = lrelu(__fadd_rn(v.y, b.y), slope);
+        v.z = lrelu(__fadd_rn(v.z, b.z), slope); v.w = lrelu(__fadd_rn(v.w, b.w), slope);
+        *reinterpret_cast<float4 *>(y + i * 4) = v;
+    }
+}
+
+// NCHW: y[n][c][hw], HW % 4 == 0
+__global__ void __launch_bounds__(256) bias_lrelu_nchw(float *__restrict__ y, const float *__restrict__ bias,
+                                                       size_t total4, unsigned hw4, unsigned C, float slope)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const float b = __ldg(bias + (unsigned)((i / hw4) % C));
+        float4 v = *reinterpret_cast<float4 *>(y + i * 4);
+        v.x = lrelu(__fadd_rn(v.x, b), slope); v.y = lrelu(__fadd_rn(v.y, b), slope);
+        v.z = lrelu(__fadd_rn(v.z, b), slope); v.w = lrelu(__fadd_rn(v.w, b), slope);
+        *reinterpret_cast<float4 *>(y + i * 4) = v;
+    }
+}
+
+// any shape / alignment
+__global__ void __launch_bounds__(256) bias_lrelu_scalar(float *__restrict__ y, const float *__restrict__ bias,
+                                                         size_t total, size_t inner, unsigned C, int channels_last, float slope)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned c = channels_last ? (unsigned)(i % C) : (unsigned)((i / inner) % C);
+        y[i] = lrelu(__fadd_rn(y[i], __ldg(bias + c)), slope);
+    }
+}
+
+}  // namespace flowops
+
+using namespace flowops;
+
+extern "C" int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int HW, int channels_last,
+                                  float slope, void *stream)
+{
+    FLOWOPS_REQUIRE(y && bias, FLOWOPS_EINVAL, "bias_lrelu: null pointer");
+    FLOWOPS_REQUIRE(N > 0 && C > 0 && HW > 0, FLOWOPS_EINVAL, "bias_lrelu: bad shape %d x %d x %d", N, C, HW);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t total = (size_t)N * C * HW;
+    auto grid_for = [](size_t items) {
+        size_t blocks = (items + 255) / 256;
+        const size_t cap = (size_t)kNumSMs * 8 * 16;
+        return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+    };
+    if (channels_last && (C & 3) == 0 && aligned16(y) && aligned16(bias))
+        bias_lrelu_nhwc<<<grid_for(total / 4), 256, 0, st>>>(y, bias, total / 4, (unsigned)(C / 4), slope);
+    else if (!channels_last && (HW & 3) == 0 && aligned16(y))
+        bias_lrelu_nchw<<<grid_for(total / 4), 256, 0, st>>>(y, bias, total / 4, (unsigned)(HW / 4), (unsigned)C, slope);
+    else
+        bias_lrelu_scalar<<<grid_for(total), 256, 0, st>>>(y, bias, total, (size_t)HW, (unsigned)C, channels_last, slope);
+    return check_launch("bias_lrelu");
+}

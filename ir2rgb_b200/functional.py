@@ -167,6 +167,25 @@ def warp_conf_forward(im1, im2, flow, thresh=0.02):
     return conf
 
 
+def bias_lrelu_(y, bias, slope):
+    """In-place per-channel bias add + LeakyReLU on a conv output (NCHW- or channels_last-contiguous)."""
+    y = _require(y, "y")
+    N, C, H, W = y.shape
+    if y.is_contiguous():
+        cl = 0
+    elif y.is_contiguous(memory_format=torch.channels_last):
+        cl = 1
+    else:
+        raise ValueError("bias_lrelu_: tensor must be dense in NCHW or channels_last order")
+    if bias.shape != (C,) or bias.dtype != torch.float32 or bias.device != y.device or not bias.is_contiguous():
+        raise ValueError("bias_lrelu_: bias must be a contiguous fp32 [C] tensor on the same device")
+    if y.numel():
+        with torch.cuda.device_of(y):
+            check(_lib.load().flowops_bias_lrelu(_p(y), _p(bias), N, C, H * W, cl, ctypes.c_float(slope), _stream()),
+                  "bias_lrelu")
+    return y
+
+
 # ---------------------------------------------------------------------------------------------
 # Correlation
 # ---------------------------------------------------------------------------------------------

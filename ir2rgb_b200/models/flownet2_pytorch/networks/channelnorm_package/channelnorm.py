@@ -34,4 +34,5 @@ class ChannelNorm(Module):
         self.norm_deg = norm_deg
 
     def forward(self, input1):
-        return ChannelNormFunction.apply(input1, self.norm_deg)
+        # .contiguous() is free for NCHW tensors and lets channels_last activations through
+        return ChannelNormFunction.apply(input1.contiguous(), self.norm_deg)

@@ -43,4 +43,4 @@ class Resample2d(Module):
 
     def forward(self, input1, input2):
         input1_c = input1.contiguous()
-        return Resample2dFunction.apply(input1_c, input2, self.kernel_size)
+        return Resample2dFunction.apply(input1_c, input2.contiguous(), self.kernel_size)

@@ -7,8 +7,30 @@ checkpoint of the reference loads unchanged.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from .... import functional as _F
 
 LEAK = 0.1
+FUSE_EPILOGUE = True      # inference only: conv -> one libflowops pass for bias + LeakyReLU
+
+
+class ConvAct(nn.Sequential):
+    """(Conv2d | ConvTranspose2d) + LeakyReLU with the reference's nn.Sequential indexing (so `conv1.0.weight`
+    keeps its name).  Under no_grad on CUDA fp32 the bias add and the activation run as one in-place
+    libflowops kernel after a bias-free convolution -- bit-identical to conv(+bias) -> LeakyReLU."""
+
+    def forward(self, x):
+        conv = self[0]
+        if (FUSE_EPILOGUE and len(self) == 2 and conv.bias is not None and not torch.is_grad_enabled()
+                and x.is_cuda and x.dtype == torch.float32):
+            if isinstance(conv, nn.ConvTranspose2d):
+                y = F.conv_transpose2d(x, conv.weight, None, conv.stride, conv.padding, conv.output_padding,
+                                       conv.groups, conv.dilation)
+            else:
+                y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            return _F.bias_lrelu_(y, conv.bias, self[1].negative_slope)
+        return super().forward(x)
 
 
 def conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1):
@@ -16,7 +38,7 @@ def conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1):
     if batchNorm:
         layers.append(nn.BatchNorm2d(out_planes))
     layers.append(nn.LeakyReLU(LEAK, inplace=True))
-    return nn.Sequential(*layers)
+    return ConvAct(*layers)
 
 
 def i_conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1, bias=True):
@@ -31,7 +53,7 @@ def predict_flow(in_planes):
 
 
 def deconv(in_planes, out_planes):
-    return nn.Sequential(nn.ConvTranspose2d(in_planes, out_planes, 4, 2, 1, bias=True), nn.LeakyReLU(LEAK, inplace=True))
+    return ConvAct(nn.ConvTranspose2d(in_planes, out_planes, 4, 2, 1, bias=True), nn.LeakyReLU(LEAK, inplace=True))
 
 
 def flow_upsampler(bias=True):

@@ -81,3 +81,33 @@ def test_flownet_wrapper_shapes_and_resize_path(nets):
     flow, conf = nets(a, b)
     assert flow.shape == (1, 2, 2, 96, 128) and conf.shape == (1, 2, 1, 96, 128)
     assert torch.isfinite(flow).all()
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("kind,cin,cout,k,s", [("conv", 12, 64, 7, 2), ("conv", 64, 66, 3, 1), ("deconv", 34, 16, 4, 2)])
+def test_fused_bias_lrelu_is_bit_identical(flowops_lib, channels_last, kind, cin, cout, k, s):
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(5)
+    mod = (sm.conv(False, cin, cout, kernel_size=k, stride=s) if kind == "conv" else sm.deconv(cin, cout)).cuda()
+    x = torch.randn(2, cin, 24, 40, device="cuda")
+    if channels_last:
+        mod = mod.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    prev, prev_det = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True       # cuDNN's transposed-conv algorithms may otherwise use atomics
+    try:
+        with torch.no_grad():
+            fused = mod(x)
+            sm.FUSE_EPILOGUE = False
+            try:
+                plain = mod(x)
+            finally:
+                sm.FUSE_EPILOGUE = True
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic = prev, prev_det
+    assert torch.equal(fused, plain)
+    # with autograd enabled the stock path runs (and is differentiable)
+    y = mod(x.requires_grad_())
+    y.sum().backward()
+    assert x.grad is not None

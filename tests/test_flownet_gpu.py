@@ -111,3 +111,25 @@ def test_fused_bias_lrelu_is_bit_identical(flowops_lib, channels_last, kind, cin
     y = mod(x.requires_grad_())
     y.sum().backward()
     assert x.grad is not None
+
+
+def test_graphed_flownet_matches_eager(nets):
+    from ir2rgb_b200.runtime import GraphedFlowNet
+    torch.manual_seed(6)
+    a = 2 * torch.rand(2, 3, 64, 128, device="cuda") - 1
+    b = 2 * torch.rand(2, 3, 64, 128, device="cuda") - 1
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        flow_e, conf_e = nets(a, b)
+        g = GraphedFlowNet(nets)
+        flow_g, conf_g = g(a, b)
+        flow_g2, _ = g(a.cpu().pin_memory(), b.cpu().pin_memory())     # pinned host inputs, same graph
+        a2 = a.flip(0).contiguous()
+        flow_g3, _ = g(a2, b)                                          # new data through the replayed graph
+        flow_e3, _ = nets(a2, b)
+    finally:
+        torch.backends.cudnn.deterministic = prev
+    assert torch.equal(flow_g, flow_e) and torch.equal(conf_g, conf_e)
+    assert torch.equal(flow_g2, flow_e)
+    assert torch.equal(flow_g3, flow_e3)

@@ -63,17 +63,17 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float *__restrict__
                                                        float invx, float invy)
 {
     const int c_n = CT > 0 ? CT : C;
-    const size_t hw = (size_t)H * W;
-    const size_t total = (size_t)B * hw;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / hw;
-        const int p = (int)(i - b * hw);
-        const int y = p / W, x = p - y * W;
-        const float dx = ldg_stream(flow + (b * 2) * hw + p);
-        const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
-        const float *src = img + b * c_n * hw;
-        float *dst = out + b * c_n * hw + p;
+    // 2-D thread blocks over (x, y), batch in grid.z: no integer divisions, 32-bit in-plane offsets
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const unsigned hw = (unsigned)H * W;
+    const unsigned p = (unsigned)y * W + x;
+    for (int b = blockIdx.z; b < B; b += gridDim.z) {
+        const float dx = ldg_stream(flow + ((size_t)b * 2) * hw + p);
+        const float dy = ldg_stream(flow + ((size_t)b * 2 + 1) * hw + p);
+        const float *src = img + (size_t)b * c_n * hw;
+        float *dst = out + (size_t)b * c_n * hw + p;
 
         if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
             float xf, yf; Corners k;
@@ -268,15 +268,25 @@ static inline unsigned warp_grid(size_t total)
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// 256-thread blocks shaped to the image width: whole warps lie along x (coalescing, and the backward's
+// lane-neighbour merging), rows fill the rest of the block
+static inline void warp_launch_shape(int B, int H, int W, dim3 &grid, dim3 &block)
+{
+    const int bx = W >= 256 ? 256 : (W > 64 ? 128 : (W > 32 ? 64 : 32));
+    block = dim3(bx, 256 / bx, 1);
+    grid = dim3((W + bx - 1) / bx, (H + block.y - 1) / block.y, B < 65535 ? B : 65535);
+}
+
 template <int MODE>
 static int launch_fwd(const float *img, const float *flow, float *out, int B, int C, int H, int W,
                       const float *lx, const float *ly, float invx, float invy, cudaStream_t st)
 {
-    const unsigned grid = warp_grid((size_t)B * H * W);
-    if (C == 3) warp_fwd_kernel<MODE, 3><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else if (C == 2) warp_fwd_kernel<MODE, 2><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else if (C == 1) warp_fwd_kernel<MODE, 1><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else warp_fwd_kernel<MODE, 0><<<grid, 256, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    dim3 grid, block;
+    warp_launch_shape(B, H, W, grid, block);
+    if (C == 3) warp_fwd_kernel<MODE, 3><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else if (C == 2) warp_fwd_kernel<MODE, 2><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else if (C == 1) warp_fwd_kernel<MODE, 1><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    else warp_fwd_kernel<MODE, 0><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
     return check_launch("warp_fwd");
 }
 

@@ -50,3 +50,55 @@ class GraphedFlowNet(torch.nn.Module):
         sb.copy_(input_B, non_blocking=True)
         g.replay()
         return tuple(o.clone() for o in out)
+
+
+class HostPipeline:
+    """Runs `net(a, b) -> (flow, conf)` over a batch that lives in PINNED HOST memory, micro-batch by micro-batch,
+    with the host->device copy of micro-batch i+1 and the device->host copy of the results of micro-batch i-1
+    overlapping the computation of micro-batch i (three streams, double-buffered staging)."""
+
+    def __init__(self, net, device):
+        self.net, self.device = net, device
+        self.copy_in = torch.cuda.Stream(device=device)
+        self.copy_out = torch.cuda.Stream(device=device)
+        self._staging = {}
+
+    def _buffers(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        if key not in self._staging:
+            mk = lambda: torch.empty(shape, dtype=dtype, device=self.device)
+            self._staging[key] = ([mk(), mk()], [mk(), mk()],
+                                  [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()])
+            # the caching allocator may hand out blocks that earlier kernels on the compute stream still use:
+            # order the copy stream after everything already queued there before it first writes the new buffers
+            self.copy_in.wait_stream(torch.cuda.current_stream(self.device))
+        return self._staging[key]
+
+    @torch.no_grad()
+    def __call__(self, host_a, host_b, micro_batch, out_flow, out_conf):
+        compute = torch.cuda.current_stream(self.device)
+        B = host_a.shape[0]
+        last = None
+        for i, s in enumerate(range(0, B, micro_batch)):
+            n = min(micro_batch, B - s)
+            sa, sb, ready, free = self._buffers((n,) + tuple(host_a.shape[1:]), host_a.dtype)
+            k = i & 1
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(free[k])                   # staging slot k was consumed two micro-batches ago
+                sa[k].copy_(host_a[s:s + n], non_blocking=True)
+                sb[k].copy_(host_b[s:s + n], non_blocking=True)
+                ready[k].record(self.copy_in)
+            compute.wait_event(ready[k])
+            flow, conf = self.net(sa[k], sb[k])
+            free[k].record(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(done)
+                out_flow[s:s + n].copy_(flow, non_blocking=True)
+                out_conf[s:s + n].copy_(conf, non_blocking=True)
+            flow.record_stream(self.copy_out)
+            conf.record_stream(self.copy_out)
+            last = flow
+        compute.wait_stream(self.copy_out)
+        return last

@@ -133,3 +133,21 @@ def test_graphed_flownet_matches_eager(nets):
     assert torch.equal(flow_g, flow_e) and torch.equal(conf_g, conf_e)
     assert torch.equal(flow_g2, flow_e)
     assert torch.equal(flow_g3, flow_e3)
+
+
+def test_host_pipeline_matches_direct_calls(nets):
+    from ir2rgb_b200.runtime import HostPipeline
+    torch.manual_seed(7)
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        h1 = (2 * torch.rand(5, 3, 64, 128) - 1).pin_memory()
+        h2 = (2 * torch.rand(5, 3, 64, 128) - 1).pin_memory()
+        hflow, hconf = torch.empty(5, 2, 64, 128).pin_memory(), torch.empty(5, 1, 64, 128).pin_memory()
+        HostPipeline(nets, torch.device("cuda", 0))(h1, h2, 2, hflow, hconf)       # micro-batches of 2, 2, 1
+        torch.cuda.synchronize()
+        for s in (0, 2, 4):
+            f, c = nets(h1[s:s + 2].cuda(), h2[s:s + 2].cuda())
+            assert torch.equal(hflow[s:s + 2], f.cpu()) and torch.equal(hconf[s:s + 2], c.cpu())
+    finally:
+        torch.backends.cudnn.deterministic = prev

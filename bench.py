@@ -226,6 +226,9 @@ def ops_table(pk, ffma):
         out[k] = {"us": round(v["us"], 2), "bound": v["bound"], "frac": round(v["frac"], 4),
                   "achieved": round(v.get("achieved_gbs", v.get("achieved_tflops", 0.0)), 2),
                   "unit": "GB/s" if v["bound"] == "hbm" else "TFLOP/s"}
+        if "cpu_reference_us" in v:
+            out[k]["cpu_reference_us"] = round(v["cpu_reference_us"], 1)
+            out[k]["cpu_threads"] = v["cpu_threads"]
     return out
 
 

@@ -125,6 +125,25 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
     flow = flows["bilinear"]
     add("gridsample_fwd_bilinear", lambda: F.warp_forward(img, flow, F.WARP_GRIDSAMPLE),
         lambda: __import__("oracle.torch_ref", fromlist=["x"]).networks_resample(img, flow), alg_bytes=8 * plane)
+    # ---- C1: vid2vid generator flow-warp, 1x3x256x512 (BASELINE configs[0], the reference's CPU-runnable case) ----
+    if not small:
+        torch.manual_seed(0)
+        img1 = torch.randn(1, 3, 256, 512)
+        flow1 = 5 * torch.randn(1, 2, 256, 512)
+        img1c, flow1c = img1.cuda(), flow1.cuda()
+        gout1 = torch.randn(1, 3, 256, 512, device="cuda")
+        add("gridsample_fwd_c1", lambda: F.warp_forward(img1c, flow1c, F.WARP_GRIDSAMPLE), None, alg_bytes=8 * 256 * 512 * 4)
+        add("gridsample_bwd_c1", lambda: F.warp_backward(img1c, flow1c, gout1, True, True, F.WARP_GRIDSAMPLE), None,
+            alg_bytes=13 * 256 * 512 * 4)
+        import time as _time
+        from oracle import torch_ref as _tr
+        for _ in range(3):
+            _tr.networks_resample(img1, flow1)
+        t0 = _time.perf_counter()
+        for _ in range(20):
+            _tr.networks_resample(img1, flow1)
+        res["ops"]["gridsample_fwd_c1"]["cpu_reference_us"] = (_time.perf_counter() - t0) / 20 * 1e6
+        res["ops"]["gridsample_fwd_c1"]["cpu_threads"] = torch.get_num_threads()
     y = F.channelnorm_forward(img)
     gy = torch.randn_like(y)
     add("cnorm_fwd_c3", lambda: F.channelnorm_forward(img),

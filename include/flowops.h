@@ -29,6 +29,10 @@ extern "C" {
 #define FLOWOPS_EUNSUPPORTED (-2)  /* parameter combination the reference never defines/uses        */
 #define FLOWOPS_EWORKSPACE (-3)    /* workspace missing, misaligned or too small                    */
 
+/* memory layout of a [B,C,H,W] input */
+#define FLOWOPS_LAYOUT_NCHW 0      /* contiguous, what the reference extensions require                */
+#define FLOWOPS_LAYOUT_NHWC 1      /* torch.channels_last: element (n,c,y,x) at ((n*H+y)*W+x)*C+c      */
+
 /* warp coordinate conventions */
 #define FLOWOPS_WARP_RESAMPLE2D 0  /* resample2d_package: sample at (x+dx, y+dy), clamp corners      */
 #define FLOWOPS_WARP_GRIDSAMPLE 1  /* models/networks.py:93-100: vid2vid grid + F.grid_sample
@@ -83,11 +87,12 @@ size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W,
                                         int pad, int k, int md, int s1, int s2);
 
 /* Replaces correlation_cuda.forward (correlation_cuda.cc:10-87 -> correlation_cuda_kernel.cu:336-427).
- * in1, in2: [B,C,H,W]; out: [B,oC,oH,oW].  corr_multiply is ignored by the reference kernels and is
- * not part of this ABI. */
+ * in1, in2: [B,C,H,W] in `in_layout` (FLOWOPS_LAYOUT_NCHW like the reference, or FLOWOPS_LAYOUT_NHWC so that a
+ * channels_last conv body can hand its features over without a layout copy; FlowNetC configuration only);
+ * out: [B,oC,oH,oW], always NCHW.  corr_multiply is ignored by the reference kernels and is not part of this ABI. */
 int flowops_corr_fwd(const float *in1, const float *in2, float *out,
                      int B, int C, int H, int W,
-                     int pad, int k, int md, int s1, int s2,
+                     int pad, int k, int md, int s1, int s2, int in_layout,
                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).

@@ -28,7 +28,7 @@ SIGNATURES = {
     "flowops_corr_out_shape": (_int, [_int] * 7 + [ctypes.POINTER(_int)] * 3),
     "flowops_corr_fwd_workspace_bytes": (_sz, [_int] * 9),
     "flowops_corr_bwd_workspace_bytes": (_sz, [_int] * 9),
-    "flowops_corr_fwd": (_int, [_vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_corr_fwd": (_int, [_vp, _vp, _vp] + [_int] * 10 + [_vp, _sz, _vp]),
     "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
     "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _vp]),

@@ -57,9 +57,11 @@ extern "C" size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W, i
 }
 
 extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
-                                int pad, int k, int md, int s1, int s2,
+                                int pad, int k, int md, int s1, int s2, int in_layout,
                                 void *workspace, size_t workspace_bytes, void *stream)
 {
+    FLOWOPS_REQUIRE(in_layout == FLOWOPS_LAYOUT_NCHW || in_layout == FLOWOPS_LAYOUT_NHWC, FLOWOPS_EINVAL,
+                    "corr_fwd: unknown input layout %d", in_layout);
     FLOWOPS_REQUIRE(in1 && in2 && out, FLOWOPS_EINVAL, "corr_fwd: null pointer");
     CorrGeom g;
     const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
@@ -67,7 +69,9 @@ extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, 
     FLOWOPS_REQUIRE(pad >= md + g.kr || k == 1, FLOWOPS_EUNSUPPORTED,
                     "corr_fwd: pad_size < max_displacement + kernel_radius reads outside the padded scratch in the reference");
     cudaStream_t st = (cudaStream_t)stream;
-    if (corr_fast_supported(g)) return corr_fast_fwd_launch(in1, in2, out, g, workspace, workspace_bytes, st);
+    if (corr_fast_supported(g)) return corr_fast_fwd_launch(in1, in2, out, g, in_layout, workspace, workspace_bytes, st);
+    FLOWOPS_REQUIRE(in_layout == FLOWOPS_LAYOUT_NCHW, FLOWOPS_EUNSUPPORTED,
+                    "corr_fwd: channels-last inputs are only taken by the FlowNetC configuration");
     return corr_fwd_generic_launch(in1, in2, out, g, st);
 }
 

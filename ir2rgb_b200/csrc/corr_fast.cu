@@ -138,6 +138,50 @@ __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ 
     }
 }
 
+// Same planes from channels-last (NHWC) inputs -- what a channels_last conv body hands over (FlowNetC's
+// conv3 features): one pass instead of an NHWC->NCHW copy followed by corr_planarize.  A CTA transposes
+// 64 pixels x 32 channels of one image row through shared memory: loads are coalesced along c (128 B per
+// pixel), stores along the plane row (128 B per channel and parity).
+constexpr int kNhwcPix = 64, kNhwcCh = 32;
+__global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restrict__ in1, const float *__restrict__ in2,
+                                                           float *__restrict__ P1, float *__restrict__ P2,
+                                                           int C, int H, int W, int Hp, int Wp, int pitch1, int pitch2)
+{
+    __shared__ float tile[2][kNhwcPix / 2][kNhwcCh + 1];       // [column parity][plane column][channel]
+    const bool second = blockIdx.z & 1;
+    const int n = blockIdx.z >> 1;
+    const float *__restrict__ in = second ? in2 : in1;
+    float *__restrict__ P = second ? P2 : P1;
+    const int pitch = second ? pitch2 : pitch1, shift = second ? kShift : 0;
+    const int c_tiles = (C + kNhwcCh - 1) / kNhwcCh;
+    const int ct = blockIdx.x % c_tiles, xt = blockIdx.x / c_tiles;
+    const int y = blockIdx.y, c0 = ct * kNhwcCh, x0 = xt * kNhwcPix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const float *row = in + ((size_t)n * H + y) * W * C;
+#pragma unroll
+    for (int i = 0; i < kNhwcPix / 8; ++i) {
+        const int px = warp + 8 * i, x = x0 + px, c = c0 + lane;
+        tile[px & 1][px >> 1][lane] = (x < W && c < C) ? ldg_stream(row + (size_t)x * C + c) : 0.f;
+    }
+    __syncthreads();
+    const int py = y & 1, yy = y >> 1;
+    const int xx0 = x0 >> 1;                                    // first plane column of this tile
+#pragma unroll
+    for (int i = 0; i < 2 * kNhwcCh / 8; ++i) {
+        const int r = warp + 8 * i;                             // (parity, channel) row of the tile
+        const int par = r / kNhwcCh, cl = r - par * kNhwcCh, c = c0 + cl;
+        if (c >= C) continue;
+        float *dst = P + ((((size_t)n * 4 + py * 2 + par) * C + c) * Hp + yy) * pitch;
+        const int xx = xx0 + lane;
+        if (xx + shift < pitch) dst[xx + shift] = tile[par][lane][cl];     // columns beyond Wp hold zeros already
+        if (shift && xt == 0 && lane < shift) dst[lane] = 0.f;             // leading zero columns of the f2 planes
+        if (xx0 + kNhwcPix / 2 >= Wp)                                      // last tile: zero the tail of the pitch
+            for (int q = Wp + shift + lane; q < pitch; q += 32)
+                if (q >= xx0 + kNhwcPix / 2 + shift) dst[q] = 0.f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
@@ -297,7 +341,7 @@ static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, int H
     return encode_map4(tm, base, dims, strides, box, "corr_fwd");
 }
 
-int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g,
+int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, int in_layout,
                          void *ws, size_t ws_bytes, cudaStream_t st)
 {
     const PlaneGeom p = plane_geom(g);
@@ -312,7 +356,14 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
         cudaError_t e = cudaMemsetAsync(ws, 0, need, st);
         if (e != cudaSuccess) { set_error("corr_fwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    {
+    if (in_layout == FLOWOPS_LAYOUT_NHWC) {
+        const int c_tiles = (g.C + kNhwcCh - 1) / kNhwcCh, x_tiles_in = (g.W + kNhwcPix - 1) / kNhwcPix;
+        FLOWOPS_REQUIRE(g.H <= 65535 && g.B * 2 <= 65535, FLOWOPS_EUNSUPPORTED, "corr_fwd: NHWC input too large for the transpose grid");
+        corr_planarize_nhwc<<<dim3(c_tiles * x_tiles_in, g.H, g.B * 2), 256, 0, st>>>(in1, in2, P1, P2, g.C, g.H, g.W,
+                                                                                   p.Hp, p.Wp, p.pitch1, p.pitch2);
+        const int rc = check_launch("corr_planarize_nhwc");
+        if (rc) return rc;
+    } else {
         const int vec_ok = (g.W % 4 == 0) && aligned16(in1) && aligned16(in2);
         const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
         size_t blocks = (total + 255) / 256;

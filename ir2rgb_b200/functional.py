@@ -201,21 +201,29 @@ def _workspace(nbytes, device):
     return torch.empty((max(nbytes, 1),), device=device, dtype=torch.uint8)
 
 
+def _is_nhwc(t):
+    return (not t.is_contiguous()) and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
-    in1 = _require(in1, "input1").contiguous()
-    in2 = _require(in2, "input2").contiguous()
+    in1, in2 = _require(in1, "input1"), _require(in2, "input2")
     if in1.shape != in2.shape or in1.device != in2.device:
         raise ValueError("input1 %s and input2 %s must have the same shape and device" % (tuple(in1.shape), tuple(in2.shape)))
     B, C, H, W = in1.shape
     params = (int(pad_size), int(kernel_size), int(max_displacement), int(stride1), int(stride2))
     lib = _lib.load()
+    # channels_last features (a channels_last conv body) are taken as they are by the FlowNetC fast path
+    layout = 1 if (_is_nhwc(in1) and _is_nhwc(in2) and lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *params) > 0) else 0
+    if layout == 0:
+        in1, in2 = in1.contiguous(), in2.contiguous()
     oc, oh, ow = correlation_out_shape(H, W, *params)
     with torch.cuda.device_of(in1):
         out = torch.empty((B, oc, oh, ow), device=in1.device, dtype=torch.float32)
         nbytes = lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *params)
         ws = _workspace(nbytes, in1.device)       # the role of rbot1/rbot2 (correlation.py:16-17)
         if in1.numel():
-            check(lib.flowops_corr_fwd(_p(in1), _p(in2), _p(out), B, C, H, W, *params, _p(ws), nbytes, _stream()), "corr_fwd")
+            check(lib.flowops_corr_fwd(_p(in1), _p(in2), _p(out), B, C, H, W, *params, layout, _p(ws), nbytes, _stream()),
+                  "corr_fwd")
     return out
 
 

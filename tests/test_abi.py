@@ -68,10 +68,10 @@ def test_bad_arguments_are_rejected_without_a_device(flowops_lib):
     assert lib.flowops_warp_fwd(one, one, one, 1, 3, 4, 4, 7, None, None, None) == -1         # unknown mode
     assert lib.flowops_warp_fwd(one, one, one, 1, 3, 4, 4, 1, None, None, None) == -1         # tables missing
     assert lib.flowops_warp_bwd(one, one, one, None, None, 1, 3, 4, 4, 0, None, None, None) == -1
-    assert lib.flowops_corr_fwd(one, one, one, 1, 4, 8, 8, 20, 2, 20, 1, 2, None, 0, None) == -1  # even kernel
+    assert lib.flowops_corr_fwd(one, one, one, 1, 4, 8, 8, 20, 2, 20, 1, 2, 0, None, 0, None) == -1  # even kernel
     assert lib.flowops_corr_bwd(one, one, one, one, one, 1, 4, 8, 8, 4, 1, 4, 2, 2, None, 0, None) == -2
     # fast path without its workspace
-    assert lib.flowops_corr_fwd(one, one, one, 1, 4, 8, 8, 20, 1, 20, 1, 2, None, 0, None) == -3
+    assert lib.flowops_corr_fwd(one, one, one, 1, 4, 8, 8, 20, 1, 20, 1, 2, 0, None, 0, None) == -3
 
 
 def test_shapes_and_workspace(flowops_lib):

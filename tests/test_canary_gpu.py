@@ -46,7 +46,7 @@ def test_correlation_fast_path_stays_in_bounds(lib, shape):
     wbuf, ws = guarded((ws_bytes + 3) // 4 + 64)
     ws_off = (-ws.data_ptr()) % 256 // 4                      # 256-byte aligned start inside the window
     ws = ws[ws_off:]
-    rc = lib.flowops_corr_fwd(p(a), p(b), p(out), B, C, H, W, *P, p(ws), ws_bytes, None)
+    rc = lib.flowops_corr_fwd(p(a), p(b), p(out), B, C, H, W, *P, 0, p(ws), ws_bytes, None)
     assert rc == 0, lib.flowops_last_error()
     torch.cuda.synchronize()
     check(obuf, n_out, "corr_fwd out")
@@ -74,7 +74,7 @@ def test_correlation_generic_stays_in_bounds(lib, params, shape):
     lib.flowops_corr_out_shape(H, W, *params, ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow))
     n_out = B * oc.value * oh.value * ow.value
     obuf, out = guarded(n_out)
-    assert lib.flowops_corr_fwd(p(a), p(b), p(out), B, C, H, W, *params, None, 0, None) == 0
+    assert lib.flowops_corr_fwd(p(a), p(b), p(out), B, C, H, W, *params, 0, None, 0, None) == 0
     torch.cuda.synchronize()
     check(obuf, n_out, "corr_fwd generic")
     if params[3] == 1:

@@ -363,3 +363,17 @@ def test_ops_are_graph_capturable_and_stream_ordered(ops):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, expect)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 24, 32), (1, 40, 6, 70), (1, 9, 7, 5), (2, 256, 64, 128)])
+def test_correlation_channels_last_inputs(ops, shape):
+    """A channels_last conv body hands its features over without a layout copy: same planes, same result."""
+    torch.manual_seed(14)
+    a, b = torch.randn(shape, device="cuda"), torch.randn(shape, device="cuda")
+    corr = ops.Correlation(*FLOWNETC, 1)
+    ref_out = corr(a, b)
+    a_cl, b_cl = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    out = corr(a_cl, b_cl)
+    assert out.is_contiguous() and torch.equal(out, ref_out)
+    # mixed layouts fall back to the NCHW path
+    assert torch.equal(corr(a_cl, b), ref_out)

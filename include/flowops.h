@@ -130,6 +130,11 @@ int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow,
 int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int HW, int channels_last,
                        float slope, void *stream);
 
+/* Channel concatenation of channels-last tensors: copies src ([n_pixels][c_src], dense) into channels
+ * [c_off, c_off + c_src) of dst ([n_pixels][c_dst]).  One call per concatenated tensor (torch.cat of the
+ * decoder skip connections, e.g. FlowNetS.py:74). */
+int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels, int c_src, int c_dst, int c_off, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

@@ -33,6 +33,7 @@ SIGNATURES = {
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
     "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _vp]),
     "flowops_bias_lrelu": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.c_float, _vp]),
+    "flowops_concat_nhwc": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp]),
     "flowops_bench_ffma": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

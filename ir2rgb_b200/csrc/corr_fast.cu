@@ -192,6 +192,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];       // one arrival per warp when it is done with a slot
 
     // tile decode: plane fastest so the two column parities of a row segment are written close in time
     int bid = blockIdx.x;
@@ -212,9 +213,10 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(full_bar);
+    const uint32_t empty_base = smem_u32(empty_bar);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8 * s, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(empty_base + 8 * s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -282,9 +284,18 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
                                   : __fmaf_rn(a[k], w2[(kD - 1 + k) / 2].x, accs[k]);
             }
         }
-        __syncthreads();                              // every warp is done with this slot
-        if (tid == 0 && it + kStages < n_it) issue(it + kStages, slot);
+        // Slot recycling without a CTA-wide barrier: each warp signals the slot's "empty" mbarrier, and the
+        // issuing thread refills the slot consumed one iteration EARLIER (by now every warp has normally left
+        // it), so the warps are free to drift apart and keep the FMA pipe fed while one of them loads.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_base + 8 * slot);
+        if (tid == 0 && it >= 1 && it - 1 + kStages < n_it) {
+            const int prev = (it - 1) % kStages;
+            mbar_wait(empty_base + 8 * prev, ((it - 1) / kStages) & 1);
+            issue(it - 1 + kStages, prev);
+        }
     }
+    __syncthreads();                                  // all warps are out of the pipeline buffers
 
     // ---- epilogue: registers -> shared (row-major 32-pixel segments) -> global ----
     // (the last loop iteration ended with __syncthreads and no TMA is in flight)

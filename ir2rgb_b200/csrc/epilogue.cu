@@ -73,3 +73,47 @@ extern "C" int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int
         bias_lrelu_scalar<<<grid_for(total), 256, 0, st>>>(y, bias, total, (size_t)HW, (unsigned)C, channels_last, slope);
     return check_launch("bias_lrelu");
 }
+
+// ---------------------------------------------------------------------------------------------
+// channel concatenation of channels-last tensors (the decoder skip concats of FlowNetC/S/SD/Fusion,
+// e.g. reference FlowNetS.py:74-90).  torch.cat's generic batched copy reaches ~1 TB/s on these shapes
+// (profiles/torchprof_flownet_cl_r01.txt); this is a plain strided row copy: every pixel's C_src channels are
+// contiguous in the source and land at a channel offset inside the C_dst-wide destination pixel.
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+template <typename V>
+__global__ void __launch_bounds__(256) copy_channels_nhwc(const V *__restrict__ src, V *__restrict__ dst,
+                                                          size_t total, unsigned src_v, unsigned dst_v, unsigned off_v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / src_v;
+        const unsigned c = (unsigned)(i - pix * src_v);
+        dst[pix * dst_v + off_v + c] = src[i];
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels, int c_src, int c_dst, int c_off, void *stream)
+{
+    FLOWOPS_REQUIRE(src && dst, FLOWOPS_EINVAL, "concat_nhwc: null pointer");
+    FLOWOPS_REQUIRE(n_pixels > 0 && c_src > 0 && c_off >= 0 && c_off + c_src <= c_dst, FLOWOPS_EINVAL,
+                    "concat_nhwc: bad channel range %d + %d of %d", c_off, c_src, c_dst);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto grid_for = [](size_t items) {
+        size_t blocks = (items + 255) / 256;
+        const size_t cap = (size_t)kNumSMs * 8 * 16;
+        return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+    };
+    const size_t total = n_pixels * (size_t)c_src;
+    if (((c_src | c_dst | c_off) & 3) == 0 && aligned16(src) && aligned16(dst))
+        copy_channels_nhwc<float4><<<grid_for(total / 4), 256, 0, st>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst),
+                                                                        total / 4, c_src / 4, c_dst / 4, c_off / 4);
+    else if (((c_src | c_dst | c_off) & 1) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 7) == 0)
+        copy_channels_nhwc<float2><<<grid_for(total / 2), 256, 0, st>>>(reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst),
+                                                                        total / 2, c_src / 2, c_dst / 2, c_off / 2);
+    else
+        copy_channels_nhwc<float><<<grid_for(total), 256, 0, st>>>(src, dst, total, c_src, c_dst, c_off);
+    return check_launch("concat_nhwc");
+}

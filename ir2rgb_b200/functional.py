@@ -25,6 +25,10 @@ def _require(t, name, ndim=4):
     return t
 
 
+def _is_nhwc(t):
+    return (not t.is_contiguous()) and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -186,6 +190,26 @@ def bias_lrelu_(y, bias, slope):
     return y
 
 
+def cat_channels(tensors):
+    """torch.cat(tensors, dim=1).  When autograd is off and every input is a dense channels_last fp32 CUDA
+    tensor the copy runs as one libflowops kernel per input; anything else goes to torch.cat."""
+    t0 = tensors[0]
+    fast = (not torch.is_grad_enabled() and all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
+                                                and t.dim() == 4 and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:]
+                                                and t.device == t0.device and _is_nhwc(t) for t in tensors))
+    if not fast or t0.numel() == 0:
+        return torch.cat(tensors, 1)
+    B, _, H, W = t0.shape
+    c_total = sum(t.shape[1] for t in tensors)
+    with torch.cuda.device_of(t0):
+        out = torch.empty((B, c_total, H, W), device=t0.device, dtype=torch.float32, memory_format=torch.channels_last)
+        lib, off = _lib.load(), 0
+        for t in tensors:
+            check(lib.flowops_concat_nhwc(_p(t), _p(out), B * H * W, t.shape[1], c_total, off, _stream()), "concat_nhwc")
+            off += t.shape[1]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # Correlation
 # ---------------------------------------------------------------------------------------------
@@ -199,10 +223,6 @@ def correlation_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1
 def _workspace(nbytes, device):
     # torch.empty on CUDA is 512-byte aligned; the library asks for 256
     return torch.empty((max(nbytes, 1),), device=device, dtype=torch.uint8)
-
-
-def _is_nhwc(t):
-    return (not t.is_contiguous()) and t.is_contiguous(memory_format=torch.channels_last)
 
 
 def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):

@@ -95,7 +95,7 @@ def refine(net, skips, top, levels, inter=False):
     for lv in levels:
         up = getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv))(flows[0])
         dec = getattr(net, "deconv%d" % lv)(feat)
-        feat = torch.cat((skips[lv], dec, up), 1)
+        feat = _F.cat_channels((skips[lv], dec, up))
         head_in = getattr(net, "inter_conv%d" % lv)(feat) if inter else feat
         flows.insert(0, getattr(net, "predict_flow%d" % lv)(head_in))
     return flows

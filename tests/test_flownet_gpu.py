@@ -151,3 +151,20 @@ def test_host_pipeline_matches_direct_calls(nets):
             assert torch.equal(hflow[s:s + 2], f.cpu()) and torch.equal(hconf[s:s + 2], c.cpu())
     finally:
         torch.backends.cudnn.deterministic = prev
+
+
+@pytest.mark.parametrize("chans", [(512, 512, 2), (64, 64), (128, 32, 2), (5, 3)])
+def test_cat_channels_matches_torch_cat(flowops_lib, chans):
+    from ir2rgb_b200 import functional as F
+    torch.manual_seed(8)
+    parts = [torch.randn(2, c, 9, 14, device="cuda").contiguous(memory_format=torch.channels_last) for c in chans]
+    with torch.no_grad():
+        out = F.cat_channels(parts)
+    ref = torch.cat(parts, 1)
+    assert torch.equal(out, ref) and out.is_contiguous(memory_format=torch.channels_last)
+    # NCHW inputs and autograd fall back to torch.cat
+    nchw = [p.contiguous() for p in parts]
+    assert torch.equal(F.cat_channels(nchw), ref)
+    req = [p.clone().requires_grad_() for p in parts]
+    F.cat_channels(req).sum().backward()
+    assert all(r.grad is not None for r in req)

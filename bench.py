@@ -305,7 +305,8 @@ def main():
         # public runtime helper: H2D of micro-batch i+1 and D2H of i-1 overlap the computation of micro-batch i
         from ir2rgb_b200.runtime import HostPipeline
         pipe = HostPipeline(net, device)
-        e2e_step = lambda: pipe(h1, h2, mb, hflow, hconf)
+        mb_host = mb if B_local >= 2 * mb else max(1, B_local // 2)     # at least two micro-batches so copies overlap compute
+        e2e_step = lambda: pipe(h1, h2, mb_host, hflow, hconf)
     else:
         e2e_step = lambda: run_step(net, h1, h2, mb, host_out=(hflow, hconf))
     ms_e2e = timed(e2e_step, max(1, args.steps), 1, dist, device)

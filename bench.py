@@ -112,8 +112,9 @@ class Launches:
     """Counts this repo's kernel launches and times the dominant operator (Correlation forward) with
     CUDA events on the launching stream, live inside the timed region."""
 
-    PER_CALL = {"correlation_forward": 2, "warp_diff_norm_forward": 1, "channelnorm_forward": 1,
-                "warp_conf_forward": 1, "warp_forward": 1}
+    PER_CALL = {"correlation_forward": 2, "correlation_planes_forward": 1, "warp_diff_norm_forward": 1,
+                "channelnorm_forward": 1, "warp_conf_forward": 1, "warp_forward": 1, "bias_lrelu_": 1, "cat_channels": 3}
+    TIMED = ("correlation_forward", "correlation_planes_forward")
 
     def __init__(self):
         self.count = 0
@@ -130,13 +131,13 @@ class Launches:
                 if not self.enabled:
                     return _orig(*a, **k)
                 self.count += _n
-                if _name != "correlation_forward":
+                if _name not in self.TIMED:
                     return _orig(*a, **k)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 out = _orig(*a, **k)
                 e1.record()
-                self.corr_events.append((e0, e1, a[0].shape))
+                self.corr_events.append((e0, e1, a[0].shape, _name))
                 return out
             setattr(F, name, wrapped)
 
@@ -355,11 +356,13 @@ def main():
         ffma = F.ffma_peak_tflops()
         # roofline of the dominant hand-written kernel in the step: Correlation forward (planarize + main)
         if corr_events:
-            us = [e0.elapsed_time(e1) * 1e3 for e0, e1, _ in corr_events]
+            us = [ev[0].elapsed_time(ev[1]) * 1e3 for ev in corr_events]
             shp = corr_events[0][2]
+            split = corr_events[0][3] == "correlation_planes_forward"
             flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]
             mean_us = sum(us) / len(us)
-            line["roofline"] = {"kernel": "corr_fwd (corr_planarize + corr_fwd_fast)", "bound": "fp32",
+            line["roofline"] = {"kernel": "corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split
+                                          else "corr_fwd (corr_planarize + corr_fwd_fast)", "bound": "fp32",
                                 "achieved": flop / mean_us / 1e6, "peak": ffma, "unit": "TFLOP/s",
                                 "frac": flop / mean_us / 1e6 / ffma, "traffic": None,
                                 "peak_source": "flowops_bench_ffma measured on this GPU (nominal 74.4)",

@@ -95,6 +95,20 @@ int flowops_corr_fwd(const float *in1, const float *in2, float *out,
                      int pad, int k, int md, int s1, int s2, int in_layout,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Split form of flowops_corr_fwd for a channels_last FlowNetC (FlowNetC.py:75-89), FlowNetC configuration only:
+ *   flowops_corr_planes_from_conv  is the epilogue of the conv3 convolution of frame `which` (0 or 1): it applies
+ *       bias + LeakyReLU(slope) to the bias-free NHWC conv output y [B,C,H,W], writes the result into the
+ *       correlation's internal layout inside `workspace`, and -- when act is not NULL (may alias y) -- also back in
+ *       NHWC order for other consumers (conv_redir reads frame 0's features, nothing else reads frame 1's);
+ *   flowops_corr_fwd_planes        then runs the correlation proper on what the workspace holds.
+ * Together they equal  bias+LeakyReLU (x2)  ->  flowops_corr_fwd  bit for bit, with two passes over each feature
+ * tensor less. */
+int flowops_corr_planes_from_conv(const float *y, const float *bias, float slope, float *act, int which,
+                                  int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int flowops_corr_fwd_planes(float *out, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).
  * gout: [B,oC,oH,oW]; gin1, gin2: [B,C,H,W] (either may be NULL). */
 int flowops_corr_bwd(const float *in1, const float *in2, const float *gout,
@@ -117,10 +131,13 @@ int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, size_t img_
                                float *norm, size_t norm_batch_stride,
                                int B, int C, int H, int W, void *stream);
 
-/* conf = (sum_c (im1 - Resample2d(im2, flow))^2 < thresh) ? 1 : 0   (models/flownet.py:50,56-57).
- * im1, im2: [B,C,H,W] contiguous; conf: [B,1,H,W]. */
+/* conf = (sum_c (im1 - warp(im2, flow))^2 < thresh) ? 1 : 0   (models/flownet.py:50,56-57).
+ * im1, im2: [B,C,H,W] contiguous; conf: [B,1,H,W].  mode / lin_x / lin_y as in flowops_warp_fwd.  As run, the
+ * reference's `self.resample` at flownet.py:50 is Model.resample (base_model.py:129, mode GRIDSAMPLE): the method
+ * shadows the Resample2d submodule of the same name. */
 int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow, float *conf,
-                          float thresh, int B, int C, int H, int W, void *stream);
+                          float thresh, int B, int C, int H, int W, int mode,
+                          const float *lin_x, const float *lin_y, void *stream);
 
 /* ---- Conv-body epilogue (FlowNet2 inference glue, not an operator of the reference's native surface) ---- */
 

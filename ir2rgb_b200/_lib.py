@@ -29,9 +29,11 @@ SIGNATURES = {
     "flowops_corr_fwd_workspace_bytes": (_sz, [_int] * 9),
     "flowops_corr_bwd_workspace_bytes": (_sz, [_int] * 9),
     "flowops_corr_fwd": (_int, [_vp, _vp, _vp] + [_int] * 10 + [_vp, _sz, _vp]),
+    "flowops_corr_planes_from_conv": (_int, [_vp, _vp, ctypes.c_float, _vp, _int] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_corr_fwd_planes": (_int, [_vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
-    "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _vp]),
+    "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "flowops_bias_lrelu": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_concat_nhwc": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp]),
     "flowops_bench_ffma": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), _vp]),

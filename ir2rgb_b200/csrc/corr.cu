@@ -75,6 +75,31 @@ extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, 
     return corr_fwd_generic_launch(in1, in2, out, g, st);
 }
 
+extern "C" int flowops_corr_planes_from_conv(const float *y, const float *bias, float slope, float *act, int which,
+                                             int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(y && bias, FLOWOPS_EINVAL, "corr_planes_from_conv: null pointer");
+    FLOWOPS_REQUIRE(which == 0 || which == 1, FLOWOPS_EINVAL, "corr_planes_from_conv: input slot must be 0 or 1");
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_planes_from_conv: FlowNetC configuration only");
+    return corr_fast_planes_nhwc(which == 0 ? y : nullptr, which == 1 ? y : nullptr, g, which, bias, slope, act,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int flowops_corr_fwd_planes(float *out, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(out, FLOWOPS_EINVAL, "corr_fwd_planes: null pointer");
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_fwd_planes: FlowNetC configuration only");
+    return corr_fast_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int flowops_corr_bwd(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
                                 int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                                 void *workspace, size_t workspace_bytes, void *stream)

@@ -143,13 +143,21 @@ __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ 
 // 64 pixels x 32 channels of one image row through shared memory: loads are coalesced along c (128 B per
 // pixel), stores along the plane row (128 B per channel and parity).
 constexpr int kNhwcPix = 64, kNhwcCh = 32;
+//
+// With `bias` the kernel is also the epilogue of the convolution that produced the features (FlowNetC's conv3,
+// FlowNetC.py:23,75-81): t = y + bias[c]; v = t > 0 ? t : t * slope is applied on the fly, the planes receive v,
+// and v is written back in NHWC order only where another consumer needs it (`act`; frame 1 feeds conv_redir,
+// frame 2 feeds nothing else).  That replaces  bias+LeakyReLU (read+write)  +  planarize (read+write)  by one read
+// and one or two writes, and leaves the correlation proper with no pre-pass of its own.
 __global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restrict__ in1, const float *__restrict__ in2,
                                                            float *__restrict__ P1, float *__restrict__ P2,
-                                                           int C, int H, int W, int Hp, int Wp, int pitch1, int pitch2)
+                                                           int C, int H, int W, int Hp, int Wp, int pitch1, int pitch2,
+                                                           int only, const float *__restrict__ bias, float slope,
+                                                           float *__restrict__ act)
 {
     __shared__ float tile[2][kNhwcPix / 2][kNhwcCh + 1];       // [column parity][plane column][channel]
-    const bool second = blockIdx.z & 1;
-    const int n = blockIdx.z >> 1;
+    const bool second = only < 0 ? (blockIdx.z & 1) : (only == 1);
+    const int n = only < 0 ? (blockIdx.z >> 1) : blockIdx.z;
     const float *__restrict__ in = second ? in2 : in1;
     float *__restrict__ P = second ? P2 : P1;
     const int pitch = second ? pitch2 : pitch1, shift = second ? kShift : 0;
@@ -158,11 +166,22 @@ __global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restri
     const int y = blockIdx.y, c0 = ct * kNhwcCh, x0 = xt * kNhwcPix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    const float *row = in + ((size_t)n * H + y) * W * C;
+    const size_t row_off = ((size_t)n * H + y) * W * C;
+    const float *row = in + row_off;
+    const float b = (bias && c0 + lane < C) ? __ldg(bias + c0 + lane) : 0.f;
 #pragma unroll
     for (int i = 0; i < kNhwcPix / 8; ++i) {
         const int px = warp + 8 * i, x = x0 + px, c = c0 + lane;
-        tile[px & 1][px >> 1][lane] = (x < W && c < C) ? ldg_stream(row + (size_t)x * C + c) : 0.f;
+        float v = 0.f;
+        if (x < W && c < C) {
+            v = ldg_stream(row + (size_t)x * C + c);
+            if (bias) {
+                const float t = __fadd_rn(v, b);
+                v = t > 0.f ? t : __fmul_rn(t, slope);
+                if (act) act[row_off + (size_t)x * C + c] = v;
+            }
+        }
+        tile[px & 1][px >> 1][lane] = v;
     }
     __syncthreads();
     const int py = y & 1, yy = y >> 1;
@@ -352,40 +371,50 @@ static int make_plane_map(CUtensorMap *tm, float *base, const CorrGeom &g, int H
     return encode_map4(tm, base, dims, strides, box, "corr_fwd");
 }
 
-int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, int in_layout,
-                         void *ws, size_t ws_bytes, cudaStream_t st)
+static int corr_fast_workspace_check(const CorrGeom &g, void *ws, size_t ws_bytes, float *&P1, float *&P2, const char *who)
 {
     const PlaneGeom p = plane_geom(g);
     const size_t need = corr_fast_fwd_workspace(g);
     FLOWOPS_REQUIRE(ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0, FLOWOPS_EWORKSPACE,
-                    "corr_fwd: workspace of %zu bytes (256-byte aligned) required, got %zu", need, ws_bytes);
-    float *P1 = reinterpret_cast<float *>(ws);
-    float *P2 = P1 + (size_t)g.B * 4 * g.C * p.elems1;
+                    "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, ws_bytes);
+    P1 = reinterpret_cast<float *>(ws);
+    P2 = P1 + (size_t)g.B * 4 * g.C * p.elems1;
+    return 0;
+}
 
-    // planes have zero padding only when W is not a multiple of 8 or H is odd
-    if ((g.W & 7) || (g.H & 1)) {
-        cudaError_t e = cudaMemsetAsync(ws, 0, need, st);
-        if (e != cudaSuccess) { set_error("corr_fwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+// NHWC features -> planes of input slot `only` (0: f1, 1: f2; -1: both), optionally fused with the producing
+// convolution's bias + LeakyReLU epilogue
+int corr_fast_planes_nhwc(const float *in1, const float *in2, const CorrGeom &g, int only, const float *bias, float slope,
+                          float *act, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    float *P1, *P2;
+    int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr planes");
+    if (rc) return rc;
+    const PlaneGeom p = plane_geom(g);
+    if ((g.W & 7) || (g.H & 1)) {      // planes then contain cells no thread writes
+        float *base = only == 1 ? P2 : P1;
+        const size_t bytes = only < 0 ? corr_fast_fwd_workspace(g)
+                                      : sizeof(float) * (size_t)g.B * 4 * g.C * (only == 1 ? p.elems2 : p.elems1);
+        cudaError_t e = cudaMemsetAsync(base, 0, bytes, st);
+        if (e != cudaSuccess) { set_error("corr planes: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    if (in_layout == FLOWOPS_LAYOUT_NHWC) {
-        const int c_tiles = (g.C + kNhwcCh - 1) / kNhwcCh, x_tiles_in = (g.W + kNhwcPix - 1) / kNhwcPix;
-        FLOWOPS_REQUIRE(g.H <= 65535 && g.B * 2 <= 65535, FLOWOPS_EUNSUPPORTED, "corr_fwd: NHWC input too large for the transpose grid");
-        corr_planarize_nhwc<<<dim3(c_tiles * x_tiles_in, g.H, g.B * 2), 256, 0, st>>>(in1, in2, P1, P2, g.C, g.H, g.W,
-                                                                                   p.Hp, p.Wp, p.pitch1, p.pitch2);
-        const int rc = check_launch("corr_planarize_nhwc");
-        if (rc) return rc;
-    } else {
-        const int vec_ok = (g.W % 4 == 0) && aligned16(in1) && aligned16(in2);
-        const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
-        size_t blocks = (total + 255) / 256;
-        if (blocks > (size_t)kNumSMs * 8 * 8) blocks = (size_t)kNumSMs * 8 * 8;
-        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
-        const int rc = check_launch("corr_planarize");
-        if (rc) return rc;
-    }
+    const int c_tiles = (g.C + kNhwcCh - 1) / kNhwcCh, x_tiles_in = (g.W + kNhwcPix - 1) / kNhwcPix;
+    const int nz = only < 0 ? g.B * 2 : g.B;
+    FLOWOPS_REQUIRE(g.H <= 65535 && nz <= 65535, FLOWOPS_EUNSUPPORTED, "corr planes: NHWC input too large for the transpose grid");
+    corr_planarize_nhwc<<<dim3(c_tiles * x_tiles_in, g.H, nz), 256, 0, st>>>(in1, in2, P1, P2, g.C, g.H, g.W, p.Hp, p.Wp,
+                                                                           p.pitch1, p.pitch2, only, bias, slope, act);
+    return check_launch("corr_planarize_nhwc");
+}
 
+// the correlation proper, on planes already in the workspace
+int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    float *P1, *P2;
+    int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr_fwd");
+    if (rc) return rc;
+    const PlaneGeom p = plane_geom(g);
     CUtensorMap tm1, tm2;
-    int rc = make_plane_map(&tm1, P1, g, p.Hp, p.pitch1, kF1W, kTY);
+    rc = make_plane_map(&tm1, P1, g, p.Hp, p.pitch1, kF1W, kTY);
     if (rc) return rc;
     rc = make_plane_map(&tm2, P2, g, p.Hp, p.pitch2, kF2W, kF2H);
     if (rc) return rc;
@@ -404,6 +433,32 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
     FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
     kernel<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
     return check_launch("corr_fwd_fast");
+}
+
+int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, int in_layout,
+                         void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    float *P1, *P2;
+    int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr_fwd");
+    if (rc) return rc;
+    if (in_layout == FLOWOPS_LAYOUT_NHWC) {
+        rc = corr_fast_planes_nhwc(in1, in2, g, -1, nullptr, 0.f, nullptr, ws, ws_bytes, st);
+        if (rc) return rc;
+    } else {
+        const PlaneGeom p = plane_geom(g);
+        if ((g.W & 7) || (g.H & 1)) {      // planes have zero padding only when W is not a multiple of 8 or H is odd
+            cudaError_t e = cudaMemsetAsync(ws, 0, corr_fast_fwd_workspace(g), st);
+            if (e != cudaSuccess) { set_error("corr_fwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        const int vec_ok = (g.W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
+        size_t blocks = (total + 255) / 256;
+        if (blocks > (size_t)kNumSMs * 8 * 8) blocks = (size_t)kNumSMs * 8 * 8;
+        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
+        rc = check_launch("corr_planarize");
+        if (rc) return rc;
+    }
+    return corr_fast_main(out, g, ws, ws_bytes, st);
 }
 
 }  // namespace flowops

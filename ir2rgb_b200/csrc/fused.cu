@@ -8,8 +8,11 @@
 //       subtract 9 + norm 4 = 27 floats;  fused: 3 + 3 + 2 read, 3 + 1 written = 12 floats.
 //       Inputs may be channel slices of a wider tensor (batch stride given), outputs may be channel
 //       slices of the concat buffer the next sub-network reads (models.py:114,126).
-//   warp_conf      : conf = (sum_c (im1 - Resample2d(im2, flow))^2 < thresh) as 0/1 floats
-//       (flownet.py:50,56-57): 3 + 3 + 2 read, 1 written, instead of five elementwise kernels.
+//   warp_conf      : conf = (sum_c (im1 - warp(im2, flow))^2 < thresh) as 0/1 floats (flownet.py:50,56-57):
+//       3 + 3 + 2 read, 1 written, instead of five elementwise kernels plus the grid_sample chain.  NOTE: in the
+//       reference `self.resample` inside FlowNet resolves to the METHOD Model.resample (base_model.py:129, the
+//       grid_sample warp), not to the Resample2d submodule assigned at flownet.py:17 -- a class attribute shadows
+//       an nn.Module submodule of the same name -- so the as-run mask uses mode GRIDSAMPLE; both modes exist here.
 #include "warp.cuh"
 
 namespace flowops {
@@ -49,10 +52,12 @@ __global__ void __launch_bounds__(256) warp_diff_norm_kernel(const float *__rest
     }
 }
 
-template <int CT>
+template <int MODE, int CT>
 __global__ void __launch_bounds__(256) warp_conf_kernel(const float *__restrict__ im1, const float *__restrict__ im2,
                                                         const float *__restrict__ flow, float *__restrict__ conf,
-                                                        float thresh, int B, int C, int H, int W)
+                                                        float thresh, int B, int C, int H, int W,
+                                                        const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                                        float invx, float invy)
 {
     const int c_n = CT > 0 ? CT : C;
     const size_t hw = (size_t)H * W;
@@ -64,16 +69,22 @@ __global__ void __launch_bounds__(256) warp_conf_kernel(const float *__restrict_
         const int y = p / W, x = p - y * W;
         const float dx = ldg_stream(flow + (b * 2) * hw + p);
         const float dy = ldg_stream(flow + (b * 2 + 1) * hw + p);
-        float xf, yf; Corners k;
-        r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
-        const R2dWeights w = r2d_weights(xf, yf);
         const float *src = im2 + b * c_n * hw;
         const float *ref = im1 + b * c_n * hw + p;
+        float xf, yf; Corners k; R2dWeights w; GsWeights gw;
+        if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
+            r2d_coords(x, y, dx, dy, H, W, xf, yf, k);
+            w = r2d_weights(xf, yf);
+        } else {
+            gw = gs_weights(gs_coords(x, y, dx, dy, H, W, lin_x, lin_y, invx, invy), H, W);
+        }
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < c_n; ++c) {
             const float *pl = src + (size_t)c * hw;
-            const float val = r2d_blend(w, __ldg(pl + k.o_tl), __ldg(pl + k.o_tr), __ldg(pl + k.o_bl), __ldg(pl + k.o_br));
+            const float val = MODE == FLOWOPS_WARP_RESAMPLE2D
+                                  ? r2d_blend(w, __ldg(pl + k.o_tl), __ldg(pl + k.o_tr), __ldg(pl + k.o_bl), __ldg(pl + k.o_br))
+                                  : gs_gather(gw, pl, W);
             const float d = __fsub_rn(ldg_stream(ref + (size_t)c * hw), val);
             // torch.sum(t*t, dim=1): products are rounded before they are added (flownet.py:56-57)
             acc = c == 0 ? __fmul_rn(d, d) : __fadd_rn(acc, __fmul_rn(d, d));
@@ -121,14 +132,24 @@ extern "C" int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, 
 }
 
 extern "C" int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow, float *conf,
-                                     float thresh, int B, int C, int H, int W, void *stream)
+                                     float thresh, int B, int C, int H, int W, int mode,
+                                     const float *lin_x, const float *lin_y, void *stream)
 {
     FLOWOPS_REQUIRE(im1 && im2 && flow && conf, FLOWOPS_EINVAL, "warp_conf_fwd: null pointer");
     FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "warp_conf_fwd: bad shape %dx%dx%dx%d", B, C, H, W);
     FLOWOPS_REQUIRE((size_t)C * H * W < (1ull << 31), FLOWOPS_EUNSUPPORTED, "warp_conf_fwd: C*H*W exceeds int32 indexing");
+    FLOWOPS_REQUIRE(mode == FLOWOPS_WARP_RESAMPLE2D || mode == FLOWOPS_WARP_GRIDSAMPLE, FLOWOPS_EINVAL, "warp_conf_fwd: unknown mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = fused_grid((size_t)B * H * W);
-    if (C == 3) warp_conf_kernel<3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W);
-    else warp_conf_kernel<0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W);
+    if (mode == FLOWOPS_WARP_GRIDSAMPLE) {
+        FLOWOPS_REQUIRE(lin_x && lin_y && H > 1 && W > 1, FLOWOPS_EINVAL, "warp_conf_fwd: GRIDSAMPLE mode needs the linspace tables and H, W > 1");
+        float invx, invy, mulx, muly;
+        gs_scales(H, W, invx, invy, mulx, muly);
+        if (C == 3) warp_conf_kernel<FLOWOPS_WARP_GRIDSAMPLE, 3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, lin_x, lin_y, invx, invy);
+        else warp_conf_kernel<FLOWOPS_WARP_GRIDSAMPLE, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, lin_x, lin_y, invx, invy);
+    } else {
+        if (C == 3) warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
+        else warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
+    }
     return check_launch("warp_conf_fwd");
 }

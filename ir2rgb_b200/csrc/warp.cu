@@ -26,33 +26,6 @@
 
 namespace flowops {
 
-// models/networks.py:97-98 + ATen grid_sampler_compute_source_index (align_corners=False, border)
-struct GsCoord {
-    float ix, iy;        // clipped source coordinates
-    int ix_nw, iy_nw;    // floor
-    float gmx, gmy;      // d(ix)/d(flow_x), d(iy)/d(flow_y) incl. the clip mask (backward only)
-};
-__device__ __forceinline__ GsCoord gs_coords(int x, int y, float dx, float dy, int H, int W,
-                                             const float *__restrict__ lin_x, const float *__restrict__ lin_y,
-                                             float invx, float invy)
-{
-    GsCoord g;
-    const float gx = __fadd_rn(__ldg(lin_x + x), __fmul_rn(dx, invx));
-    const float gy = __fadd_rn(__ldg(lin_y + y), __fmul_rn(dy, invy));
-    // ((coord + 1) * size - 1) / 2 ; nvcc contracts the multiply-subtract in ATen's build
-    float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), (float)W, -1.f), 0.5f);
-    float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), (float)H, -1.f), 0.5f);
-    // clip_coordinates_set_grad: gradient is zero at and beyond both borders
-    g.gmx = (ix <= 0.f || ix >= (float)(W - 1)) ? 0.f : 1.f;
-    g.gmy = (iy <= 0.f || iy >= (float)(H - 1)) ? 0.f : 1.f;
-    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
-    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
-    g.ix = ix; g.iy = iy;
-    g.ix_nw = (int)floorf(ix);
-    g.iy_nw = (int)floorf(iy);
-    return g;
-}
-
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -87,25 +60,9 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float *__restrict__
             }
         } else {
             const GsCoord g = gs_coords(x, y, dx, dy, H, W, lin_x, lin_y, invx, invy);
-            const int ix_nw = g.ix_nw, iy_nw = g.iy_nw;
-            const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
-            const float nw = __fmul_rn(__fsub_rn((float)ix_se, g.ix), __fsub_rn((float)iy_se, g.iy));
-            const float ne = __fmul_rn(__fsub_rn(g.ix, (float)ix_nw), __fsub_rn((float)iy_se, g.iy));
-            const float sw = __fmul_rn(__fsub_rn((float)ix_se, g.ix), __fsub_rn(g.iy, (float)iy_nw));
-            const float se = __fmul_rn(__fsub_rn(g.ix, (float)ix_nw), __fsub_rn(g.iy, (float)iy_nw));
-            // after the border clip (ix_nw, iy_nw) is always inside; the +1 neighbours may be one past
-            const bool in_e = ix_se < W, in_s = iy_se < H;
-            const int o_nw = iy_nw * W + ix_nw;
+            const GsWeights w = gs_weights(g, H, W);
 #pragma unroll
-            for (int c = 0; c < c_n; ++c) {
-                const float *pl = src + (size_t)c * hw + o_nw;
-                float acc = 0.f;
-                acc = __fmaf_rn(__ldg(pl), nw, acc);
-                if (in_e) acc = __fmaf_rn(__ldg(pl + 1), ne, acc);
-                if (in_s) acc = __fmaf_rn(__ldg(pl + W), sw, acc);
-                if (in_e && in_s) acc = __fmaf_rn(__ldg(pl + W + 1), se, acc);
-                stg_stream(dst + (size_t)c * hw, acc);
-            }
+            for (int c = 0; c < c_n; ++c) stg_stream(dst + (size_t)c * hw, gs_gather(w, src + (size_t)c * hw, W));
         }
     }
 }
@@ -314,17 +271,6 @@ static int launch_bwd(const float *img, const float *flow, const float *gout, fl
     else if (gimg) launch_bwd_c<MODE, true, false>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
     else launch_bwd_c<MODE, false, true>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
     return check_launch("warp_bwd");
-}
-
-// fp32 constants of the models/networks.py:97 normalisation: flow / ((W-1)/2) runs on CUDA as a
-// multiply by the fp32 reciprocal of the fp32 scalar.
-static inline void gs_scales(int H, int W, float &invx, float &invy, float &mulx, float &muly)
-{
-    const float sx = (float)((W - 1.0) / 2.0), sy = (float)((H - 1.0) / 2.0);
-    invx = 1.0f / sx; invy = 1.0f / sy;
-    // d(ix)/d(flow_x) = (W/2) * invx  (unnormalize gradient times the reciprocal above)
-    mulx = ((float)W * 0.5f) * invx;
-    muly = ((float)H * 0.5f) * invy;
 }
 
 }  // namespace flowops

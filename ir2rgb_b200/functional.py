@@ -156,18 +156,19 @@ def warp_diff_norm_forward(x, flow, out=None, need_warped=True):
     return warped, norm
 
 
-def warp_conf_forward(im1, im2, flow, thresh=0.02):
+def warp_conf_forward(im1, im2, flow, thresh=0.02, mode=WARP_GRIDSAMPLE):
     im1 = _require(im1, "im1").contiguous()
     im2 = _require(im2, "im2").contiguous()
     flow = _require(flow, "flow").contiguous()
     B, C, H, W = im1.shape
     if im2.shape != im1.shape or flow.shape != (B, 2, H, W):
         raise ValueError("shape mismatch: %s %s %s" % (tuple(im1.shape), tuple(im2.shape), tuple(flow.shape)))
+    lx, ly = _lin_tables(H, W, im1.device) if mode == WARP_GRIDSAMPLE else (None, None)
     with torch.cuda.device_of(im1):
         conf = torch.empty((B, 1, H, W), device=im1.device, dtype=torch.float32)
         if im1.numel():
             check(_lib.load().flowops_warp_conf_fwd(_p(im1), _p(im2), _p(flow), _p(conf), ctypes.c_float(thresh),
-                                                    B, C, H, W, _stream()), "warp_conf_fwd")
+                                                    B, C, H, W, mode, _p(lx), _p(ly), _stream()), "warp_conf_fwd")
     return conf
 
 
@@ -245,6 +246,47 @@ def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, strid
             check(lib.flowops_corr_fwd(_p(in1), _p(in2), _p(out), B, C, H, W, *params, layout, _p(ws), nbytes, _stream()),
                   "corr_fwd")
     return out
+
+
+class CorrelationPlanes:
+    """Workspace of one FlowNetC correlation whose input planes are written by the conv3 epilogues
+    (flowops_corr_planes_from_conv) before `forward()` runs the correlation proper."""
+
+    def __init__(self, shape, device, params=(20, 1, 20, 1, 2)):
+        self.shape, self.params, self.device = tuple(shape), tuple(int(p) for p in params), device
+        B, C, H, W = self.shape
+        self.nbytes = _lib.load().flowops_corr_fwd_workspace_bytes(B, C, H, W, *self.params)
+        if self.nbytes == 0:
+            raise NotImplementedError("CorrelationPlanes: FlowNetC configuration only")
+        with torch.cuda.device(device):
+            self.ws = _workspace(self.nbytes, device)
+
+    def fill_from_conv_(self, y, bias, slope, which, write_act):
+        """y: bias-free conv output, dense channels_last.  Applies bias + LeakyReLU, fills input slot `which`;
+        with write_act the activated features also replace y in place.  Returns y (activated) or None."""
+        y = _require(y, "y")
+        if tuple(y.shape) != self.shape or not _is_nhwc(y):
+            raise ValueError("fill_from_conv_: expected a dense channels_last tensor of shape %s" % (self.shape,))
+        B, C, H, W = self.shape
+        with torch.cuda.device_of(y):
+            check(_lib.load().flowops_corr_planes_from_conv(_p(y), _p(bias), ctypes.c_float(slope), _p(y if write_act else None),
+                                                            which, B, C, H, W, *self.params, _p(self.ws), self.nbytes, _stream()),
+                  "corr_planes_from_conv")
+        return y if write_act else None
+
+    def forward(self):
+        B, C, H, W = self.shape
+        oc, oh, ow = correlation_out_shape(H, W, *self.params)
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, oc, oh, ow), device=self.device, dtype=torch.float32)
+            check(_lib.load().flowops_corr_fwd_planes(_p(out), B, C, H, W, *self.params, _p(self.ws), self.nbytes, _stream()),
+                  "corr_fwd_planes")
+        return out
+
+
+def correlation_planes_forward(planes):
+    """Module-level entry (so that bench.py can time the correlation proper)."""
+    return planes.forward()
 
 
 def correlation_backward(in1, in2, gout, pad_size, kernel_size, max_displacement, stride1, stride2,

@@ -9,6 +9,13 @@ shipped with the reference; benchmarks run on random weights).  Unlike the refer
 The confidence mask ``(sum_c (im1 - warp(im2, flow))^2 < 0.02)`` (flownet.py:50) is one libflowops
 kernel (warp + squared error + threshold) instead of a warp, a subtraction, a square, a reduction and
 a comparison.
+
+As-run quirk that is reproduced on purpose: inside the reference's FlowNet, ``self.resample`` does NOT
+reach the ``Resample2d()`` submodule assigned at flownet.py:17.  ``Model`` defines a *method* ``resample``
+(base_model.py:129, the ``grid_sample`` warp); nn.Module keeps submodules in ``_modules`` and
+``__getattr__`` only runs when normal lookup fails, so the class attribute wins.  The confidence mask is
+therefore computed with the ``grid_sample`` warp (align_corners=False on the vid2vid grid), and so it is
+here: the same shadowing happens in this class, and the fused kernel runs in GRIDSAMPLE mode.
 """
 from abc import ABC
 
@@ -66,7 +73,7 @@ class FlowNet(Model, ABC):
         data1 = torch.cat([im1.unsqueeze(2), im2.unsqueeze(2)], dim=2)
         flow1 = self.flowNet(data1)
         if self.fuse_conf and flow1.dtype == torch.float32 and im1.dtype == torch.float32:
-            conf = _F.warp_conf_forward(im1, im2, flow1, 0.02)
+            conf = _F.warp_conf_forward(im1, im2, flow1, 0.02, _F.WARP_GRIDSAMPLE)
         else:
             conf = (self.norm(im1 - self.resample(im2, flow1)) < 0.02).float()
         if old_h != new_h:

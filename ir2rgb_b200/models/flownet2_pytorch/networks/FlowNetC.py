@@ -6,7 +6,10 @@ s1 1, s2 2 -> 441 channels), and the cost volume joins a 32-channel redirect of 
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
+from .... import functional as _F
+from . import submodules as _sm
 from .correlation_package.correlation import Correlation
 from .submodules import add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
 
@@ -40,13 +43,37 @@ class FlowNetC(nn.Module):
         c2 = self.conv2(self.conv1(frame))
         return c2, self.conv3(c2)
 
+    def _fused_features_and_cost(self, x):
+        """Inference fast path on a channels_last conv body: conv3's bias + LeakyReLU epilogue writes the
+        correlation's input planes directly (flowops_corr_planes_from_conv), so neither a separate activation
+        pass nor the correlation's own layout pre-pass runs.  Same values as the plain path, bit for bit."""
+        conv3, act3 = self.conv3[0], self.conv3[1]
+        c2a = self.conv2(self.conv1(x[:, 0:3]))
+        c2b = self.conv2(self.conv1(x[:, 3:]))
+        y3a = F.conv2d(c2a, conv3.weight, None, conv3.stride, conv3.padding)
+        y3b = F.conv2d(c2b, conv3.weight, None, conv3.stride, conv3.padding)
+        if not (_F._is_nhwc(y3a) and _F._is_nhwc(y3b)):
+            return None
+        planes = _F.CorrelationPlanes(y3a.shape, y3a.device)
+        c3a = planes.fill_from_conv_(y3a, conv3.bias, act3.negative_slope, 0, write_act=True)    # also feeds conv_redir
+        planes.fill_from_conv_(y3b, conv3.bias, act3.negative_slope, 1, write_act=False)         # only the correlation reads it
+        return c2a, c3a, _F.correlation_planes_forward(planes)
+
     def forward(self, x):
-        c2a, c3a = self.tower(x[:, 0:3])
-        _, c3b = self.tower(x[:, 3:])
-        if self.fp16:       # the operator is fp32-only, as in the reference (FlowNetC.py:86-87)
-            cost = self.corr(c3a.float(), c3b.float()).half()
+        fused = None
+        if (_sm.FUSE_EPILOGUE and not torch.is_grad_enabled() and not self.fp16 and not self.batchNorm and x.is_cuda
+                and x.dtype == torch.float32 and self.conv3[0].weight.is_contiguous(memory_format=torch.channels_last)
+                and not self.conv3[0].weight.is_contiguous()):
+            fused = self._fused_features_and_cost(x)
+        if fused is not None:
+            c2a, c3a, cost = fused
         else:
-            cost = self.corr(c3a, c3b)
+            c2a, c3a = self.tower(x[:, 0:3])
+            _, c3b = self.tower(x[:, 3:])
+            if self.fp16:       # the operator is fp32-only, as in the reference (FlowNetC.py:86-87)
+                cost = self.corr(c3a.float(), c3b.float()).half()
+            else:
+                cost = self.corr(c3a, c3b)
         cost = self.corr_activation(cost)
         c3 = self.conv3_1(torch.cat((self.conv_redir(c3a), cost), 1))
         c4 = self.conv4_1(self.conv4(c3))

@@ -69,7 +69,9 @@ class OracleFlowNet(nn.Module):
         if state_dict is not None:
             net.load_state_dict(state_dict)
         self.flowNet = swap_ops(net, kind).to(device).eval()
-        self.resample = {"torch": _TorchResample2d, "ref": _RefResample2d}[kind]()
+        # flownet.py:50 calls `self.resample`, which in the reference resolves to the METHOD Model.resample
+        # (base_model.py:129: get_grid + F.grid_sample), not to the Resample2d submodule of the same name
+        self.resample = tr.networks_resample
 
     @torch.no_grad()
     def forward(self, im1, im2):

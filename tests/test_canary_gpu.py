@@ -127,7 +127,7 @@ def test_fused_glue_stays_in_bounds(lib):
     assert lib.flowops_warp_diff_norm_fwd(x0, x1, 6 * hw, p(flow), p(warped), 3 * hw, p(norm), hw, B, 3, H, W, None) == 0
     cbuf, conf = guarded(B * hw)
     a, b = x[:, :3].contiguous(), x[:, 3:].contiguous()
-    assert lib.flowops_warp_conf_fwd(p(a), p(b), p(flow), p(conf), ctypes.c_float(0.02), B, 3, H, W, None) == 0
+    assert lib.flowops_warp_conf_fwd(p(a), p(b), p(flow), p(conf), ctypes.c_float(0.02), B, 3, H, W, 0, None, None, None) == 0
     ybuf, y = guarded(B * 5 * hw)
     y.copy_(torch.randn(B * 5 * hw, device="cuda"))
     bias = torch.randn(5, device="cuda")

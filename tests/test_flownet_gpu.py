@@ -68,10 +68,15 @@ def test_fused_glue_is_bit_identical_to_operator_chain(nets):
     _, norm_only = F.warp_diff_norm_forward(x, flow, need_warped=False)
     assert torch.equal(norm_only, n_ref)
     # confidence mask
-    conf = F.warp_conf_forward(x[:, :3].contiguous(), x[:, 3:].contiguous(), flow, 0.02)
+    conf = F.warp_conf_forward(x[:, :3].contiguous(), x[:, 3:].contiguous(), flow, 0.02, F.WARP_RESAMPLE2D)
     t = x[:, :3] - w_ref
     conf_ref = (torch.sum(t * t, dim=1, keepdim=True) < 0.02).float()
     assert (conf != conf_ref).float().mean().item() <= 1e-4
+    # as-run mode of the reference's FlowNet: the grid_sample warp (Model.resample shadows the Resample2d submodule)
+    from ir2rgb_b200.models import networks
+    conf_gs = F.warp_conf_forward(x[:, :3].contiguous(), x[:, 3:].contiguous(), flow, 0.02, F.WARP_GRIDSAMPLE)
+    t = x[:, :3] - networks.resample(x[:, 3:].contiguous(), flow)
+    assert (conf_gs != (torch.sum(t * t, dim=1, keepdim=True) < 0.02).float()).float().mean().item() <= 1e-4
 
 
 def test_flownet_wrapper_shapes_and_resize_path(nets):
@@ -168,3 +173,30 @@ def test_cat_channels_matches_torch_cat(flowops_lib, chans):
     req = [p.clone().requires_grad_() for p in parts]
     F.cat_channels(req).sum().backward()
     assert all(r.grad is not None for r in req)
+
+
+def test_channels_last_flownet_with_fused_conv3_epilogue_matches_plain_path(flowops_lib):
+    """channels_last conv body: conv3's bias+LeakyReLU epilogue writes the correlation's planes directly.
+    Same network with every fusion switched off must give the same flow, bit for bit."""
+    from ir2rgb_b200.models.flownet import FlowNet
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(9)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, True, False
+    try:
+        net = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[0], checkpoints_dir=".", name="t").eval()
+        net.flowNet = net.flowNet.to(memory_format=torch.channels_last)
+        a = 2 * torch.rand(2, 3, 128, 192, device="cuda") - 1
+        b = 2 * torch.rand(2, 3, 128, 192, device="cuda") - 1
+        flow_fused, conf_fused = net(a, b)
+        sm.FUSE_EPILOGUE = False
+        net.flowNet.fuse_glue = False
+        net.fuse_conf = False
+        try:
+            flow_plain, conf_plain = net(a, b)
+        finally:
+            sm.FUSE_EPILOGUE = True
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = prev
+    assert torch.equal(flow_fused, flow_plain)
+    assert (conf_fused != conf_plain).float().mean().item() <= 1e-4

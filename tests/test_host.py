@@ -76,3 +76,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_flownet_resample_resolves_to_the_method_like_the_reference():
+    """In the reference, `self.resample` inside FlowNet is Model.resample (the grid_sample warp), because the class
+    method shadows the Resample2d submodule assigned in __init__ (flownet.py:17,50; base_model.py:129).  The drop-in
+    keeps both the attribute layout and the lookup result."""
+    from ir2rgb_b200.models.base_model import Model
+    from ir2rgb_b200.models.flownet import FlowNet
+    assert FlowNet.resample is Model.resample
+
+    class Probe(Model):
+        def __init__(self):
+            super().__init__(gpu_ids=[], checkpoints_dir=".", name="probe")
+            self.resample = torch.nn.Identity()
+
+        def save(self, label):
+            pass
+
+    p = Probe()
+    assert isinstance(p._modules["resample"], torch.nn.Identity)
+    assert getattr(p.resample, "__func__", None) is Model.resample

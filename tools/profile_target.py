@@ -1,5 +1,5 @@
 """Tiny launcher for ncu: runs ONE operator a few times at its BASELINE config.
-    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
+    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_fwd_c4b16|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
 """
 import os
 import sys
@@ -17,6 +17,9 @@ if op in ("corr_fwd", "corr_bwd"):
     a, b = torch.randn(8, 256, 48, 64, device="cuda"), torch.randn(8, 256, 48, 64, device="cuda")
     go = torch.randn(8, 441, 48, 64, device="cuda")
     fn = (lambda: F.correlation_forward(a, b, *P)) if op == "corr_fwd" else (lambda: F.correlation_backward(a, b, go, *P))
+elif op == "corr_fwd_c4b16":       # the shape bench.py's FlowNet2 step runs per micro-batch of 16 pairs
+    a, b = torch.randn(16, 256, 64, 128, device="cuda"), torch.randn(16, 256, 64, 128, device="cuda")
+    fn = lambda: F.correlation_forward(a, b, *P)
 elif op == "corr_fwd_c4":
     a, b = torch.randn(8, 256, 64, 128, device="cuda"), torch.randn(8, 256, 64, 128, device="cuda")
     fn = lambda: F.correlation_forward(a, b, *P)

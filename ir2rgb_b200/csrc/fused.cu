@@ -13,7 +13,7 @@
 //       reference `self.resample` inside FlowNet resolves to the METHOD Model.resample (base_model.py:129, the
 //       grid_sample warp), not to the Resample2d submodule assigned at flownet.py:17 -- a class attribute shadows
 //       an nn.Module submodule of the same name -- so the as-run mask uses mode GRIDSAMPLE; both modes exist here.
-#include "warp.cuh"
+#include "warp_rows.cuh"
 
 namespace flowops {
 
@@ -117,7 +117,19 @@ extern "C" int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, 
                     (!warped || warped_batch_stride >= (size_t)C * hw), FLOWOPS_EINVAL,
                     "warp_diff_norm_fwd: batch stride smaller than one item");
     FLOWOPS_REQUIRE((size_t)C * hw < (1ull << 31), FLOWOPS_EUNSUPPORTED, "warp_diff_norm_fwd: C*H*W exceeds int32 indexing");
+    FLOWOPS_REQUIRE(H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED, "warp_diff_norm_fwd: H, W above 2^22 are not supported");
     cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 3) {
+        // row-pipelined gather (warp_rows.cuh) with the subtract + ChannelNorm epilogue
+        WarpArgs a{};
+        a.img = img1; a.img_bs = img_batch_stride; a.flow = flow; a.ref = img0; a.ref_bs = img_batch_stride;
+        a.out = warped; a.out_bs = warped_batch_stride; a.aux = norm; a.aux_bs = norm_batch_stride;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
+        a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+        if (warped) launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_DIFF_NORM, true>(a, st);
+        else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_DIFF_NORM, false>(a, st);
+        return check_launch("warp_diff_norm_fwd");
+    }
     const unsigned grid = fused_grid((size_t)B * hw);
 #define LAUNCH(CT)                                                                                              \
     do {                                                                                                        \
@@ -126,7 +138,7 @@ extern "C" int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, 
         else warp_diff_norm_kernel<CT, false><<<grid, 256, 0, st>>>(img0, img1, img_batch_stride, flow,        \
                         warped, warped_batch_stride, norm, norm_batch_stride, B, C, H, W);                     \
     } while (0)
-    if (C == 3) LAUNCH(3); else LAUNCH(0);
+    LAUNCH(0);
 #undef LAUNCH
     return check_launch("warp_diff_norm_fwd");
 }
@@ -139,17 +151,30 @@ extern "C" int flowops_warp_conf_fwd(const float *im1, const float *im2, const f
     FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "warp_conf_fwd: bad shape %dx%dx%dx%d", B, C, H, W);
     FLOWOPS_REQUIRE((size_t)C * H * W < (1ull << 31), FLOWOPS_EUNSUPPORTED, "warp_conf_fwd: C*H*W exceeds int32 indexing");
     FLOWOPS_REQUIRE(mode == FLOWOPS_WARP_RESAMPLE2D || mode == FLOWOPS_WARP_GRIDSAMPLE, FLOWOPS_EINVAL, "warp_conf_fwd: unknown mode %d", mode);
+    FLOWOPS_REQUIRE(H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED, "warp_conf_fwd: H, W above 2^22 are not supported");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = fused_grid((size_t)B * H * W);
+    float invx = 0.f, invy = 0.f, mulx, muly;
     if (mode == FLOWOPS_WARP_GRIDSAMPLE) {
         FLOWOPS_REQUIRE(lin_x && lin_y && H > 1 && W > 1, FLOWOPS_EINVAL, "warp_conf_fwd: GRIDSAMPLE mode needs the linspace tables and H, W > 1");
-        float invx, invy, mulx, muly;
         gs_scales(H, W, invx, invy, mulx, muly);
-        if (C == 3) warp_conf_kernel<FLOWOPS_WARP_GRIDSAMPLE, 3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, lin_x, lin_y, invx, invy);
-        else warp_conf_kernel<FLOWOPS_WARP_GRIDSAMPLE, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, lin_x, lin_y, invx, invy);
-    } else {
-        if (C == 3) warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 3><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
-        else warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
     }
+    if (C <= 3) {
+        // row-pipelined gather (warp_rows.cuh) with the sum-of-squares threshold epilogue
+        WarpArgs a{};
+        const size_t chw = (size_t)C * H * W;
+        a.img = im2; a.img_bs = chw; a.flow = flow; a.ref = im1; a.ref_bs = chw;
+        a.aux = conf; a.aux_bs = (size_t)H * W;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
+        a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+        a.lin_x = lin_x; a.lin_y = lin_y; a.invx = invx; a.invy = invy; a.thresh = thresh;
+        if (mode == FLOWOPS_WARP_GRIDSAMPLE) launch_warp_rows<FLOWOPS_WARP_GRIDSAMPLE, EPI_CONF, false>(a, st);
+        else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONF, false>(a, st);
+        return check_launch("warp_conf_fwd");
+    }
+    if (mode == FLOWOPS_WARP_GRIDSAMPLE)
+        warp_conf_kernel<FLOWOPS_WARP_GRIDSAMPLE, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, lin_x, lin_y, invx, invy);
+    else
+        warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
     return check_launch("warp_conf_fwd");
 }

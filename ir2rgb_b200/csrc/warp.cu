@@ -22,7 +22,7 @@
 // products in fp64, the fourth in fp32, fp32 adds in TL,TR,BL,BR order) and is bit-identical to it.
 // GRIDSAMPLE reproduces ATen's fp32 op chain (GridSampler.cuh: unnormalize -> clip -> floor ->
 // weights as differences -> nw,ne,sw,se FFMA chain).
-#include "warp.cuh"
+#include "warp_rows.cuh"
 
 namespace flowops {
 
@@ -239,11 +239,18 @@ static int launch_fwd(const float *img, const float *flow, float *out, int B, in
                       const float *lx, const float *ly, float invx, float invy, cudaStream_t st)
 {
     dim3 grid, block;
-    warp_launch_shape(B, H, W, grid, block);
-    if (C == 3) warp_fwd_kernel<MODE, 3><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else if (C == 2) warp_fwd_kernel<MODE, 2><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else if (C == 1) warp_fwd_kernel<MODE, 1><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
-    else warp_fwd_kernel<MODE, 0><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
+    if (C <= 3) {
+        // row-pipelined kernel (warp_rows.cuh)
+        WarpArgs a{};
+        a.img = img; a.img_bs = (size_t)C * H * W; a.flow = flow; a.out = out; a.out_bs = (size_t)C * H * W;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
+        a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+        a.lin_x = lx; a.lin_y = ly; a.invx = invx; a.invy = invy;
+        launch_warp_rows<MODE, EPI_STORE, true>(a, st);
+        return check_launch("warp_fwd");
+    }
+    warp_launch_shape(B, H, W, grid, block);      // any other channel count: channel loop at run time
+    warp_fwd_kernel<MODE, 0><<<grid, block, 0, st>>>(img, flow, out, B, C, H, W, lx, ly, invx, invy);
     return check_launch("warp_fwd");
 }
 
@@ -283,6 +290,7 @@ static int warp_check(const char *who, const void *img, const void *flow, int B,
     FLOWOPS_REQUIRE(img && flow, FLOWOPS_EINVAL, "%s: null pointer", who);
     FLOWOPS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "%s: bad shape %dx%dx%dx%d", who, B, C, H, W);
     FLOWOPS_REQUIRE((size_t)C * H * W < (1ull << 31), FLOWOPS_EUNSUPPORTED, "%s: C*H*W exceeds int32 indexing", who);
+    FLOWOPS_REQUIRE(H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED, "%s: H, W above 2^22 are not supported", who);
     FLOWOPS_REQUIRE(mode == FLOWOPS_WARP_RESAMPLE2D || mode == FLOWOPS_WARP_GRIDSAMPLE, FLOWOPS_EINVAL, "%s: unknown mode %d", who, mode);
     if (mode == FLOWOPS_WARP_GRIDSAMPLE) {
         FLOWOPS_REQUIRE(lin_x && lin_y, FLOWOPS_EINVAL, "%s: GRIDSAMPLE mode needs the linspace tables", who);

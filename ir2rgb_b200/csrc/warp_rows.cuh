@@ -1,0 +1,256 @@
+// warp_rows.cuh -- the row-pipelined forward gather shared by flowops_warp_fwd (warp.cu) and the fused
+// FlowNet2 glue kernels (fused.cu).
+//
+// Why it looks like this (ncu, profiles/ncu_warp_fwd_smooth_r01.txt): a thread-per-pixel forward warp is
+// neither HBM- nor L1-bound but LATENCY-bound (long_scoreboard 9.6 of 16 stall cycles): every pixel pays a
+// flow load and then a dependent gather, one after the other, and the bit-exact fp64 weights of the
+// reference keep the conversion (XU) pipe 63 % busy, with ~240 instructions per pixel, most of them 64-bit
+// address arithmetic.  Here a thread walks `rows` consecutive rows of one column:
+//   * the flow of row y+1 is in flight while row y is gathered and blended, so the two dependent latencies
+//     overlap (a deeper pipeline with double-buffered gathers was measured: no better, 24 more registers);
+//   * consecutive rows share their corner rows in L1 (sector hit rate 57 % -> 72 %);
+//   * the batch index is block-uniform and corners are 32-bit offsets from one opaque base: one IMAD.WIDE per
+//     corner row, the right-hand neighbour is an immediate +4 (134 instructions per pixel, 37 of them the
+//     reference's fp64 arithmetic);
+//   * floor / int<->float conversions run on the FP32/ALU pipes with exact magic-number arithmetic, which
+//     leaves the XU pipe only the 20 F2F conversions per pixel that the reference's mixed precision forces.
+// Measured on B200, config 3, smooth flow: 110 -> 81 us (RESAMPLE2D), 114 -> 80 us (GRIDSAMPLE), bit-identical.
+#pragma once
+#include "warp.cuh"
+
+namespace flowops {
+
+constexpr float kMagic15 = 12582912.f;   // 1.5 * 2^23: ulp is 1 on [2^23, 2^24)
+
+// v is an integer-valued float in [0, 2^22)
+__device__ __forceinline__ int small_float_as_int(float v)
+{
+    return __float_as_int(__fadd_rn(v, kMagic15)) - 0x4B400000;
+}
+// i in [0, 2^23)
+__device__ __forceinline__ float small_int_as_float(int i)
+{
+    return __fsub_rn(__int_as_float(0x4B000000 | i), 8388608.f);
+}
+
+struct WarpArgs {
+    const float *img;  size_t img_bs;    // gather source [B,C,H,W] view, batch stride in floats
+    const float *flow;                   // [B,2,H,W] contiguous, pixels
+    const float *ref;  size_t ref_bs;    // fused epilogues: the frame the warp is compared with
+    float *out;        size_t out_bs;    // warped frame (may be null for DIFF_NORM)
+    float *aux;        size_t aux_bs;    // DIFF_NORM: norm plane; CONF: mask plane
+    int B, C, H, W, rows;
+    float wm1, hm1;                      // (float)(W-1), (float)(H-1)
+    const float *lin_x, *lin_y;          // GRIDSAMPLE tables
+    float invx, invy, thresh;
+};
+
+enum { EPI_STORE = 0, EPI_DIFF_NORM = 1, EPI_CONF = 2 };
+
+// per-pixel state between the pipeline stages.  Corner addressing is kept as two 32-bit row offsets
+// (top-left, bottom-left) plus "the right-hand column is one to the right" -- one 64-bit address per
+// corner ROW and an immediate +4 for the right neighbour, instead of four 64-bit addresses per channel.
+template <int MODE> struct PixPrep;
+template <> struct PixPrep<FLOWOPS_WARP_RESAMPLE2D> {
+    unsigned o_t, o_b;      // yT*W + xL, yB*W + xL
+    bool ex;                // xR == xL + 1 (false when both clamp to the same border column)
+    R2dWeights w;
+};
+template <> struct PixPrep<FLOWOPS_WARP_GRIDSAMPLE> {
+    unsigned o_t, o_b;      // iy_nw*W + ix_nw, and the row below (same row when it is out of bounds: never read)
+    bool in_e, in_s;
+    float nw, ne, sw, se;
+};
+
+// resample2d_kernel.cu:40-51 with the conversions moved off the XU pipe (same values bit for bit)
+__device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q, const WarpArgs &a, float xfl, float yfl,
+                                         int /*x*/, int /*y*/, float dx, float dy)
+{
+    const float xf = __fadd_rn(xfl, dx), yf = __fadd_rn(yfl, dy);
+    // floor on the FP32 pipe: round to nearest integer with the 1.5*2^23 trick, step down if that rounded up.
+    // Exact for |v| < 2^22; anything larger (or inf / NaN) takes the FRND path, one rare branch for both axes.
+    float fx = __fsub_rn(__fadd_rn(xf, kMagic15), kMagic15); fx = fx > xf ? __fsub_rn(fx, 1.f) : fx;
+    float fy = __fsub_rn(__fadd_rn(yf, kMagic15), kMagic15); fy = fy > yf ? __fsub_rn(fy, 1.f) : fy;
+    if (__builtin_expect(!(fmaxf(fabsf(xf), fabsf(yf)) < 4194304.f), 0)) { fx = floorf(xf); fy = floorf(yf); }
+    // max(min((int)f, n-1), 0) == (int)clamp(f, 0, n-1) for every f, NaN and inf included;
+    // the right / bottom neighbour is a different pixel iff the floor lies in [0, n-2]
+    const unsigned xL = (unsigned)small_float_as_int(fminf(fmaxf(fx, 0.f), a.wm1));
+    const unsigned yT = (unsigned)small_float_as_int(fminf(fmaxf(fy, 0.f), a.hm1));
+    q.ex = fx >= 0.f && fx < a.wm1;
+    q.o_t = yT * (unsigned)a.W + xL;
+    q.o_b = (fy >= 0.f && fy < a.hm1) ? q.o_t + (unsigned)a.W : q.o_t;
+    const float alpha = __fsub_rn(xf, fx), beta = __fsub_rn(yf, fy);
+    const double wa = 1. - (double)alpha, wb = 1. - (double)beta;
+    q.w.w_tl = wa * wb; q.w.w_tr = (double)alpha * wb; q.w.w_bl = wa * (double)beta;
+    q.w.w_br = __fmul_rn(alpha, beta);
+}
+
+// models/networks.py:97-98 + ATen grid_sampler (align_corners=False, border); see gs_coords / gs_weights
+__device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q, const WarpArgs &a, float /*xfl*/, float /*yfl*/,
+                                         int x, int y, float dx, float dy)
+{
+    const float gx = __fadd_rn(__ldg(a.lin_x + x), __fmul_rn(dx, a.invx));
+    const float gy = __fadd_rn(__ldg(a.lin_y + y), __fmul_rn(dy, a.invy));
+    float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), a.wm1 + 1.f, -1.f), 0.5f);
+    float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), a.hm1 + 1.f, -1.f), 0.5f);
+    ix = fminf(a.wm1, fmaxf(ix, 0.f));
+    iy = fminf(a.hm1, fmaxf(iy, 0.f));
+    // the clipped coordinate is in [0, n-1]: the magic-number floor needs no slow path
+    float fx = __fsub_rn(__fadd_rn(ix, kMagic15), kMagic15); fx = fx > ix ? __fsub_rn(fx, 1.f) : fx;
+    float fy = __fsub_rn(__fadd_rn(iy, kMagic15), kMagic15); fy = fy > iy ? __fsub_rn(fy, 1.f) : fy;
+    const float ex = __fadd_rn(fx, 1.f), ey = __fadd_rn(fy, 1.f);        // (float)ix_se, (float)iy_se
+    q.nw = __fmul_rn(__fsub_rn(ex, ix), __fsub_rn(ey, iy));
+    q.ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ey, iy));
+    q.sw = __fmul_rn(__fsub_rn(ex, ix), __fsub_rn(iy, fy));
+    q.se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+    q.in_e = ex <= a.wm1; q.in_s = ey <= a.hm1;
+    q.o_t = (unsigned)small_float_as_int(fy) * (unsigned)a.W + (unsigned)small_float_as_int(fx);
+    q.o_b = q.in_s ? q.o_t + (unsigned)a.W : q.o_t;
+}
+
+template <int CT> struct PixVals { float v[CT][4]; float r[CT]; };
+
+template <int CT, bool NEED_REF>
+__device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q,
+                                           const float *__restrict__ src, const float *__restrict__ ref, unsigned hw)
+{
+    const float *pt = src + q.o_t, *pb = src + q.o_b;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        // the right-hand loads must not wait for the left-hand values: a clamped column is patched in at blend time
+        g.v[c][0] = __ldg(pt); g.v[c][2] = __ldg(pb);
+        g.v[c][1] = q.ex ? __ldg(pt + 1) : 0.f;
+        g.v[c][3] = q.ex ? __ldg(pb + 1) : 0.f;
+        if (NEED_REF) { g.r[c] = ldg_stream(ref); ref += hw; }
+        pt += hw; pb += hw;
+    }
+}
+template <int CT, bool NEED_REF>
+__device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q,
+                                           const float *__restrict__ src, const float *__restrict__ ref, unsigned hw)
+{
+    const float *pt = src + q.o_t, *pb = src + q.o_b;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        g.v[c][0] = __ldg(pt);
+        g.v[c][1] = q.in_e ? __ldg(pt + 1) : 0.f;
+        g.v[c][2] = q.in_s ? __ldg(pb) : 0.f;
+        g.v[c][3] = (q.in_e && q.in_s) ? __ldg(pb + 1) : 0.f;
+        if (NEED_REF) { g.r[c] = ldg_stream(ref); ref += hw; }
+        pt += hw; pb += hw;
+    }
+}
+
+__device__ __forceinline__ float pix_blend(const PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q, const float (&v)[4])
+{
+    return r2d_blend(q.w, v[0], q.ex ? v[1] : v[0], v[2], q.ex ? v[3] : v[2]);
+}
+// out_acc += val * weight in nw, ne, sw, se order, skipping out-of-bounds corners (ATen grid_sampler_2d_kernel)
+__device__ __forceinline__ float pix_blend(const PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q, const float (&v)[4])
+{
+    float acc = __fmaf_rn(v[0], q.nw, 0.f);
+    if (q.in_e) acc = __fmaf_rn(v[1], q.ne, acc);
+    if (q.in_s) acc = __fmaf_rn(v[2], q.sw, acc);
+    if (q.in_e && q.in_s) acc = __fmaf_rn(v[3], q.se, acc);
+    return acc;
+}
+
+// `out` / `aux` point at this pixel in channel 0 of this batch item
+template <int MODE, int CT, int EPI, bool WRITE_WARPED>
+__device__ __forceinline__ void pix_finish(const WarpArgs &a, const PixPrep<MODE> &q, const PixVals<CT> &g,
+                                           float *__restrict__ out, float *__restrict__ aux, unsigned hw)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const float val = pix_blend(q, g.v[c]);
+        if (WRITE_WARPED) { stg_stream(out, val); out += hw; }
+        if (EPI == EPI_DIFF_NORM) {
+            const float d = __fsub_rn(g.r[c], val);                   // img0 - warped (models.py:110)
+            acc = __fmaf_rn(d, d, acc);                               // channelnorm_kernel.cu:55-56
+        } else if (EPI == EPI_CONF) {
+            const float d = __fsub_rn(g.r[c], val);
+            // torch.sum(t*t, dim=1): products are rounded before they are added (flownet.py:56-57)
+            acc = c == 0 ? __fmul_rn(d, d) : __fadd_rn(acc, __fmul_rn(d, d));
+        }
+    }
+    if (EPI == EPI_DIFF_NORM) stg_stream(aux, __fsqrt_rn(acc));
+    if (EPI == EPI_CONF) stg_stream(aux, acc < a.thresh ? 1.f : 0.f);
+}
+
+// grid: (W / blockDim.x, H / (blockDim.y * rows), B)  -- the batch index is block-uniform, so every base
+// pointer below lives in uniform registers and per-thread addressing is 32-bit offsets
+template <int MODE, int CT, int EPI, bool WRITE_WARPED>
+__global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant__ WarpArgs a)
+{
+    constexpr bool NEED_REF = EPI != EPI_STORE;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
+    if (x >= a.W || y0 >= a.H) return;
+    const int y1 = min(y0 + a.rows, a.H);
+    const unsigned hw = (unsigned)a.H * a.W, W = (unsigned)a.W;
+    const size_t b = blockIdx.z;
+    const float *src = a.img + b * a.img_bs;
+    asm("" : "+l"(src));     // keep the batch base as one opaque 64-bit value (no b*stride folded into every gather)
+    const unsigned p0 = (unsigned)y0 * W + (unsigned)x;
+    const float *fl = a.flow + b * 2 * hw + p0;                       // walks down the column
+    const float *ref = NEED_REF ? a.ref + b * a.ref_bs + p0 : src;    // unused when !NEED_REF
+    float *out = WRITE_WARPED ? a.out + b * a.out_bs + p0 : nullptr;
+    float *aux = EPI != EPI_STORE ? a.aux + b * a.aux_bs + p0 : nullptr;
+    const float xfl = small_int_as_float(x);
+    float yfl = small_int_as_float(y0);
+    float dx = ldg_stream(fl), dy = ldg_stream(fl + hw);
+    for (int y = y0; y < y1; ++y) {
+        float ndx = 0.f, ndy = 0.f;
+        if (y + 1 < y1) { ndx = ldg_stream(fl + W); ndy = ldg_stream(fl + W + hw); }     // next row's flow
+        PixPrep<MODE> cur;
+        PixVals<CT> vcur;
+        pix_prep(cur, a, xfl, yfl, x, y, dx, dy);
+        pix_gather<CT, NEED_REF>(vcur, cur, src, ref, hw);
+        pix_finish<MODE, CT, EPI, WRITE_WARPED>(a, cur, vcur, out, aux, hw);
+        dx = ndx; dy = ndy;
+        fl += W; ref += W; out += W; aux += W; yfl = __fadd_rn(yfl, 1.f);
+    }
+}
+
+// 256-thread blocks shaped to the image width: whole warps lie along x (coalescing), the block's rows
+// are `rows` apart so that each thread walks its own strip
+static inline void warp_rows_shape(int B, int H, int W, int rows, dim3 &grid, dim3 &block)
+{
+    const int bx = W >= 256 ? 256 : (W > 64 ? 128 : (W > 32 ? 64 : 32));
+    block = dim3(bx, 256 / bx, 1);
+    const int strip = (int)block.y * rows;
+    grid = dim3((W + bx - 1) / bx, (H + strip - 1) / strip, B);     // callers split B > 65535
+}
+
+// rows per thread: long strips amortise the pipeline fill, but the grid should still be several waves
+static inline int warp_rows_pick(int B, int H, int W)
+{
+    const long long px = (long long)B * H * W;
+    int rows = 4;
+    while (rows > 1 && px / (256LL * rows) < 4LL * kNumSMs * 5) rows >>= 1;
+    return rows;
+}
+
+// C must be 1..3 (compile-time channel counts; the register pipeline is sized by them)
+template <int MODE, int EPI, bool WRITE_WARPED>
+static inline void launch_warp_rows(WarpArgs a, cudaStream_t st)
+{
+    const int B = a.B;
+    const size_t hw = (size_t)a.H * a.W;
+    for (int b0 = 0; b0 < B; b0 += 65535) {            // gridDim.z limit
+        WarpArgs c = a;
+        c.B = B - b0 < 65535 ? B - b0 : 65535;
+        c.img = a.img + (size_t)b0 * a.img_bs; c.flow = a.flow + (size_t)b0 * 2 * hw;
+        if (a.ref) c.ref = a.ref + (size_t)b0 * a.ref_bs;
+        if (a.out) c.out = a.out + (size_t)b0 * a.out_bs;
+        if (a.aux) c.aux = a.aux + (size_t)b0 * a.aux_bs;
+        dim3 grid, block;
+        warp_rows_shape(c.B, c.H, c.W, c.rows, grid, block);
+        if (a.C == 3) warp_rows_kernel<MODE, 3, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
+        else if (a.C == 2) warp_rows_kernel<MODE, 2, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
+        else warp_rows_kernel<MODE, 1, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
+    }
+}
+
+}  // namespace flowops

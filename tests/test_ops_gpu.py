@@ -162,6 +162,57 @@ def test_resample2d_grad_flags(ops):
         ops.Resample2d(kernel_size=3)(img2, flow2)
 
 
+def _special_flow(H, W, rng):
+    """Flow values that exercise every branch of the coordinate arithmetic: exact integers, half-integers, the
+    2^22 boundary of the FP32-pipe floor, huge / infinite / NaN displacements, signed zeros, every border."""
+    specials = np.array([0.0, -0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 1e-20, -1e-20, 0.99999994, -0.99999994,
+                         4194303.5, -4194303.5, 4194304.0, -4194304.0, 4194304.5, 8388607.5, -8388607.5,
+                         1e9, -1e9, 3e38, -3e38, np.inf, -np.inf, np.nan, W - 1.0, -(W - 1.0), W - 1.5, H - 1.0,
+                         -(H - 1.0), 2.0 ** -126, 1e-40], dtype=np.float32)
+    flow = (3.0 * rng.standard_normal((1, 2, H, W))).astype(np.float32)
+    idx = rng.integers(0, specials.size, size=(1, 2, H, W))
+    mask = rng.random((1, 2, H, W)) < 0.5
+    flow[mask] = specials[idx[mask]]
+    # make the flow cancel the pixel index at some places so that x + dx is exactly 0 / W-1 / -1
+    flow[0, 0, 0, :] = -np.arange(W, dtype=np.float32)
+    flow[0, 0, 1, :] = (W - 1) - np.arange(W, dtype=np.float32)
+    flow[0, 0, 2, :] = -1.0 - np.arange(W, dtype=np.float32)
+    return flow
+
+
+def test_resample2d_special_values_bit_exact(ops, c_oracle, ref):
+    """The forward replaces floorf / int conversions by FP32-pipe arithmetic (warp_rows.cuh); every special value
+    must still give the reference's bits (C restatement of resample2d_kernel.cu:40-62 and, live, the reference's
+    own kernel)."""
+    rng = np.random.default_rng(5)
+    H, W = 24, 40
+    img = rng.standard_normal((1, 3, H, W)).astype(np.float32)
+    flow = _special_flow(H, W, rng)
+    out = ops.Resample2d()(cu(img), cu(flow)).cpu().numpy()
+    want = c_oracle.resample2d_fwd(img, flow)
+    def same_bits(a, b):      # NaN payloads differ between x86 and the GPU; everything else must match bit for bit
+        nan = np.isnan(a)
+        return np.array_equal(nan, np.isnan(b)) and np.array_equal(a.view(np.uint32)[~nan], b.view(np.uint32)[~nan])
+    assert same_bits(out, want)
+    live = ref.resample2d_forward(cu(img), cu(flow)).cpu().numpy()
+    assert same_bits(out, live)
+    assert np.isnan(out).mean() < 0.5
+
+
+def test_networks_resample_special_values_match_aten(ops):
+    """Same for the grid_sample mode: ATen's own CUDA kernel is the reference for these inputs."""
+    from oracle import torch_ref as tr
+    rng = np.random.default_rng(6)
+    H, W = 24, 40
+    img = cu(rng.standard_normal((1, 3, H, W)).astype(np.float32))
+    flow = cu(_special_flow(H, W, rng))
+    out = ops.networks.resample(img, flow)
+    want = tr.networks_resample(img, flow)
+    both_nan = torch.isnan(out) & torch.isnan(want)
+    assert torch.equal(torch.isnan(out), torch.isnan(want))
+    assert maxrel(torch.where(both_nan, torch.zeros_like(out), out), torch.where(both_nan, torch.zeros_like(out), want)) <= 1e-6
+
+
 @pytest.mark.parametrize("flavour", ["randn", "bilinear_up", "nearest_up"])
 def test_resample2d_vs_reference_ext_full_size(ops, ref, flavour):
     """SURVEY 8d C3 shapes (batch 4 of the 16 to bound test time), the three flow flavours."""

@@ -224,7 +224,8 @@ def ops_table(pk, ffma):
     res = opbench.run(iters=10, skip_ref=True, quiet=True, ffma=ffma)
     out = {}
     for k, v in res["ops"].items():
-        out[k] = {"us": round(v["us"], 2), "bound": v["bound"], "frac": round(v["frac"], 4),
+        out[k] = {"us": round(v["us"], 2), "us_single_flushed": round(v["us_single_flushed"], 2),
+                  "bound": v["bound"], "frac": round(v["frac"], 4),
                   "achieved": round(v.get("achieved_gbs", v.get("achieved_tflops", 0.0)), 2),
                   "unit": "GB/s" if v["bound"] == "hbm" else "TFLOP/s"}
         if "cpu_reference_us" in v:

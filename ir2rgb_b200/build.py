@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libflowops.so")
 SOURCES = ["api.cu", "cnorm.cu", "warp.cu", "corr.cu", "corr_generic.cu", "corr_fast.cu", "corr_bwd.cu", "fused.cu", "epilogue.cu"]
-HEADERS = ["common.cuh", "corr.cuh", "warp.cuh", "warp_rows.cuh", "tma.cuh", os.path.join("..", "..", "include", "flowops.h")]
+HEADERS = ["common.cuh", "corr.cuh", "warp.cuh", "warp_rows.cuh", "warp_rows_bwd.cuh", "tma.cuh", os.path.join("..", "..", "include", "flowops.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

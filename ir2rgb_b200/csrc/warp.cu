@@ -22,7 +22,7 @@
 // products in fp64, the fourth in fp32, fp32 adds in TL,TR,BL,BR order) and is bit-identical to it.
 // GRIDSAMPLE reproduces ATen's fp32 op chain (GridSampler.cuh: unnormalize -> clip -> floor ->
 // weights as differences -> nw,ne,sw,se FFMA chain).
-#include "warp_rows.cuh"
+#include "warp_rows_bwd.cuh"
 
 namespace flowops {
 
@@ -260,9 +260,8 @@ static void launch_bwd_c(const float *img, const float *flow, const float *gout,
                          float invx, float invy, float mulx, float muly, cudaStream_t st)
 {
     const unsigned grid = warp_grid((size_t)B * H * W);
-    if (C == 3) warp_bwd_kernel<MODE, 3, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
-    else if (C == 1) warp_bwd_kernel<MODE, 1, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
-    else warp_bwd_kernel<MODE, 0, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
+    // only channel counts above 3 get here (run-time channel loop); 1..3 use warp_rows_bwd.cuh
+    warp_bwd_kernel<MODE, 0, NI, NF><<<grid, 256, 0, st>>>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly);
 }
 
 template <int MODE>
@@ -273,6 +272,18 @@ static int launch_bwd(const float *img, const float *flow, const float *gout, fl
     if (gimg) {
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, st);
         if (e != cudaSuccess) { set_error("warp_bwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    if (C <= 3) {
+        // row-walking kernel (warp_rows_bwd.cuh)
+        WarpBwdArgs a{};
+        a.img = img; a.flow = flow; a.gout = gout; a.gimg = gimg; a.gflow = gflow;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W, 8);
+        a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+        a.lin_x = lx; a.lin_y = ly; a.invx = invx; a.invy = invy; a.mulx = mulx; a.muly = muly;
+        if (gimg && gflow) launch_warp_rows_bwd<MODE, true, true>(a, st);
+        else if (gimg) launch_warp_rows_bwd<MODE, true, false>(a, st);
+        else launch_warp_rows_bwd<MODE, false, true>(a, st);
+        return check_launch("warp_bwd");
     }
     if (gimg && gflow) launch_bwd_c<MODE, true, true>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);
     else if (gimg) launch_bwd_c<MODE, true, false>(img, flow, gout, gimg, gflow, B, C, H, W, lx, ly, invx, invy, mulx, muly, st);

@@ -224,10 +224,9 @@ static inline void warp_rows_shape(int B, int H, int W, int rows, dim3 &grid, di
 }
 
 // rows per thread: long strips amortise the pipeline fill, but the grid should still be several waves
-static inline int warp_rows_pick(int B, int H, int W)
+static inline int warp_rows_pick(int B, int H, int W, int rows = 4)
 {
     const long long px = (long long)B * H * W;
-    int rows = 4;
     while (rows > 1 && px / (256LL * rows) < 4LL * kNumSMs * 5) rows >>= 1;
     return rows;
 }

@@ -29,6 +29,16 @@
 
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
+/* float -> int as the GPU does it (cvt.rzi.s32.f32): saturating, NaN -> 0.  In C the conversion of an
+ * out-of-range value is undefined (x86 yields INT_MIN), so a flow of 3e38 would clamp to column 0 here and
+ * to column W-1 in the reference kernel. */
+static inline int f2i_cuda(float v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)v;
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* ChannelNorm                                                                                */
@@ -85,10 +95,10 @@ void oracle_resample2d_fwd(const float *img, const float *flow, float *out,
                 const float yf = (float)y + dy;
                 const float alpha = xf - floorf(xf);                       /* :45 */
                 const float beta = yf - floorf(yf);
-                const int xL = imax(imin((int)floorf(xf), W - 1), 0);      /* :48-51 */
-                const int xR = imax(imin((int)(floorf(xf) + 1), W - 1), 0);
-                const int yT = imax(imin((int)floorf(yf), H - 1), 0);
-                const int yB = imax(imin((int)(floorf(yf) + 1), H - 1), 0);
+                const int xL = imax(imin(f2i_cuda(floorf(xf)), W - 1), 0);      /* :48-51 */
+                const int xR = imax(imin(f2i_cuda(floorf(xf) + 1), W - 1), 0);
+                const int yT = imax(imin(f2i_cuda(floorf(yf)), H - 1), 0);
+                const int yB = imax(imin(f2i_cuda(floorf(yf) + 1), H - 1), 0);
                 for (int c = 0; c < C; ++c) {
                     const float tl = img[IDX4(b, c, yT, xL, C, H, W)];
                     const float tr = img[IDX4(b, c, yT, xR, C, H, W)];
@@ -120,12 +130,12 @@ void oracle_resample2d_bwd_img(const float *flow, const float *gout, float *gimg
                     const float dy = flow[IDX4(b, 1, y, x, 2, H, W)];
                     const float xf = (float)x + dx;
                     const float yf = (float)y + dy;
-                    const float alpha = xf - (float)(int)xf;               /* :97 */
-                    const float beta = yf - (float)(int)yf;                /* :98 */
-                    const int xL = imax(imin((int)floorf(xf), W - 1), 0);  /* :103-106 */
-                    const int xR = imax(imin((int)(floorf(xf) + 1), W - 1), 0);
-                    const int yT = imax(imin((int)floorf(yf), H - 1), 0);
-                    const int yB = imax(imin((int)(floorf(yf) + 1), H - 1), 0);
+                    const float alpha = xf - (float)f2i_cuda(xf);               /* :97 */
+                    const float beta = yf - (float)f2i_cuda(yf);                /* :98 */
+                    const int xL = imax(imin(f2i_cuda(floorf(xf)), W - 1), 0);  /* :103-106 */
+                    const int xR = imax(imin(f2i_cuda(floorf(xf) + 1), W - 1), 0);
+                    const int yT = imax(imin(f2i_cuda(floorf(yf)), H - 1), 0);
+                    const int yB = imax(imin(f2i_cuda(floorf(yf) + 1), H - 1), 0);
                     const float g = gout[IDX4(b, c, y, x, C, H, W)];
                     gimg[IDX4(b, c, yT, xL, C, H, W)] += (1 - alpha) * (1 - beta) * g;   /* :110 */
                     gimg[IDX4(b, c, yT, xR, C, H, W)] += (alpha) * (1 - beta) * g;       /* :111 */
@@ -148,10 +158,10 @@ void oracle_resample2d_bwd_flow(const float *img, const float *flow, const float
                     const float dy = flow[IDX4(b, 1, y, x, 2, H, W)];
                     const float xf = (float)x + dx;
                     const float yf = (float)y + dy;
-                    const int xL = imax(imin((int)floorf(xf), W - 1), 0);  /* :154-157 */
-                    const int xR = imax(imin((int)(floorf(xf) + 1), W - 1), 0);
-                    const int yT = imax(imin((int)floorf(yf), H - 1), 0);
-                    const int yB = imax(imin((int)(floorf(yf) + 1), H - 1), 0);
+                    const int xL = imax(imin(f2i_cuda(floorf(xf)), W - 1), 0);  /* :154-157 */
+                    const int xR = imax(imin(f2i_cuda(floorf(xf) + 1), W - 1), 0);
+                    const int yT = imax(imin(f2i_cuda(floorf(yf)), H - 1), 0);
+                    const int yB = imax(imin(f2i_cuda(floorf(yf) + 1), H - 1), 0);
                     float output = 0.0f;
                     if (c % 2) {                                           /* :159-170, d/d(dy) */
                         const float gamma = 1 - (xf - floorf(xf));

@@ -112,9 +112,8 @@ class Launches:
     """Counts this repo's kernel launches and times the dominant operator (Correlation forward) with
     CUDA events on the launching stream, live inside the timed region."""
 
-    PER_CALL = {"correlation_forward": 2, "correlation_planes_forward": 1, "warp_diff_norm_forward": 1,
-                "channelnorm_forward": 1, "warp_conf_forward": 1, "warp_forward": 1, "bias_lrelu_": 1, "cat_channels": 3}
-    TIMED = ("correlation_forward", "correlation_planes_forward")
+    TIMED = ("correlation_forward", "correlation_planes_forward", "correlation_planes_forward_into")
+    NO_KERNEL = ("corr_out_shape",)
 
     def __init__(self):
         self.count = 0
@@ -123,21 +122,24 @@ class Launches:
 
     def install(self):
         import torch
+        from ir2rgb_b200 import _lib
         from ir2rgb_b200 import functional as F
-        for name, n in self.PER_CALL.items():
+
+        def hook(what, n):          # every libflowops call that launches kernels goes through _lib.check()
+            if self.enabled and what not in self.NO_KERNEL:
+                self.count += n
+        _lib.launch_hook = hook
+        for name in self.TIMED:
             orig = getattr(F, name)
 
-            def wrapped(*a, _orig=orig, _n=n, _name=name, **k):
+            def wrapped(*a, _orig=orig, _name=name, **k):
                 if not self.enabled:
-                    return _orig(*a, **k)
-                self.count += _n
-                if _name not in self.TIMED:
                     return _orig(*a, **k)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 out = _orig(*a, **k)
                 e1.record()
-                self.corr_events.append((e0, e1, a[0].shape, _name))
+                self.corr_events.append((e0, e1, tuple(a[0].shape), _name))
                 return out
             setattr(F, name, wrapped)
 
@@ -359,7 +361,7 @@ def main():
         if corr_events:
             us = [ev[0].elapsed_time(ev[1]) * 1e3 for ev in corr_events]
             shp = corr_events[0][2]
-            split = corr_events[0][3] == "correlation_planes_forward"
+            split = corr_events[0][3].startswith("correlation_planes_forward")
             flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]
             mean_us = sum(us) / len(us)
             line["roofline"] = {"kernel": "corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split

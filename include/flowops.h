@@ -109,6 +109,14 @@ int flowops_corr_planes_from_conv(const float *y, const float *bias, float slope
 int flowops_corr_fwd_planes(float *out, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Channels-last form of flowops_corr_fwd_planes for a channels_last FlowNetC: the 441-channel cost volume goes to
+ * channels [c_off, c_off + 441) of out, a channels-last [B, H, W, c_dst] tensor, with LeakyReLU(lrelu_slope) applied
+ * (1.0f = none).  That is `corr_activation` and the concat with conv_redir of FlowNetC.py:89-94 folded into the
+ * correlation's store -- same values as correlation -> LeakyReLU -> torch.cat, bit for bit. */
+int flowops_corr_fwd_planes_nhwc(float *out, int c_dst, int c_off, float lrelu_slope,
+                                 int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).
  * gout: [B,oC,oH,oW]; gin1, gin2: [B,C,H,W] (either may be NULL). */
 int flowops_corr_bwd(const float *in1, const float *in2, const float *gout,
@@ -146,6 +154,17 @@ int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow,
  * (channels_last = 0) or NHWC (channels_last = 1); HW = H*W. */
 int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int HW, int channels_last,
                        float slope, void *stream);
+
+/* Out-of-place form for channels-last tensors: dst[pix][c_off + c] = lrelu(y[pix][c] + bias[c]) with y dense
+ * [n_pixels][C] and dst [n_pixels][c_dst].  Lets a decoder deconvolution (submodules.py:34-38) write its activated
+ * output directly into the concat buffer of torch.cat((skip, deconv, flow_up), 1) (e.g. FlowNetS.py:74-76). */
+int flowops_bias_lrelu_nhwc_to(const float *y, const float *bias, float *dst, size_t n_pixels,
+                               int C, int c_dst, int c_off, float slope, void *stream);
+
+/* dst[pix][c_off .. c_off + c_n) = value for every pixel of a channels-last [n_pixels][c_dst] tensor: the zero pad
+ * channels that round a concat buffer up to a multiple of 8 channels (cuDNN otherwise re-pads odd channel counts
+ * -- 1026, 770, 386, 194, 473 ... -- with a kernel of its own in front of every convolution that reads them). */
+int flowops_fill_channels_nhwc(float *dst, size_t n_pixels, int c_dst, int c_off, int c_n, float value, void *stream);
 
 /* Channel concatenation of channels-last tensors: copies src ([n_pixels][c_src], dense) into channels
  * [c_off, c_off + c_src) of dst ([n_pixels][c_dst]).  One call per concatenated tensor (torch.cat of the

@@ -31,10 +31,13 @@ SIGNATURES = {
     "flowops_corr_fwd": (_int, [_vp, _vp, _vp] + [_int] * 10 + [_vp, _sz, _vp]),
     "flowops_corr_planes_from_conv": (_int, [_vp, _vp, ctypes.c_float, _vp, _int] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_fwd_planes": (_int, [_vp] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_corr_fwd_planes_nhwc": (_int, [_vp, _int, _int, ctypes.c_float] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
     "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "flowops_bias_lrelu": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.c_float, _vp]),
+    "flowops_bias_lrelu_nhwc_to": (_int, [_vp, _vp, _vp, _sz, _int, _int, _int, ctypes.c_float, _vp]),
+    "flowops_fill_channels_nhwc": (_int, [_vp, _sz, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_concat_nhwc": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp]),
     "flowops_bench_ffma": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), _vp]),
 }
@@ -66,9 +69,17 @@ def load():
     return lib
 
 
+# kernels (and memsets) each library call launches, keyed by the name the wrappers pass to check();
+# bench.py's `gpu_launches` is counted from this table through `launch_hook`
+KERNELS_PER_CALL = {"corr_fwd": 2, "corr_bwd": 6, "warp_bwd": 2}
+launch_hook = None          # callable(what, n_kernels) or None
+
+
 def check(rc, what):
     """Turn a non-zero return into a RuntimeError, like the reference's AT_ERROR
     (correlation_cuda.cc:81-83)."""
+    if launch_hook is not None and rc == 0:
+        launch_hook(what, KERNELS_PER_CALL.get(what, 1))
     if rc != 0:
         msg = load().flowops_last_error().decode("utf-8", "replace")
         if rc == -2:

@@ -116,3 +116,17 @@ extern "C" int flowops_corr_bwd(const float *in1, const float *in2, const float 
     if (corr_fast_supported(g)) return corr_fast_bwd_launch(in1, in2, gout, gin1, gin2, g, workspace, workspace_bytes, st);
     return corr_bwd_generic_launch(in1, in2, gout, gin1, gin2, g, st);
 }
+
+extern "C" int flowops_corr_fwd_planes_nhwc(float *out, int c_dst, int c_off, float lrelu_slope,
+                                            int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                            void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(out, FLOWOPS_EINVAL, "corr_fwd_planes_nhwc: null pointer");
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_fwd_planes_nhwc: FlowNetC configuration only");
+    FLOWOPS_REQUIRE(c_off >= 0 && c_off + g.D * g.D <= c_dst, FLOWOPS_EINVAL,
+                    "corr_fwd_planes_nhwc: channels [%d, %d) do not fit in %d", c_off, c_off + g.D * g.D, c_dst);
+    return corr_fast_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream, true, c_dst, c_off, lrelu_slope);
+}

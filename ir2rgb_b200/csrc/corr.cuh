@@ -28,7 +28,8 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
                          void *ws, size_t ws_bytes, cudaStream_t st);
 int corr_fast_planes_nhwc(const float *in1, const float *in2, const CorrGeom &g, int only, const float *bias, float slope,
                           float *act, void *ws, size_t ws_bytes, cudaStream_t st);
-int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
+int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
+                   bool nhwc_out = false, int c_dst = 0, int c_off = 0, float slope = 1.f);
 int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
                          const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
 

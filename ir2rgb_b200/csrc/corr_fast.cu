@@ -24,8 +24,6 @@
 //
 // Roofline: FP32-FMA pipe.  Algorithmic work 2*B*H*W*441*C FLOP (dense count, taps that fall in
 // the zero padding included -- the kernel does not skip them).
-#include <stdlib.h>
-
 #include "corr.cuh"
 #include "tma.cuh"
 
@@ -46,8 +44,8 @@ constexpr int kF1Floats = kCK * kTY * kF1W;  // 864
 constexpr int kStageBytes = (kF2Floats + kF1Floats) * 4;   // 41728 (multiple of 128)
 constexpr int kPairs = kTY * kD;             // 63 (row, tj) pairs per tile column block
 constexpr int kEpiPitch = 36;                // floats per staged output row
-constexpr int kEpiGroup = 7;                 // tj values staged per epilogue pass
-constexpr int kEpiRows = kEpiGroup * kD * kTY;              // 441
+constexpr int kEpiGroup = 11;                // tj values staged per epilogue pass: two passes (11 + 10)
+constexpr int kEpiRows = kEpiGroup * kD * kTY;              // 693
 constexpr int kSmemBytes = kStages * kStageBytes;           // 166912
 static_assert(kEpiRows * kEpiPitch * 4 <= kSmemBytes, "epilogue staging must fit in the pipeline buffers");
 static_assert(kStageBytes % 128 == 0 && (kF2Floats * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
@@ -204,10 +202,22 @@ __global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restri
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <int UNROLL>
+// channels-last epilogue staging: [row of the tile][pixel][channel of the group], pitches chosen so that the 21
+// (tj, row) writers of a group hit 21 different banks (see the epilogue)
+constexpr int kNhwcGroup = 11;                                // tj values per epilogue pass: two passes (11 + 10)
+constexpr int kNhwcTjPitch = 24;                              // the 21 channels of one tj, padded so that they start 16-byte aligned
+constexpr int kNhwcPixPitch = kNhwcGroup * kNhwcTjPitch + 4;  // 268 floats per staged pixel
+constexpr int kNhwcRowPitch = kTX * kNhwcPixPitch + 8;        // 8584
+static_assert(kTY * kNhwcRowPitch * 4 <= kSmemBytes, "NHWC epilogue staging must fit in the pipeline buffers");
+
+// NHWC_OUT: the cost volume is written channels-last into channels [c_off, c_off + 441) of a [B, H, W, c_dst]
+// tensor, with LeakyReLU(slope) applied (slope 1 = identity) -- FlowNetC's `corr_activation` and the concat with
+// conv_redir (FlowNetC.py:89-94) folded into the store, for a channels_last conv body.
+template <int UNROLL, bool NHWC_OUT>
 __global__ void __launch_bounds__(256, 1)
 corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-              float *__restrict__ out, int C, int H, int W, int row_tiles, int x_tiles)
+              float *__restrict__ out, int C, int H, int W, int row_tiles, int x_tiles,
+              int c_dst, int c_off, float slope)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -323,9 +333,55 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
     const float inv_nelems = 1.0f / nelems;
     const size_t hw = (size_t)H * W;
     float *out_n = out + (size_t)n * (kD * kD) * hw;
+    if (NHWC_OUT) {
 #pragma unroll 1
-    for (int grp = 0; grp < kD / kEpiGroup; ++grp) {
-        if (live && tj >= grp * kEpiGroup && tj < (grp + 1) * kEpiGroup) {
+        for (int grp = 0; grp < (kD + kNhwcGroup - 1) / kNhwcGroup; ++grp) {
+            const int tj0 = grp * kNhwcGroup;
+            const int n_ch = (min(kD, tj0 + kNhwcGroup) - tj0) * kD;          // 231, then 210
+            if (live && tj >= tj0 && tj < tj0 + kNhwcGroup) {
+                // stage[row][pixel][tj-in-group][24]: a thread's 21 channels of one pixel are contiguous and 16-byte
+                // aligned -> 5 STS.128 + 1 STS.32 per pixel
+                float *dst = stage + yi * kNhwcRowPitch + (xb * kPX) * kNhwcPixPitch + (tj - tj0) * kNhwcTjPitch;
+#pragma unroll
+                for (int k = 0; k < kPX; ++k) {
+                    float v[kD];
+#pragma unroll
+                    for (int i = 0; i < kD; ++i) {
+                        float t;
+                        if (k & 1) t = (i == 0) ? accs[k] : (((i - 1) & 1) ? accp[k][(i - 1) / 2].y : accp[k][(i - 1) / 2].x);
+                        else       t = (i == kD - 1) ? accs[k] : ((i & 1) ? accp[k][i / 2].y : accp[k][i / 2].x);
+                        v[i] = div_nelems(t, nelems, inv_nelems);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kD / 4; ++q)
+                        *reinterpret_cast<float4 *>(dst + k * kNhwcPixPitch + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    dst[k * kNhwcPixPitch + kD - 1] = v[kD - 1];
+                }
+            }
+            __syncthreads();
+            // one warp per pixel: the group's channels are contiguous in the destination pixel
+            for (int pix = warp; pix < kTY * kTX; pix += 8) {
+                const int ry = pix / kTX, cx = pix - ry * kTX;
+                const int y = 2 * (y0 + ry) + py, x = 2 * (x0 + cx) + px;
+                if (y < H && x < W) {
+                    const float *src = stage + ry * kNhwcRowPitch + cx * kNhwcPixPitch;
+                    float *dst = out + (((size_t)n * H + y) * W + x) * c_dst + c_off + tj0 * kD;
+                    for (int ch = lane; ch < n_ch; ch += 32) {
+                        const int tjl = ch / kD;                                   // constant divisor: mul + shift
+                        const float v = src[ch + tjl * (kNhwcTjPitch - kD)];
+                        dst[ch] = v > 0.f ? v : __fmul_rn(v, slope);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int grp = 0; grp < (kD + kEpiGroup - 1) / kEpiGroup; ++grp) {
+        const bool mine = live && tj >= grp * kEpiGroup && tj < (grp + 1) * kEpiGroup;
+        const int n_tj = min(kD, (grp + 1) * kEpiGroup) - grp * kEpiGroup;
+        if (mine) {
             float *dst = stage + ((tj - grp * kEpiGroup) * kD * kTY + yi) * kEpiPitch + xb * kPX;
 #pragma unroll
             for (int i = 0; i < kD; ++i) {
@@ -345,7 +401,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
         // each warp takes (tj-in-group, row) pairs and walks the 21 horizontal displacements with
         // constant strides: one LDS + one STG per output row segment
         const int x = 2 * (x0 + lane) + px;
-        for (int pr = warp; pr < kEpiGroup * kTY; pr += 8) {
+        for (int pr = warp; pr < n_tj * kTY; pr += 8) {
             const int tjl = pr / kTY, ry = pr - tjl * kTY;
             const int y = 2 * (y0 + ry) + py;
             if (y < H && x < W) {
@@ -407,7 +463,8 @@ int corr_fast_planes_nhwc(const float *in1, const float *in2, const CorrGeom &g,
 }
 
 // the correlation proper, on planes already in the workspace
-int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st)
+int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
+                   bool nhwc_out, int c_dst, int c_off, float slope)
 {
     float *P1, *P2;
     int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr_fwd");
@@ -419,19 +476,20 @@ int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cud
     rc = make_plane_map(&tm2, P2, g, p.Hp, p.pitch2, kF2W, kF2H);
     if (rc) return rc;
 
-    static const int unroll = getenv("FLOWOPS_CORR_UNROLL") ? atoi(getenv("FLOWOPS_CORR_UNROLL")) : 2;   // dev knob
-    auto kernel = unroll == 1 ? corr_fwd_fast<1> : corr_fwd_fast<2>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
     const int row_tiles = (p.Hp + kTY - 1) / kTY, x_tiles = (p.Wp + kTX - 1) / kTX;
     const size_t grid = (size_t)g.B * row_tiles * x_tiles * 4;
     FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
-    kernel<<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles);
+    if (nhwc_out)
+        corr_fwd_fast<2, true><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, c_dst, c_off, slope);
+    else
+        corr_fwd_fast<2, false><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, 0, 0, 1.f);
     return check_launch("corr_fwd_fast");
 }
 

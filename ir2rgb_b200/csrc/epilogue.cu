@@ -39,6 +39,40 @@ __global__ void __launch_bounds__(256) bias_lrelu_nchw(float *__restrict__ y, co
     }
 }
 
+// channels-last, out of place into a channel slice of a wider pixel: dst[pix][c_off + c] = lrelu(y[pix][c] + b[c]).
+// The epilogue of a decoder deconvolution writes straight into the concat buffer the next layers read
+// (reference FlowNetS.py:74-76: torch.cat((out_conv5, out_deconv5, flow6_up), 1)), which saves the concat's own
+// read + write of that tensor.  V = float4 when every channel count / offset is a multiple of 4, else float.
+template <typename V>
+__global__ void __launch_bounds__(256) bias_lrelu_nhwc_to(const V *__restrict__ y, const V *__restrict__ bias, V *__restrict__ dst,
+                                                          size_t total, unsigned src_v, unsigned dst_v, unsigned off_v, float slope)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / src_v;
+        const unsigned c = (unsigned)(i - pix * src_v);
+        if constexpr (sizeof(V) == 16) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c);
+            float4 v = ldg_stream4(reinterpret_cast<const float *>(y + i));
+            v.x = lrelu(__fadd_rn(v.x, b.x), slope); v.y = lrelu(__fadd_rn(v.y, b.y), slope);
+            v.z = lrelu(__fadd_rn(v.z, b.z), slope); v.w = lrelu(__fadd_rn(v.w, b.w), slope);
+            reinterpret_cast<float4 *>(dst)[pix * dst_v + off_v + c] = v;
+        } else {
+            reinterpret_cast<float *>(dst)[pix * dst_v + off_v + c] =
+                lrelu(__fadd_rn(reinterpret_cast<const float *>(y)[i], __ldg(reinterpret_cast<const float *>(bias) + c)), slope);
+        }
+    }
+}
+
+// dst[pix][c_off .. c_off + c_n) = value  (the zero pad channels that round a concat buffer up to a multiple of 8)
+__global__ void __launch_bounds__(256) fill_channels_nhwc(float *__restrict__ dst, size_t total, unsigned c_n, unsigned c_dst,
+                                                          unsigned c_off, float value)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / c_n;
+        dst[pix * c_dst + c_off + (unsigned)(i - pix * c_n)] = value;
+    }
+}
+
 // any shape / alignment
 __global__ void __launch_bounds__(256) bias_lrelu_scalar(float *__restrict__ y, const float *__restrict__ bias,
                                                          size_t total, size_t inner, unsigned C, int channels_last, float slope)
@@ -72,6 +106,40 @@ extern "C" int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int
     else
         bias_lrelu_scalar<<<grid_for(total), 256, 0, st>>>(y, bias, total, (size_t)HW, (unsigned)C, channels_last, slope);
     return check_launch("bias_lrelu");
+}
+
+extern "C" int flowops_bias_lrelu_nhwc_to(const float *y, const float *bias, float *dst, size_t n_pixels,
+                                          int C, int c_dst, int c_off, float slope, void *stream)
+{
+    FLOWOPS_REQUIRE(y && bias && dst, FLOWOPS_EINVAL, "bias_lrelu_nhwc_to: null pointer");
+    FLOWOPS_REQUIRE(n_pixels > 0 && C > 0 && c_off >= 0 && c_off + C <= c_dst, FLOWOPS_EINVAL,
+                    "bias_lrelu_nhwc_to: bad channel range %d + %d of %d", c_off, C, c_dst);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto grid_for = [](size_t items) {
+        size_t blocks = (items + 255) / 256;
+        const size_t cap = (size_t)kNumSMs * 8 * 16;
+        return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+    };
+    const size_t total = n_pixels * (size_t)C;
+    if (((C | c_dst | c_off) & 3) == 0 && aligned16(y) && aligned16(dst) && aligned16(bias))
+        bias_lrelu_nhwc_to<float4><<<grid_for(total / 4), 256, 0, st>>>(reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(bias),
+                                                                        reinterpret_cast<float4 *>(dst), total / 4, C / 4, c_dst / 4, c_off / 4, slope);
+    else
+        bias_lrelu_nhwc_to<float><<<grid_for(total), 256, 0, st>>>(y, bias, dst, total, C, c_dst, c_off, slope);
+    return check_launch("bias_lrelu_nhwc_to");
+}
+
+extern "C" int flowops_fill_channels_nhwc(float *dst, size_t n_pixels, int c_dst, int c_off, int c_n, float value, void *stream)
+{
+    FLOWOPS_REQUIRE(dst, FLOWOPS_EINVAL, "fill_channels_nhwc: null pointer");
+    FLOWOPS_REQUIRE(n_pixels > 0 && c_n > 0 && c_off >= 0 && c_off + c_n <= c_dst, FLOWOPS_EINVAL,
+                    "fill_channels_nhwc: bad channel range %d + %d of %d", c_off, c_n, c_dst);
+    const size_t total = n_pixels * (size_t)c_n;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    fill_channels_nhwc<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, total, c_n, c_dst, c_off, value);
+    return check_launch("fill_channels_nhwc");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -191,24 +191,59 @@ def bias_lrelu_(y, bias, slope):
     return y
 
 
-def cat_channels(tensors):
-    """torch.cat(tensors, dim=1).  When autograd is off and every input is a dense channels_last fp32 CUDA
-    tensor the copy runs as one libflowops kernel per input; anything else goes to torch.cat."""
+def _cat_fast(tensors):
     t0 = tensors[0]
-    fast = (not torch.is_grad_enabled() and all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
-                                                and t.dim() == 4 and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:]
-                                                and t.device == t0.device and _is_nhwc(t) for t in tensors))
-    if not fast or t0.numel() == 0:
+    return (not torch.is_grad_enabled() and t0.numel() > 0 and
+            all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4
+                and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:] and t.device == t0.device and _is_nhwc(t)
+                for t in tensors))
+
+
+class ConcatBuffer:
+    """A channels_last [B, C_pad, H, W] concat target that producers fill slice by slice (inference only).
+    C_pad rounds the channel count up to a multiple of `pad_to`; the pad channels are zero, and the layers that
+    read the buffer use weights zero-padded to match (networks/submodules.py), so results are those of the
+    unpadded concat."""
+
+    def __init__(self, like, c_total, pad_to=8):
+        B, _, H, W = like.shape
+        self.c_total = c_total
+        self.c_pad = -(-c_total // pad_to) * pad_to
+        self.n_pixels = B * H * W
+        with torch.cuda.device_of(like):
+            self.tensor = torch.empty((B, self.c_pad, H, W), device=like.device, dtype=torch.float32,
+                                      memory_format=torch.channels_last)
+            if self.c_pad > c_total:
+                check(_lib.load().flowops_fill_channels_nhwc(_p(self.tensor), self.n_pixels, self.c_pad, c_total,
+                                                             self.c_pad - c_total, ctypes.c_float(0.0), _stream()), "fill_channels_nhwc")
+
+    def copy_in(self, t, c_off):
+        with torch.cuda.device_of(t):
+            check(_lib.load().flowops_concat_nhwc(_p(t), _p(self.tensor), self.n_pixels, t.shape[1], self.c_pad, c_off, _stream()),
+                  "concat_nhwc")
+        return c_off + t.shape[1]
+
+    def bias_lrelu_in(self, y, bias, slope, c_off):
+        """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y."""
+        if not _is_nhwc(y) or y.shape[0] * y.shape[2] * y.shape[3] != self.n_pixels:
+            raise ValueError("bias_lrelu_in: y must be dense channels_last with the buffer's batch and spatial shape")
+        with torch.cuda.device_of(y):
+            check(_lib.load().flowops_bias_lrelu_nhwc_to(_p(y), _p(bias), _p(self.tensor), self.n_pixels, y.shape[1], self.c_pad,
+                                                         c_off, ctypes.c_float(slope), _stream()), "bias_lrelu_nhwc_to")
+        return c_off + y.shape[1]
+
+
+def cat_channels(tensors, pad_to=1):
+    """torch.cat(tensors, dim=1).  When autograd is off and every input is a dense channels_last fp32 CUDA
+    tensor the copy runs as one libflowops kernel per input; anything else goes to torch.cat.  With pad_to > 1 the
+    fast path returns a tensor whose channel count is rounded up to a multiple of pad_to (zero channels)."""
+    if not _cat_fast(tensors):
         return torch.cat(tensors, 1)
-    B, _, H, W = t0.shape
-    c_total = sum(t.shape[1] for t in tensors)
-    with torch.cuda.device_of(t0):
-        out = torch.empty((B, c_total, H, W), device=t0.device, dtype=torch.float32, memory_format=torch.channels_last)
-        lib, off = _lib.load(), 0
-        for t in tensors:
-            check(lib.flowops_concat_nhwc(_p(t), _p(out), B * H * W, t.shape[1], c_total, off, _stream()), "concat_nhwc")
-            off += t.shape[1]
-    return out
+    buf = ConcatBuffer(tensors[0], sum(t.shape[1] for t in tensors), pad_to)
+    off = 0
+    for t in tensors:
+        off = buf.copy_in(t, off)
+    return buf.tensor
 
 
 # ---------------------------------------------------------------------------------------------
@@ -282,6 +317,18 @@ class CorrelationPlanes:
             check(_lib.load().flowops_corr_fwd_planes(_p(out), B, C, H, W, *self.params, _p(self.ws), self.nbytes, _stream()),
                   "corr_fwd_planes")
         return out
+
+
+def correlation_planes_forward_into(planes, buf, c_off, slope):
+    """The correlation proper, written channels-last into channels [c_off, c_off + 441) of the ConcatBuffer `buf`
+    with LeakyReLU(slope) applied (module-level so that bench.py can time it)."""
+    B, C, H, W = planes.shape
+    if buf.n_pixels != B * H * W:
+        raise ValueError("correlation_planes_forward_into: buffer shape does not match the correlation output")
+    with torch.cuda.device(planes.device):
+        check(_lib.load().flowops_corr_fwd_planes_nhwc(_p(buf.tensor), buf.c_pad, c_off, ctypes.c_float(slope), B, C, H, W,
+                                                       *planes.params, _p(planes.ws), planes.nbytes, _stream()), "corr_fwd_planes_nhwc")
+    return c_off + correlation_out_shape(H, W, *planes.params)[0]
 
 
 def correlation_planes_forward(planes):

@@ -57,7 +57,7 @@ class FlowNetC(nn.Module):
         planes = _F.CorrelationPlanes(y3a.shape, y3a.device)
         c3a = planes.fill_from_conv_(y3a, conv3.bias, act3.negative_slope, 0, write_act=True)    # also feeds conv_redir
         planes.fill_from_conv_(y3b, conv3.bias, act3.negative_slope, 1, write_act=False)         # only the correlation reads it
-        return c2a, c3a, _F.correlation_planes_forward(planes)
+        return c2a, c3a, planes
 
     def forward(self, x):
         fused = None
@@ -66,7 +66,14 @@ class FlowNetC(nn.Module):
                 and not self.conv3[0].weight.is_contiguous()):
             fused = self._fused_features_and_cost(x)
         if fused is not None:
-            c2a, c3a, cost = fused
+            # the concat of FlowNetC.py:94 is allocated first (473 -> 480 channels, zero pad); conv_redir's epilogue and
+            # the correlation (with corr_activation folded into its store) each write their channel slice
+            c2a, c3a, planes = fused
+            buf = _F.ConcatBuffer(c3a, self.conv_redir[0].out_channels + 441, _sm.PAD_CHANNELS)
+            off = self.conv_redir[0].out_channels
+            self.conv_redir(c3a, into=(buf, 0))
+            _F.correlation_planes_forward_into(planes, buf, off, self.corr_activation.negative_slope)
+            cat = buf.tensor
         else:
             c2a, c3a = self.tower(x[:, 0:3])
             _, c3b = self.tower(x[:, 3:])
@@ -74,8 +81,8 @@ class FlowNetC(nn.Module):
                 cost = self.corr(c3a.float(), c3b.float()).half()
             else:
                 cost = self.corr(c3a, c3b)
-        cost = self.corr_activation(cost)
-        c3 = self.conv3_1(torch.cat((self.conv_redir(c3a), cost), 1))
+            cat = torch.cat((self.conv_redir(c3a), self.corr_activation(cost)), 1)
+        c3 = self.conv3_1(cat)
         c4 = self.conv4_1(self.conv4(c3))
         c5 = self.conv5_1(self.conv5(c4))
         c6 = self.conv6_1(self.conv6(c5))

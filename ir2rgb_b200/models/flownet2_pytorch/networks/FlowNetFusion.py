@@ -3,7 +3,8 @@ import torch
 import torch.nn as nn
 
 from .... import functional as _F
-from .submodules import add_layers, deconv, flow_upsampler, i_conv, predict_flow, reference_init
+from . import submodules as _sm
+from .submodules import add_layers, apply_conv, deconv, flow_upsampler, i_conv, predict_flow, reference_init
 
 ENCODER = [("conv0", 11, 64, 3, 1), ("conv1", 64, 64, 3, 2), ("conv1_1", 64, 128, 3, 1), ("conv2", 128, 128, 3, 2),
            ("conv2_1", 128, 128, 3, 1)]
@@ -25,7 +26,8 @@ class FlowNetFusion(nn.Module):
         c1 = self.conv1_1(self.conv1(c0))
         c2 = self.conv2_1(self.conv2(c1))
         flow2 = self.predict_flow2(c2)
-        cat1 = _F.cat_channels((c1, self.deconv1(c2), self.upsampled_flow2_to_1(flow2)))
-        flow1 = self.predict_flow1(self.inter_conv1(cat1))
-        cat0 = _F.cat_channels((c0, self.deconv0(cat1), self.upsampled_flow1_to_0(flow1)))
-        return self.predict_flow0(self.inter_conv0(cat0))
+        # inference: the concat buffers carry zero pad channels up to a multiple of 8 (162 -> 168, 82 -> 88)
+        cat1 = _F.cat_channels((c1, self.deconv1(c2), self.upsampled_flow2_to_1(flow2)), pad_to=_sm.PAD_CHANNELS)
+        flow1 = self.predict_flow1(apply_conv(self.inter_conv1, cat1))
+        cat0 = _F.cat_channels((c0, apply_conv(self.deconv0, cat1), self.upsampled_flow1_to_0(flow1)), pad_to=_sm.PAD_CHANNELS)
+        return self.predict_flow0(apply_conv(self.inter_conv0, cat0))

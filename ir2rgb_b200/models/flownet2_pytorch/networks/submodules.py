@@ -15,21 +15,78 @@ LEAK = 0.1
 FUSE_EPILOGUE = True      # inference only: conv -> one libflowops pass for bias + LeakyReLU
 
 
+PAD_CHANNELS = 8          # inference only: concat buffers are rounded up to this many channels (zero-filled)
+
+
+def padded_weight(conv, cin):
+    """conv.weight zero-padded along its input-channel axis to `cin` channels, cached on the module.  Lets a layer
+    read a concat buffer whose channel count was rounded up (cuDNN pads odd channel counts -- 1026, 770, 386, 194,
+    473 ... -- with a kernel of its own on every call; the extra zero channels add exact zeros to each sum)."""
+    w = conv.weight
+    axis = 0 if isinstance(conv, nn.ConvTranspose2d) else 1
+    if w.shape[axis] == cin:
+        return w
+    key = (w.data_ptr(), w._version, cin)
+    cache = conv.__dict__.get("_flowops_wpad")
+    if cache is None or cache[0] != key:
+        shape = list(w.shape)
+        shape[axis] = cin - w.shape[axis]
+        wp = torch.cat((w.detach(), w.new_zeros(shape)), axis)
+        if w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous():
+            wp = wp.contiguous(memory_format=torch.channels_last)
+        cache = (key, wp)
+        conv.__dict__["_flowops_wpad"] = cache
+    return cache[1]
+
+
+def _raw_conv(conv, x, bias):
+    w = padded_weight(conv, x.shape[1])
+    if isinstance(conv, nn.ConvTranspose2d):
+        return F.conv_transpose2d(x, w, bias, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+    return F.conv2d(x, w, bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def apply_conv(mod, x):
+    """mod(x) where x may carry zero pad channels beyond mod's in_channels (mod: ConvAct, Conv2d, ConvTranspose2d,
+    or an nn.Sequential starting with one of the two)."""
+    if isinstance(mod, ConvAct):
+        return mod(x)
+    conv = mod[0] if isinstance(mod, nn.Sequential) else mod
+    cin = conv.weight.shape[0 if isinstance(conv, nn.ConvTranspose2d) else 1] * conv.groups
+    if x.shape[1] == cin:
+        return mod(x)
+    y = _raw_conv(conv, x, conv.bias)
+    if isinstance(mod, nn.Sequential):
+        for layer in list(mod)[1:]:
+            y = layer(y)
+    return y
+
+
 class ConvAct(nn.Sequential):
     """(Conv2d | ConvTranspose2d) + LeakyReLU with the reference's nn.Sequential indexing (so `conv1.0.weight`
-    keeps its name).  Under no_grad on CUDA fp32 the bias add and the activation run as one in-place
-    libflowops kernel after a bias-free convolution -- bit-identical to conv(+bias) -> LeakyReLU."""
+    keeps its name).  Under no_grad on CUDA fp32 the bias add and the activation run as one libflowops kernel
+    after a bias-free convolution -- bit-identical to conv(+bias) -> LeakyReLU -- either in place, or (`into`)
+    straight into a channel slice of the concat buffer the next layers read."""
 
-    def forward(self, x):
+    def fusable(self, x):
+        return (FUSE_EPILOGUE and len(self) == 2 and self[0].bias is not None and not torch.is_grad_enabled()
+                and x.is_cuda and x.dtype == torch.float32)
+
+    def forward(self, x, into=None):
         conv = self[0]
-        if (FUSE_EPILOGUE and len(self) == 2 and conv.bias is not None and not torch.is_grad_enabled()
-                and x.is_cuda and x.dtype == torch.float32):
-            if isinstance(conv, nn.ConvTranspose2d):
-                y = F.conv_transpose2d(x, conv.weight, None, conv.stride, conv.padding, conv.output_padding,
-                                       conv.groups, conv.dilation)
-            else:
-                y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if self.fusable(x):
+            y = _raw_conv(conv, x, None)
+            if into is not None:
+                buf, c_off = into
+                buf.bias_lrelu_in(y, conv.bias, self[1].negative_slope, c_off)
+                return None
             return _F.bias_lrelu_(y, conv.bias, self[1].negative_slope)
+        assert into is None
+        if x.shape[1] != conv.weight.shape[0 if isinstance(conv, nn.ConvTranspose2d) else 1] * conv.groups:
+            y = _raw_conv(conv, x, conv.bias)          # zero pad channels in x: weights padded to match
+            for layer in list(self)[1:]:
+                y = layer(y)
+            return y
         return super().forward(x)
 
 
@@ -89,13 +146,26 @@ def add_layers(net, batchNorm, table):
 def refine(net, skips, top, levels, inter=False):
     """Shared coarse-to-fine decoder of FlowNetC / FlowNetS / FlowNetSD (e.g. FlowNetS.py:70-90):
     at each level predict a flow, upsample it and the features, concatenate with the skip tensor.
-    Returns the flows from finest to coarsest."""
+    Returns the flows from finest to coarsest.
+
+    Inference on a channels_last body: the concat buffer is allocated first (channel count rounded up to a
+    multiple of PAD_CHANNELS, pad channels zero), the skip tensor and the upsampled flow are copied in, and the
+    deconvolution's bias + LeakyReLU epilogue writes its slice directly."""
     feat = top
-    flows = [getattr(net, "predict_flow%d" % (levels[0] + 1))(top)]
+    flows = [apply_conv(getattr(net, "predict_flow%d" % (levels[0] + 1)), top)]
     for lv in levels:
         up = getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv))(flows[0])
-        dec = getattr(net, "deconv%d" % lv)(feat)
-        feat = _F.cat_channels((skips[lv], dec, up))
-        head_in = getattr(net, "inter_conv%d" % lv)(feat) if inter else feat
-        flows.insert(0, getattr(net, "predict_flow%d" % lv)(head_in))
+        deconv_lv = getattr(net, "deconv%d" % lv)
+        skip = skips[lv]
+        if deconv_lv.fusable(feat) and _F._cat_fast((skip, up)) and _F._is_nhwc(feat):
+            c_dec = deconv_lv[0].out_channels
+            buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + up.shape[1], PAD_CHANNELS)
+            off = buf.copy_in(skip, 0)
+            deconv_lv(feat, into=(buf, off))
+            buf.copy_in(up, off + c_dec)
+            feat = buf.tensor
+        else:
+            feat = _F.cat_channels((skip, deconv_lv(feat), up))
+        head_in = apply_conv(getattr(net, "inter_conv%d" % lv), feat) if inter else feat
+        flows.insert(0, apply_conv(getattr(net, "predict_flow%d" % lv), head_in))
     return flows

@@ -428,3 +428,52 @@ def test_correlation_channels_last_inputs(ops, shape):
     assert out.is_contiguous() and torch.equal(out, ref_out)
     # mixed layouts fall back to the NCHW path
     assert torch.equal(corr(a_cl, b), ref_out)
+
+
+# =============================================================================================
+# inference glue for a channels_last FlowNet2 body: concat buffers filled slice by slice
+# =============================================================================================
+@pytest.mark.parametrize("shape", [(2, 64, 24, 40), (1, 256, 64, 128), (1, 32, 13, 21)])
+def test_correlation_nhwc_output_with_lrelu_matches_nchw_path(ops, shape):
+    """flowops_corr_fwd_planes_nhwc: the cost volume written channels-last into a slice of the (padded) concat
+    buffer with corr_activation folded in == correlation -> LeakyReLU -> cat, bit for bit (FlowNetC.py:89-94)."""
+    from ir2rgb_b200 import functional as F
+    torch.manual_seed(21)
+    B, C, H, W = shape
+    a = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    b = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    want = torch.nn.functional.leaky_relu(F.correlation_forward(a, b, 20, 1, 20, 1, 2), 0.1)
+    planes = F.CorrelationPlanes(a.shape, a.device)
+    zero_bias = torch.zeros(C, device="cuda")
+    planes.fill_from_conv_(a.clone(memory_format=torch.channels_last), zero_bias, 1.0, 0, write_act=False)   # slope 1: identity
+    planes.fill_from_conv_(b.clone(memory_format=torch.channels_last), zero_bias, 1.0, 1, write_act=False)
+    buf = F.ConcatBuffer(a, 32 + 441, 8)
+    assert buf.c_pad == 480 and buf.tensor.is_contiguous(memory_format=torch.channels_last)
+    buf.tensor[:, :32] = 7.0
+    end = F.correlation_planes_forward_into(planes, buf, 32, 0.1)
+    assert end == 473
+    assert torch.equal(buf.tensor[:, 32:473], want)
+    assert (buf.tensor[:, :32] == 7.0).all() and (buf.tensor[:, 473:] == 0).all()
+
+
+@pytest.mark.parametrize("c,c_total,c_off", [(64, 130, 64), (30, 45, 7), (512, 1026, 512)])
+def test_epilogue_into_concat_buffer(ops, c, c_total, c_off):
+    from ir2rgb_b200 import functional as F
+    torch.manual_seed(22)
+    y = torch.randn(2, c, 12, 20, device="cuda").contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda")
+    buf = F.ConcatBuffer(y, c_total, 8)
+    assert buf.c_pad % 8 == 0 and buf.c_pad >= c_total
+    buf.tensor[:, :c_total] = -3.0
+    buf.bias_lrelu_in(y, bias, 0.1, c_off)
+    want = torch.nn.functional.leaky_relu(y + bias.view(1, -1, 1, 1), 0.1)
+    assert torch.equal(buf.tensor[:, c_off:c_off + c], want)
+    untouched = torch.ones(buf.c_pad, dtype=torch.bool, device="cuda")
+    untouched[c_off:c_off + c] = False
+    untouched[c_total:] = False
+    assert (buf.tensor[:, untouched] == -3.0).all() and (buf.tensor[:, c_total:] == 0).all()
+    # padded concat == torch.cat plus zero channels
+    parts = (torch.randn(2, 5, 12, 20, device="cuda").contiguous(memory_format=torch.channels_last), y)
+    with torch.no_grad():
+        cat = F.cat_channels(parts, pad_to=8)
+    assert cat.shape[1] == -(-(c + 5) // 8) * 8 and torch.equal(cat[:, :c + 5], torch.cat(parts, 1)) and (cat[:, c + 5:] == 0).all()

@@ -107,6 +107,10 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# (timed entry point, (B, C, H, W)) -> DRAM bytes per launch measured with `ncu --set full` (profiles/)
+NCU_DRAM_BYTES = {("correlation_planes_forward_into", (16, 256, 64, 128)): 281336576 + 196153088}
+
+
 # ---------------------------------------------------------------------------------------------------
 class Launches:
     """Counts this repo's kernel launches and times the dominant operator (Correlation forward) with
@@ -364,10 +368,14 @@ def main():
             split = corr_events[0][3].startswith("correlation_planes_forward")
             flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]
             mean_us = sum(us) / len(us)
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this launch shape, from the committed
+            # `ncu --set full` capture (tools/profile_target.py corr_fwd_nhwc_b16); algorithmic bytes are 499.1 MB
+            traffic = NCU_DRAM_BYTES.get((corr_events[0][3], tuple(shp)))
             line["roofline"] = {"kernel": "corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split
                                           else "corr_fwd (corr_planarize + corr_fwd_fast)", "bound": "fp32",
                                 "achieved": flop / mean_us / 1e6, "peak": ffma, "unit": "TFLOP/s",
-                                "frac": flop / mean_us / 1e6 / ffma, "traffic": None,
+                                "frac": flop / mean_us / 1e6 / ffma, "traffic": traffic,
+                                "traffic_source": "profiles/ncu_corr_fwd_nhwc_b16_r01.txt (bytes per launch)" if traffic else None,
                                 "peak_source": "flowops_bench_ffma measured on this GPU (nominal 74.4)",
                                 "alg_flop_per_launch": flop, "us_per_launch": mean_us, "launches_timed": len(us),
                                 "share_of_step": sum(us) / (ms_eager * 1e3),

@@ -147,6 +147,24 @@ int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow,
                           float thresh, int B, int C, int H, int W, int mode,
                           const float *lin_x, const float *lin_y, void *stream);
 
+/* The whole concat of models.py:112-114 / 124-126 in one pass, channels-last:
+ *   out[b,y,x, 0:12] = (frame 0, frame 1, Resample2d(frame 1, flow), flow / div_flow, ChannelNorm(frame 0 - warped)),
+ *   out[b,y,x, 12:c_dst] = 0
+ * x: [B,6,H,W] planar stack of both frames, flow: [B,2,H,W], out: [B,H,W,c_dst] (c_dst a multiple of 4, >= 12).
+ * Same values as the separate operators followed by torch.cat, bit for bit (flow / div_flow is evaluated as ATen does for a
+ * CUDA tensor and a Python scalar: a multiply by the fp32 reciprocal; the same holds for rgb_max below); the layout and the padded channel count
+ * are what the first convolution of the next FlowNetS (FlowNetS.py:20) wants on a channels_last body. */
+int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *flow, float div_flow, float *out, int c_dst,
+                                       int B, int H, int W, void *stream);
+
+/* FlowNet2 input preparation (models.py:97-101): x = (inputs - rgb_mean) / rgb_max with the two frames stacked
+ * along channels.  inputs: [B,3,2,H,W]; rgb_mean: [B,3] (the caller computes the mean).  Outputs, each optional:
+ * x_planar [B,6,H,W]; channels-last copies padded with zero channels -- xa_nhwc4 / xb_nhwc4 [B,H,W,4] (frame 0 / 1,
+ * FlowNetC's tower inputs, FlowNetC.py:75-76) and x_nhwc8 [B,H,W,8] (both frames, FlowNetSD's conv0). */
+int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_max,
+                          float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
+                          int B, int H, int W, void *stream);
+
 /* ---- Conv-body epilogue (FlowNet2 inference glue, not an operator of the reference's native surface) ---- */
 
 /* In place: t = y + bias[c]; y = t > 0 ? t : t * slope.  Replaces the separate bias-add and LeakyReLU kernels

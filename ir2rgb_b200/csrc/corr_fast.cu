@@ -333,7 +333,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
     const float inv_nelems = 1.0f / nelems;
     const size_t hw = (size_t)H * W;
     float *out_n = out + (size_t)n * (kD * kD) * hw;
-    if (NHWC_OUT) {
+    if constexpr (NHWC_OUT) {
 #pragma unroll 1
         for (int grp = 0; grp < (kD + kNhwcGroup - 1) / kNhwcGroup; ++grp) {
             const int tj0 = grp * kNhwcGroup;
@@ -375,8 +375,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
             }
             __syncthreads();
         }
-        return;
-    }
+    } else {
 #pragma unroll 1
     for (int grp = 0; grp < (kD + kEpiGroup - 1) / kEpiGroup; ++grp) {
         const bool mine = live && tj >= grp * kEpiGroup && tj < (grp + 1) * kEpiGroup;
@@ -412,6 +411,7 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
             }
         }
         __syncthreads();
+    }
     }
 }
 

@@ -178,3 +178,77 @@ extern "C" int flowops_warp_conf_fwd(const float *im1, const float *im2, const f
         warp_conf_kernel<FLOWOPS_WARP_RESAMPLE2D, 0><<<grid, 256, 0, st>>>(im1, im2, flow, conf, thresh, B, C, H, W, nullptr, nullptr, 0.f, 0.f);
     return check_launch("warp_conf_fwd");
 }
+
+extern "C" int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *flow, float div_flow, float *out, int c_dst,
+                                                  int B, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(x && flow && out, FLOWOPS_EINVAL, "warp_diff_norm_concat_nhwc: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0, FLOWOPS_EINVAL, "warp_diff_norm_concat_nhwc: bad shape %dx%dx%d", B, H, W);
+    FLOWOPS_REQUIRE(c_dst >= 12 && (c_dst & 3) == 0 && aligned16(out), FLOWOPS_EINVAL,
+                    "warp_diff_norm_concat_nhwc: c_dst must be a multiple of 4 and at least 12, out 16-byte aligned");
+    FLOWOPS_REQUIRE((size_t)6 * H * W < (1ull << 31) && H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED,
+                    "warp_diff_norm_concat_nhwc: frame too large for int32 indexing");
+    const size_t hw = (size_t)H * W;
+    WarpArgs a{};
+    a.img = x + 3 * hw; a.img_bs = 6 * hw; a.flow = flow; a.ref = x; a.ref_bs = 6 * hw;
+    a.aux = out; a.aux_bs = hw * c_dst; a.c_dst = c_dst; a.inv_div_flow = 1.0f / div_flow;
+    a.B = B; a.C = 3; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
+    a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+    launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONCAT, false>(a, (cudaStream_t)stream);
+    return check_launch("warp_diff_norm_concat_nhwc");
+}
+
+// ---------------------------------------------------------------------------------------------
+// FlowNet2 input preparation (models.py:97-101): x = (inputs - rgb_mean) / rgb_max, frames stacked along
+// channels -- written once in every layout its consumers want: planar [B,6,H,W] for the warp kernels, and
+// channels-last copies padded to 4 / 4 / 8 channels for the first convolutions of FlowNetC (per frame) and
+// FlowNetSD (both frames), which otherwise each trigger a slice copy, a layout conversion and cuDNN's own
+// channel padding.
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+__global__ void __launch_bounds__(256) flownet2_prep_kernel(const float *__restrict__ in, const float *__restrict__ mean, float inv_rgb_max,
+                                                            float *__restrict__ xp, float4 *__restrict__ xa, float4 *__restrict__ xb,
+                                                            float4 *__restrict__ x8, unsigned hw, size_t total)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / hw;
+        const unsigned p = (unsigned)(i - b * hw);
+        float v[6];                                          // v[f*3 + c]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float m = __ldg(mean + b * 3 + c);
+#pragma unroll
+            for (int f = 0; f < 2; ++f)                      // inputs[b][c][f][p]
+                v[f * 3 + c] = __fmul_rn(__fsub_rn(ldg_stream(in + ((b * 3 + c) * 2 + f) * hw + p), m), inv_rgb_max);
+        }
+        if (xp) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) xp[(b * 6 + k) * hw + p] = v[k];
+        }
+        if (xa) xa[i] = make_float4(v[0], v[1], v[2], 0.f);
+        if (xb) xb[i] = make_float4(v[3], v[4], v[5], 0.f);
+        if (x8) { x8[2 * i] = make_float4(v[0], v[1], v[2], v[3]); x8[2 * i + 1] = make_float4(v[4], v[5], 0.f, 0.f); }
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_max,
+                                     float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
+                                     int B, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(inputs && rgb_mean, FLOWOPS_EINVAL, "flownet2_prep: null pointer");
+    FLOWOPS_REQUIRE(x_planar || xa_nhwc4 || xb_nhwc4 || x_nhwc8, FLOWOPS_EINVAL, "flownet2_prep: no output requested");
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (size_t)H * W < (1ull << 31), FLOWOPS_EINVAL, "flownet2_prep: bad shape %dx%dx%d", B, H, W);
+    FLOWOPS_REQUIRE(aligned16(xa_nhwc4) && aligned16(xb_nhwc4) && aligned16(x_nhwc8), FLOWOPS_EINVAL, "flownet2_prep: outputs must be 16-byte aligned");
+    const size_t total = (size_t)B * H * W;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    // tensor / python-scalar on CUDA is tensor * (1.0f / scalar) in ATen; reproduced so that x matches models.py:98 bit for bit
+    flownet2_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
+        reinterpret_cast<float4 *>(xa_nhwc4), reinterpret_cast<float4 *>(xb_nhwc4), reinterpret_cast<float4 *>(x_nhwc8),
+        (unsigned)((size_t)H * W), total);
+    return check_launch("flownet2_prep");
+}

@@ -43,9 +43,15 @@ struct WarpArgs {
     float wm1, hm1;                      // (float)(W-1), (float)(H-1)
     const float *lin_x, *lin_y;          // GRIDSAMPLE tables
     float invx, invy, thresh;
+    int c_dst;                           // CONCAT: channels per pixel of the channels-last destination
+    float inv_div_flow;                  // CONCAT: the flow is stored times 1/div_flow (models.py:112; torch divides a CUDA
+                                         // tensor by a Python scalar as a multiply by the fp32 reciprocal)
 };
 
-enum { EPI_STORE = 0, EPI_DIFF_NORM = 1, EPI_CONF = 2 };
+// EPI_CONCAT (C = 3 only): the whole `concat1` / `concat2` tensor of models.py:112-114,124-126 --
+// (frame 0, frame 1, warped frame 1, flow / div_flow, |frame 0 - warped|) -- written channels-last with the pixel
+// padded to c_dst channels (zeros), i.e. the layout and channel count the next FlowNetS's first convolution wants
+enum { EPI_STORE = 0, EPI_DIFF_NORM = 1, EPI_CONF = 2, EPI_CONCAT = 3 };
 
 // per-pixel state between the pipeline stages.  Corner addressing is kept as two 32-bit row offsets
 // (top-left, bottom-left) plus "the right-hand column is one to the right" -- one 64-bit address per
@@ -108,11 +114,12 @@ __device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q, co
     q.o_b = q.in_s ? q.o_t + (unsigned)a.W : q.o_t;
 }
 
-template <int CT> struct PixVals { float v[CT][4]; float r[CT]; };
+template <int CT> struct PixVals { float v[CT][4]; float r[CT]; float s[CT]; };    // corners, reference frame, source frame
 
-template <int CT, bool NEED_REF>
+template <int CT, bool NEED_REF, bool NEED_SELF>
 __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q,
-                                           const float *__restrict__ src, const float *__restrict__ ref, unsigned hw)
+                                           const float *__restrict__ src, const float *__restrict__ ref,
+                                           const float *__restrict__ self, unsigned hw)
 {
     const float *pt = src + q.o_t, *pb = src + q.o_b;
 #pragma unroll
@@ -122,12 +129,14 @@ __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS
         g.v[c][1] = q.ex ? __ldg(pt + 1) : 0.f;
         g.v[c][3] = q.ex ? __ldg(pb + 1) : 0.f;
         if (NEED_REF) { g.r[c] = ldg_stream(ref); ref += hw; }
+        if (NEED_SELF) { g.s[c] = __ldg(self); self += hw; }
         pt += hw; pb += hw;
     }
 }
-template <int CT, bool NEED_REF>
+template <int CT, bool NEED_REF, bool NEED_SELF>
 __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q,
-                                           const float *__restrict__ src, const float *__restrict__ ref, unsigned hw)
+                                           const float *__restrict__ src, const float *__restrict__ ref,
+                                           const float *__restrict__ /*self*/, unsigned hw)
 {
     const float *pt = src + q.o_t, *pb = src + q.o_b;
 #pragma unroll
@@ -158,14 +167,16 @@ __device__ __forceinline__ float pix_blend(const PixPrep<FLOWOPS_WARP_GRIDSAMPLE
 // `out` / `aux` point at this pixel in channel 0 of this batch item
 template <int MODE, int CT, int EPI, bool WRITE_WARPED>
 __device__ __forceinline__ void pix_finish(const WarpArgs &a, const PixPrep<MODE> &q, const PixVals<CT> &g,
-                                           float *__restrict__ out, float *__restrict__ aux, unsigned hw)
+                                           float *__restrict__ out, float *__restrict__ aux, unsigned hw, float dx, float dy)
 {
     float acc = 0.f;
+    float warped[CT];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
         const float val = pix_blend(q, g.v[c]);
+        warped[c] = val;
         if (WRITE_WARPED) { stg_stream(out, val); out += hw; }
-        if (EPI == EPI_DIFF_NORM) {
+        if (EPI == EPI_DIFF_NORM || EPI == EPI_CONCAT) {
             const float d = __fsub_rn(g.r[c], val);                   // img0 - warped (models.py:110)
             acc = __fmaf_rn(d, d, acc);                               // channelnorm_kernel.cu:55-56
         } else if (EPI == EPI_CONF) {
@@ -176,6 +187,14 @@ __device__ __forceinline__ void pix_finish(const WarpArgs &a, const PixPrep<MODE
     }
     if (EPI == EPI_DIFF_NORM) stg_stream(aux, __fsqrt_rn(acc));
     if (EPI == EPI_CONF) stg_stream(aux, acc < a.thresh ? 1.f : 0.f);
+    if (EPI == EPI_CONCAT) {
+        // written for 3-channel frames (the launcher also instantiates CT = 1, 2, which are never launched)
+        float4 *dst = reinterpret_cast<float4 *>(aux);            // c_dst is a multiple of 4: 16-byte aligned pixels
+        dst[0] = make_float4(g.r[0], g.r[1 % CT], g.r[2 % CT], g.s[0]);
+        dst[1] = make_float4(g.s[1 % CT], g.s[2 % CT], warped[0], warped[1 % CT]);
+        dst[2] = make_float4(warped[2 % CT], __fmul_rn(dx, a.inv_div_flow), __fmul_rn(dy, a.inv_div_flow), __fsqrt_rn(acc));
+        for (int q4 = 3; q4 < a.c_dst / 4; ++q4) dst[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // grid: (W / blockDim.x, H / (blockDim.y * rows), B)  -- the batch index is block-uniform, so every base
@@ -184,6 +203,7 @@ template <int MODE, int CT, int EPI, bool WRITE_WARPED>
 __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant__ WarpArgs a)
 {
     constexpr bool NEED_REF = EPI != EPI_STORE;
+    constexpr bool NEED_SELF = EPI == EPI_CONCAT;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
     if (x >= a.W || y0 >= a.H) return;
@@ -196,7 +216,9 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
     const float *fl = a.flow + b * 2 * hw + p0;                       // walks down the column
     const float *ref = NEED_REF ? a.ref + b * a.ref_bs + p0 : src;    // unused when !NEED_REF
     float *out = WRITE_WARPED ? a.out + b * a.out_bs + p0 : nullptr;
-    float *aux = EPI != EPI_STORE ? a.aux + b * a.aux_bs + p0 : nullptr;
+    const unsigned aux_px = EPI == EPI_CONCAT ? (unsigned)a.c_dst : 1u;      // floats per destination pixel
+    float *aux = EPI != EPI_STORE ? a.aux + b * a.aux_bs + (size_t)p0 * aux_px : nullptr;
+    const float *self = src + p0;                                            // CONCAT: frame 1 at this pixel
     const float xfl = small_int_as_float(x);
     float yfl = small_int_as_float(y0);
     float dx = ldg_stream(fl), dy = ldg_stream(fl + hw);
@@ -206,10 +228,10 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
         PixPrep<MODE> cur;
         PixVals<CT> vcur;
         pix_prep(cur, a, xfl, yfl, x, y, dx, dy);
-        pix_gather<CT, NEED_REF>(vcur, cur, src, ref, hw);
-        pix_finish<MODE, CT, EPI, WRITE_WARPED>(a, cur, vcur, out, aux, hw);
+        pix_gather<CT, NEED_REF, NEED_SELF>(vcur, cur, src, ref, self, hw);
+        pix_finish<MODE, CT, EPI, WRITE_WARPED>(a, cur, vcur, out, aux, hw, dx, dy);
         dx = ndx; dy = ndy;
-        fl += W; ref += W; out += W; aux += W; yfl = __fadd_rn(yfl, 1.f);
+        fl += W; ref += W; self += W; out += W; aux += (size_t)W * aux_px; yfl = __fadd_rn(yfl, 1.f);
     }
 }
 

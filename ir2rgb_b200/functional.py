@@ -156,6 +156,42 @@ def warp_diff_norm_forward(x, flow, out=None, need_warped=True):
     return warped, norm
 
 
+def warp_diff_norm_concat(x, flow, div_flow, c_pad=16):
+    """The concat of models.py:112-114 in one pass: returns a channels_last [B, c_pad, H, W] tensor whose first 12
+    channels are (frame 0, frame 1, Resample2d(frame 1, flow), flow / div_flow, ChannelNorm(frame 0 - warped)) and
+    whose remaining channels are zero.  x: [B,6,H,W] contiguous (planar), flow: [B,2,H,W]."""
+    x = _require(x, "x").contiguous()
+    flow = _require(flow, "flow").contiguous()
+    B, C6, H, W = x.shape
+    if C6 != 6 or flow.shape != (B, 2, H, W):
+        raise ValueError("expected x [B,6,H,W] and flow [B,2,H,W], got %s and %s" % (tuple(x.shape), tuple(flow.shape)))
+    with torch.cuda.device_of(x):
+        out = torch.empty((B, c_pad, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if x.numel():
+            check(_lib.load().flowops_warp_diff_norm_concat_nhwc(_p(x), _p(flow), ctypes.c_float(div_flow), _p(out), c_pad,
+                                                                 B, H, W, _stream()), "warp_diff_norm_concat_nhwc")
+    return out
+
+
+def flownet2_prep(inputs, rgb_mean, rgb_max):
+    """x = (inputs - rgb_mean) / rgb_max for inputs [B,3,2,H,W] (models.py:97-101), in the four layouts its consumers
+    read: (x planar [B,6,H,W], frame 0 and frame 1 as channels_last [B,4,H,W], both frames as channels_last [B,8,H,W]);
+    the extra channels are zero."""
+    inputs = _require(inputs, "inputs", ndim=5).contiguous()
+    B, C, F2, H, W = inputs.shape
+    if C != 3 or F2 != 2:
+        raise ValueError("inputs must be [B,3,2,H,W], got %s" % (tuple(inputs.shape),))
+    rgb_mean = rgb_mean.reshape(B, 3).contiguous()
+    with torch.cuda.device_of(inputs):
+        cl = dict(device=inputs.device, dtype=torch.float32, memory_format=torch.channels_last)
+        x = torch.empty((B, 6, H, W), device=inputs.device, dtype=torch.float32)
+        xa, xb, x8 = torch.empty((B, 4, H, W), **cl), torch.empty((B, 4, H, W), **cl), torch.empty((B, 8, H, W), **cl)
+        if inputs.numel():
+            check(_lib.load().flowops_flownet2_prep(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb), _p(x8),
+                                                    B, H, W, _stream()), "flownet2_prep")
+    return x, xa, xb, x8
+
+
 def warp_conf_forward(im1, im2, flow, thresh=0.02, mode=WARP_GRIDSAMPLE):
     im1 = _require(im1, "im1").contiguous()
     im2 = _require(im2, "im2").contiguous()

@@ -77,7 +77,37 @@ class FlowNet2(nn.Module):
         warped = self.resample(x[:, 3:, :, :], flow)
         return warped, self.channelnorm(x[:, :3, :, :] - warped)
 
+    def _channels_last_body(self):
+        w = self.flownets_1.conv1[0].weight
+        return w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()
+
+    def _forward_fused(self, inputs):
+        """Inference on a channels_last conv body: the same computation as forward(), with the
+        tensors between the sub-networks produced directly in the layout and channel count their consumers read --
+        no torch.cat, no slice copies, no NCHW<->NHWC conversions, no cuDNN channel re-padding."""
+        rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1)
+        x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max))
+
+        flownetc_flow = self.upsample1(self.flownetc(x, frames=(xa, xb))[0] * self.div_flow)
+        concat1 = _F.warp_diff_norm_concat(x, flownetc_flow, self.div_flow)
+        flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
+        concat2 = _F.warp_diff_norm_concat(x, flownets1_flow, self.div_flow)
+        flownets2_flow = self.upsample4(self.flownets_2(concat2)[0] * self.div_flow)
+        norm_flownets2_flow = self.channelnorm(flownets2_flow)
+        _, diff_flownets2_img1 = self.warp_error(x, flownets2_flow)
+
+        flownetsd_flow = self.upsample3(self.flownets_d(x8)[0] / self.div_flow)
+        norm_flownetsd_flow = self.channelnorm(flownetsd_flow)
+        _, diff_flownetsd_img1 = self.warp_error(x, flownetsd_flow)
+
+        concat3 = torch.cat((x[:, :3, :, :], flownetsd_flow, flownets2_flow, norm_flownetsd_flow, norm_flownets2_flow,
+                             diff_flownetsd_img1, diff_flownets2_img1), dim=1)
+        return self.flownetfusion(concat3)
+
     def forward(self, inputs):
+        if (self.fuse_glue and not torch.is_grad_enabled() and inputs.is_cuda and inputs.dtype == torch.float32
+                and not self.fp16 and not self.batchNorm and inputs.dim() == 5 and self._channels_last_body()):
+            return self._forward_fused(inputs)
         rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1).view(inputs.size()[:2] + (1, 1, 1,))
         x = (inputs - rgb_mean) / self.rgb_max
         x = torch.cat((x[:, :, 0, :, :], x[:, :, 1, :, :]), dim=1)

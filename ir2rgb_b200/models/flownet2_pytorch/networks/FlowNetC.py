@@ -43,13 +43,14 @@ class FlowNetC(nn.Module):
         c2 = self.conv2(self.conv1(frame))
         return c2, self.conv3(c2)
 
-    def _fused_features_and_cost(self, x):
+    def _fused_features_and_cost(self, x, frames=None):
         """Inference fast path on a channels_last conv body: conv3's bias + LeakyReLU epilogue writes the
         correlation's input planes directly (flowops_corr_planes_from_conv), so neither a separate activation
         pass nor the correlation's own layout pre-pass runs.  Same values as the plain path, bit for bit."""
         conv3, act3 = self.conv3[0], self.conv3[1]
-        c2a = self.conv2(self.conv1(x[:, 0:3]))
-        c2b = self.conv2(self.conv1(x[:, 3:]))
+        fa, fb = frames if frames is not None else (x[:, 0:3], x[:, 3:])      # frames: channels-last, zero-padded to 4 channels
+        c2a = self.conv2(self.conv1(fa))
+        c2b = self.conv2(self.conv1(fb))
         y3a = F.conv2d(c2a, conv3.weight, None, conv3.stride, conv3.padding)
         y3b = F.conv2d(c2b, conv3.weight, None, conv3.stride, conv3.padding)
         if not (_F._is_nhwc(y3a) and _F._is_nhwc(y3b)):
@@ -59,12 +60,12 @@ class FlowNetC(nn.Module):
         planes.fill_from_conv_(y3b, conv3.bias, act3.negative_slope, 1, write_act=False)         # only the correlation reads it
         return c2a, c3a, planes
 
-    def forward(self, x):
+    def forward(self, x, frames=None):
         fused = None
         if (_sm.FUSE_EPILOGUE and not torch.is_grad_enabled() and not self.fp16 and not self.batchNorm and x.is_cuda
                 and x.dtype == torch.float32 and self.conv3[0].weight.is_contiguous(memory_format=torch.channels_last)
                 and not self.conv3[0].weight.is_contiguous()):
-            fused = self._fused_features_and_cost(x)
+            fused = self._fused_features_and_cost(x, frames)
         if fused is not None:
             # the concat of FlowNetC.py:94 is allocated first (473 -> 480 channels, zero pad); conv_redir's epilogue and
             # the correlation (with corr_activation folded into its store) each write their channel slice

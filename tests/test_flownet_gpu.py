@@ -79,6 +79,32 @@ def test_fused_glue_is_bit_identical_to_operator_chain(nets):
     assert (conf_gs != (torch.sum(t * t, dim=1, keepdim=True) < 0.02).float()).float().mean().item() <= 1e-4
 
 
+def test_input_prep_and_concat_assembly_are_bit_identical(nets):
+    """flowops_flownet2_prep and flowops_warp_diff_norm_concat_nhwc against the torch expressions of models.py:97-114."""
+    from ir2rgb_b200 import functional as F
+    torch.manual_seed(8)
+    B, H, W = 2, 64, 96
+    inputs = 2 * torch.rand(B, 3, 2, H, W, device="cuda") - 1
+    rgb_mean = inputs.contiguous().view(B, 3, -1).mean(dim=-1)
+    x_ref = (inputs - rgb_mean.view(B, 3, 1, 1, 1)) / 1.0
+    x_ref = torch.cat((x_ref[:, :, 0], x_ref[:, :, 1]), dim=1)
+    for rgb_max in (1.0, 255.0):
+        x, xa, xb, x8 = F.flownet2_prep(inputs, rgb_mean, rgb_max)
+        want = torch.cat((((inputs - rgb_mean.view(B, 3, 1, 1, 1)) / rgb_max)[:, :, 0],
+                          ((inputs - rgb_mean.view(B, 3, 1, 1, 1)) / rgb_max)[:, :, 1]), dim=1)
+        assert torch.equal(x, want)
+        assert torch.equal(xa[:, :3], want[:, :3]) and torch.equal(xb[:, :3], want[:, 3:]) and torch.equal(x8[:, :6], want)
+        assert (xa[:, 3:] == 0).all() and (xb[:, 3:] == 0).all() and (x8[:, 6:] == 0).all()
+        assert xa.is_contiguous(memory_format=torch.channels_last) and x8.is_contiguous(memory_format=torch.channels_last)
+    x = x_ref.contiguous()
+    flow = 6 * torch.randn(B, 2, H, W, device="cuda")
+    cat = F.warp_diff_norm_concat(x, flow, 20.0)
+    warped, norm = F.warp_diff_norm_forward(x, flow)
+    want = torch.cat((x, warped, flow / 20.0, norm), dim=1)
+    assert cat.shape == (B, 16, H, W) and cat.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(cat[:, :12], want) and (cat[:, 12:] == 0).all()
+
+
 def test_flownet_wrapper_shapes_and_resize_path(nets):
     # 5-D input (b, n, c, h, w) and a height that is not a multiple of 64 (flownet.py:27-33,41-47,51-53)
     a = 2 * torch.rand(1, 2, 3, 96, 128, device="cuda") - 1

@@ -1,5 +1,5 @@
 """Tiny launcher for ncu: runs ONE operator a few times at its BASELINE config.
-    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_fwd_c4b16|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
+    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_fwd_c4b16|corr_fwd_nhwc_b16|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
 """
 import os
 import sys
@@ -17,6 +17,15 @@ if op in ("corr_fwd", "corr_bwd"):
     a, b = torch.randn(8, 256, 48, 64, device="cuda"), torch.randn(8, 256, 48, 64, device="cuda")
     go = torch.randn(8, 441, 48, 64, device="cuda")
     fn = (lambda: F.correlation_forward(a, b, *P)) if op == "corr_fwd" else (lambda: F.correlation_backward(a, b, go, *P))
+elif op == "corr_fwd_nhwc_b16":    # what the FlowNet2 step launches: planes from the conv3 epilogue, channels-last store + LeakyReLU
+    a = torch.randn(16, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
+    b = torch.randn(16, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
+    planes = F.CorrelationPlanes(a.shape, a.device)
+    zb = torch.zeros(256, device="cuda")
+    planes.fill_from_conv_(a, zb, 1.0, 0, write_act=False)
+    planes.fill_from_conv_(b, zb, 1.0, 1, write_act=False)
+    buf = F.ConcatBuffer(a, 473, 8)
+    fn = lambda: F.correlation_planes_forward_into(planes, buf, 32, 0.1)
 elif op == "corr_fwd_c4b16":       # the shape bench.py's FlowNet2 step runs per micro-batch of 16 pairs
     a, b = torch.randn(16, 256, 64, 128, device="cuda"), torch.randn(16, 256, 64, 128, device="cuda")
     fn = lambda: F.correlation_forward(a, b, *P)

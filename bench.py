@@ -122,6 +122,7 @@ class Launches:
     def __init__(self):
         self.count = 0
         self.corr_events = []
+        self.epi_events = []        # (e0, e1, bytes) of the in-place bias + LeakyReLU epilogue launches
         self.enabled = False
 
     def install(self):
@@ -146,6 +147,18 @@ class Launches:
                 self.corr_events.append((e0, e1, tuple(a[0].shape), _name))
                 return out
             setattr(F, name, wrapped)
+        orig_epi = F.bias_lrelu_
+
+        def epi(y, *a, **k):
+            if not self.enabled:
+                return orig_epi(y, *a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_epi(y, *a, **k)
+            e1.record()
+            self.epi_events.append((e0, e1, 2 * y.numel() * 4))
+            return out
+        F.bias_lrelu_ = epi
 
 
 def build_native(device, memory_format="channels_last"):
@@ -380,6 +393,18 @@ def main():
                                 "alg_flop_per_launch": flop, "us_per_launch": mean_us, "launches_timed": len(us),
                                 "share_of_step": sum(us) / (ms_eager * 1e3),
                                 "timed_in": "one eagerly launched step of the same workload (the timed steps replay these kernels from a CUDA graph)"}
+        # the largest hand-written kernel family of the step by time (ncu launch list: bias_lrelu_nhwc ~12 % of GPU time):
+        # the in-place bias + LeakyReLU epilogue that follows every convolution -- HBM-bound, 8 bytes per element
+        if launches.epi_events:
+            us = [ev[0].elapsed_time(ev[1]) * 1e3 for ev in launches.epi_events]
+            nbytes = sum(ev[2] for ev in launches.epi_events)
+            gbs = nbytes / sum(us) / 1e3
+            line["roofline_epilogue"] = {"kernel": "bias_lrelu_nhwc (all in-place conv epilogues of the step)", "bound": "hbm",
+                                         "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                         "traffic": None, "alg_bytes_per_launch": nbytes / len(us), "us_per_launch": sum(us) / len(us),
+                                         "launches_timed": len(us), "share_of_step": sum(us) / (ms_eager * 1e3),
+                                         "timed_in": "the same eagerly launched step; launches are back to back with cuDNN kernels, "
+                                                     "so part of each tensor is still in L2 when its epilogue runs"}
         line["peaks"] = dict(pk, ffma_tflops=ffma)
         if not args.no_ops:
             try:

@@ -175,9 +175,11 @@ int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int HW, int ch
 
 /* Out-of-place form for channels-last tensors: dst[pix][c_off + c] = lrelu(y[pix][c] + bias[c]) with y dense
  * [n_pixels][C] and dst [n_pixels][c_dst].  Lets a decoder deconvolution (submodules.py:34-38) write its activated
- * output directly into the concat buffer of torch.cat((skip, deconv, flow_up), 1) (e.g. FlowNetS.py:74-76). */
+ * output directly into the concat buffer of torch.cat((skip, deconv, flow_up), 1) (e.g. FlowNetS.py:74-76).
+ * `also` (may be NULL, may alias y): a dense [n_pixels][C] copy of the result as well, for an encoder layer whose
+ * output is both the next layer's input and a skip connection (FlowNetS.py:63-67 -> :74). */
 int flowops_bias_lrelu_nhwc_to(const float *y, const float *bias, float *dst, size_t n_pixels,
-                               int C, int c_dst, int c_off, float slope, void *stream);
+                               int C, int c_dst, int c_off, float slope, float *also, void *stream);
 
 /* dst[pix][c_off .. c_off + c_n) = value for every pixel of a channels-last [n_pixels][c_dst] tensor: the zero pad
  * channels that round a concat buffer up to a multiple of 8 channels (cuDNN otherwise re-pads odd channel counts

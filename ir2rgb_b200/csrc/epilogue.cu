@@ -43,22 +43,27 @@ __global__ void __launch_bounds__(256) bias_lrelu_nchw(float *__restrict__ y, co
 // The epilogue of a decoder deconvolution writes straight into the concat buffer the next layers read
 // (reference FlowNetS.py:74-76: torch.cat((out_conv5, out_deconv5, flow6_up), 1)), which saves the concat's own
 // read + write of that tensor.  V = float4 when every channel count / offset is a multiple of 4, else float.
+// `also` (nullable, may alias y): a dense copy of the result as well -- an encoder layer whose output is both the next
+// layer's input and a decoder skip connection is written to both places from one read.
 template <typename V>
-__global__ void __launch_bounds__(256) bias_lrelu_nhwc_to(const V *__restrict__ y, const V *__restrict__ bias, V *__restrict__ dst,
-                                                          size_t total, unsigned src_v, unsigned dst_v, unsigned off_v, float slope)
+__global__ void __launch_bounds__(256) bias_lrelu_nhwc_to(const V *y, const V *__restrict__ bias, V *__restrict__ dst,
+                                                          size_t total, unsigned src_v, unsigned dst_v, unsigned off_v, float slope,
+                                                          V *also)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t pix = i / src_v;
         const unsigned c = (unsigned)(i - pix * src_v);
         if constexpr (sizeof(V) == 16) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c);
-            float4 v = ldg_stream4(reinterpret_cast<const float *>(y + i));
+            float4 v = *reinterpret_cast<const float4 *>(y + i);     // plain load: `also` may alias y
             v.x = lrelu(__fadd_rn(v.x, b.x), slope); v.y = lrelu(__fadd_rn(v.y, b.y), slope);
             v.z = lrelu(__fadd_rn(v.z, b.z), slope); v.w = lrelu(__fadd_rn(v.w, b.w), slope);
             reinterpret_cast<float4 *>(dst)[pix * dst_v + off_v + c] = v;
+            if (also) reinterpret_cast<float4 *>(also)[i] = v;
         } else {
-            reinterpret_cast<float *>(dst)[pix * dst_v + off_v + c] =
-                lrelu(__fadd_rn(reinterpret_cast<const float *>(y)[i], __ldg(reinterpret_cast<const float *>(bias) + c)), slope);
+            const float v = lrelu(__fadd_rn(reinterpret_cast<const float *>(y)[i], __ldg(reinterpret_cast<const float *>(bias) + c)), slope);
+            reinterpret_cast<float *>(dst)[pix * dst_v + off_v + c] = v;
+            if (also) reinterpret_cast<float *>(also)[i] = v;
         }
     }
 }
@@ -109,7 +114,7 @@ extern "C" int flowops_bias_lrelu(float *y, const float *bias, int N, int C, int
 }
 
 extern "C" int flowops_bias_lrelu_nhwc_to(const float *y, const float *bias, float *dst, size_t n_pixels,
-                                          int C, int c_dst, int c_off, float slope, void *stream)
+                                          int C, int c_dst, int c_off, float slope, float *also, void *stream)
 {
     FLOWOPS_REQUIRE(y && bias && dst, FLOWOPS_EINVAL, "bias_lrelu_nhwc_to: null pointer");
     FLOWOPS_REQUIRE(n_pixels > 0 && C > 0 && c_off >= 0 && c_off + C <= c_dst, FLOWOPS_EINVAL,
@@ -121,11 +126,12 @@ extern "C" int flowops_bias_lrelu_nhwc_to(const float *y, const float *bias, flo
         return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
     };
     const size_t total = n_pixels * (size_t)C;
-    if (((C | c_dst | c_off) & 3) == 0 && aligned16(y) && aligned16(dst) && aligned16(bias))
+    if (((C | c_dst | c_off) & 3) == 0 && aligned16(y) && aligned16(dst) && aligned16(bias) && aligned16(also))
         bias_lrelu_nhwc_to<float4><<<grid_for(total / 4), 256, 0, st>>>(reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(bias),
-                                                                        reinterpret_cast<float4 *>(dst), total / 4, C / 4, c_dst / 4, c_off / 4, slope);
+                                                                        reinterpret_cast<float4 *>(dst), total / 4, C / 4, c_dst / 4, c_off / 4, slope,
+                                                                        reinterpret_cast<float4 *>(also));
     else
-        bias_lrelu_nhwc_to<float><<<grid_for(total), 256, 0, st>>>(y, bias, dst, total, C, c_dst, c_off, slope);
+        bias_lrelu_nhwc_to<float><<<grid_for(total), 256, 0, st>>>(y, bias, dst, total, C, c_dst, c_off, slope, also);
     return check_launch("bias_lrelu_nhwc_to");
 }
 

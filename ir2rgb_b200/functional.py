@@ -259,13 +259,15 @@ class ConcatBuffer:
                   "concat_nhwc")
         return c_off + t.shape[1]
 
-    def bias_lrelu_in(self, y, bias, slope, c_off):
-        """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y."""
+    def bias_lrelu_in(self, y, bias, slope, c_off, in_place_too=False):
+        """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y; with in_place_too
+        y itself receives the result as well (one read, two writes)."""
         if not _is_nhwc(y) or y.shape[0] * y.shape[2] * y.shape[3] != self.n_pixels:
             raise ValueError("bias_lrelu_in: y must be dense channels_last with the buffer's batch and spatial shape")
         with torch.cuda.device_of(y):
             check(_lib.load().flowops_bias_lrelu_nhwc_to(_p(y), _p(bias), _p(self.tensor), self.n_pixels, y.shape[1], self.c_pad,
-                                                         c_off, ctypes.c_float(slope), _stream()), "bias_lrelu_nhwc_to")
+                                                         c_off, ctypes.c_float(slope), _p(y if in_place_too else None), _stream()),
+                  "bias_lrelu_nhwc_to")
         return c_off + y.shape[1]
 
 

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from .... import functional as _F
 from . import submodules as _sm
 from .correlation_package.correlation import Correlation
-from .submodules import add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
+from .submodules import Skip, add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
 
 TOWER = [("conv1", 3, 64, 7, 2), ("conv2", 64, 128, 5, 2), ("conv3", 128, 256, 5, 2), ("conv_redir", 256, 32, 1, 1)]
 TRUNK = [("conv3_1", 473, 256, 3, 1), ("conv4", 256, 512, 3, 2), ("conv4_1", 512, 512, 3, 1), ("conv5", 512, 512, 3, 2),
@@ -83,9 +83,10 @@ class FlowNetC(nn.Module):
             else:
                 cost = self.corr(c3a, c3b)
             cat = torch.cat((self.conv_redir(c3a), self.corr_activation(cost)), 1)
-        c3 = self.conv3_1(cat)
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        sk = {lv: Skip(self, lv) for lv in (5, 4, 3)}        # c2a is produced inside the tower: copied by refine()
+        c3 = self.conv3_1(cat, skip=sk[3])
+        c4 = self.conv4_1(self.conv4(c3), skip=sk[4])
+        c5 = self.conv5_1(self.conv5(c4), skip=sk[5])
         c6 = self.conv6_1(self.conv6(c5))
-        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2a}, c6, (5, 4, 3, 2))
+        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2a}, c6, (5, 4, 3, 2), skip_bufs=sk)
         return tuple(flows) if self.training else (flows[0],)

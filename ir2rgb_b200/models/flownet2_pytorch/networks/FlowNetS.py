@@ -1,7 +1,7 @@
 """FlowNetS (reference networks/FlowNetS.py:15-95; 38,676,504 parameters), table-driven."""
 import torch.nn as nn
 
-from .submodules import add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
+from .submodules import Skip, add_layers, deconv, flow_upsampler, predict_flow, refine, reference_init
 
 ENCODER = [("conv1", None, 64, 7, 2), ("conv2", 64, 128, 5, 2), ("conv3", 128, 256, 5, 2), ("conv3_1", 256, 256, 3, 1),
            ("conv4", 256, 512, 3, 2), ("conv4_1", 512, 512, 3, 1), ("conv5", 512, 512, 3, 2), ("conv5_1", 512, 512, 3, 1),
@@ -25,10 +25,11 @@ class FlowNetS(nn.Module):
         self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
 
     def forward(self, x):
-        c2 = self.conv2(self.conv1(x))
-        c3 = self.conv3_1(self.conv3(c2))
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        sk = {lv: Skip(self, lv) for lv in (5, 4, 3, 2)}      # inference: skip tensors are written into their concat slices
+        c2 = self.conv2(self.conv1(x), skip=sk[2])
+        c3 = self.conv3_1(self.conv3(c2), skip=sk[3])
+        c4 = self.conv4_1(self.conv4(c3), skip=sk[4])
+        c5 = self.conv5_1(self.conv5(c4), skip=sk[5])
         c6 = self.conv6_1(self.conv6(c5))
-        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2}, c6, (5, 4, 3, 2))
+        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2}, c6, (5, 4, 3, 2), skip_bufs=sk)
         return tuple(flows) if self.training else (flows[0],)

@@ -1,7 +1,7 @@
 """FlowNetSD (reference networks/FlowNetSD.py:11-106; 45,371,666 parameters), table-driven."""
 import torch.nn as nn
 
-from .submodules import add_layers, deconv, flow_upsampler, i_conv, predict_flow, refine, reference_init
+from .submodules import Skip, add_layers, deconv, flow_upsampler, i_conv, predict_flow, refine, reference_init
 
 ENCODER = [("conv0", 6, 64, 3, 1), ("conv1", 64, 64, 3, 2), ("conv1_1", 64, 128, 3, 1), ("conv2", 128, 128, 3, 2),
            ("conv2_1", 128, 128, 3, 1), ("conv3", 128, 256, 3, 2), ("conv3_1", 256, 256, 3, 1), ("conv4", 256, 512, 3, 2),
@@ -30,10 +30,11 @@ class FlowNetSD(nn.Module):
 
     def forward(self, x):
         c1 = self.conv1_1(self.conv1(self.conv0(x)))
-        c2 = self.conv2_1(self.conv2(c1))
-        c3 = self.conv3_1(self.conv3(c2))
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        sk = {lv: Skip(self, lv) for lv in (5, 4, 3, 2)}
+        c2 = self.conv2_1(self.conv2(c1), skip=sk[2])
+        c3 = self.conv3_1(self.conv3(c2), skip=sk[3])
+        c4 = self.conv4_1(self.conv4(c3), skip=sk[4])
+        c5 = self.conv5_1(self.conv5(c4), skip=sk[5])
         c6 = self.conv6_1(self.conv6(c5))
-        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2}, c6, (5, 4, 3, 2), inter=True)
+        flows = refine(self, {5: c5, 4: c4, 3: c3, 2: c2}, c6, (5, 4, 3, 2), inter=True, skip_bufs=sk)
         return tuple(flows) if self.training else (flows[0],)

@@ -72,7 +72,7 @@ class ConvAct(nn.Sequential):
         return (FUSE_EPILOGUE and len(self) == 2 and self[0].bias is not None and not torch.is_grad_enabled()
                 and x.is_cuda and x.dtype == torch.float32)
 
-    def forward(self, x, into=None):
+    def forward(self, x, into=None, skip=None):
         conv = self[0]
         if self.fusable(x):
             y = _raw_conv(conv, x, None)
@@ -80,6 +80,12 @@ class ConvAct(nn.Sequential):
                 buf, c_off = into
                 buf.bias_lrelu_in(y, conv.bias, self[1].negative_slope, c_off)
                 return None
+            if skip is not None and _F._is_nhwc(y):
+                # this output is also a decoder skip connection: allocate that level's concat buffer now and write the
+                # activated features to both places from one read
+                skip.buf = _F.ConcatBuffer(y, skip.c_total(y.shape[1]), PAD_CHANNELS)
+                skip.buf.bias_lrelu_in(y, conv.bias, self[1].negative_slope, 0, in_place_too=True)
+                return y
             return _F.bias_lrelu_(y, conv.bias, self[1].negative_slope)
         assert into is None
         if x.shape[1] != conv.weight.shape[0 if isinstance(conv, nn.ConvTranspose2d) else 1] * conv.groups:
@@ -88,6 +94,18 @@ class ConvAct(nn.Sequential):
                 y = layer(y)
             return y
         return super().forward(x)
+
+
+class Skip:
+    """Hand-over of a decoder level's concat buffer from the encoder layer that produces the skip tensor
+    (ConvAct.forward(skip=...)) to refine()."""
+
+    def __init__(self, net, lv):
+        self.extra = getattr(net, "deconv%d" % lv)[0].out_channels + 2      # deconv features + upsampled flow
+        self.buf = None
+
+    def c_total(self, c_skip):
+        return c_skip + self.extra
 
 
 def conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1):
@@ -143,7 +161,7 @@ def add_layers(net, batchNorm, table):
         setattr(net, name, conv(batchNorm, cin, cout, kernel_size=k, stride=s))
 
 
-def refine(net, skips, top, levels, inter=False):
+def refine(net, skips, top, levels, inter=False, skip_bufs=None):
     """Shared coarse-to-fine decoder of FlowNetC / FlowNetS / FlowNetSD (e.g. FlowNetS.py:70-90):
     at each level predict a flow, upsample it and the features, concatenate with the skip tensor.
     Returns the flows from finest to coarsest.
@@ -159,8 +177,12 @@ def refine(net, skips, top, levels, inter=False):
         skip = skips[lv]
         if deconv_lv.fusable(feat) and _F._cat_fast((skip, up)) and _F._is_nhwc(feat):
             c_dec = deconv_lv[0].out_channels
-            buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + up.shape[1], PAD_CHANNELS)
-            off = buf.copy_in(skip, 0)
+            buf = skip_bufs[lv].buf if skip_bufs is not None and skip_bufs.get(lv) is not None else None
+            if buf is not None:                 # the encoder already wrote the skip tensor into its slice
+                off = skip.shape[1]
+            else:
+                buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + up.shape[1], PAD_CHANNELS)
+                off = buf.copy_in(skip, 0)
             deconv_lv(feat, into=(buf, off))
             buf.copy_in(up, off + c_dec)
             feat = buf.tensor

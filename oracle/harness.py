@@ -56,6 +56,11 @@ def swap_ops(flownet2, kind):
     flownet2.resample = mods[1]()
     flownet2.channelnorm = mods[2]()
     flownet2.fuse_glue = False
+    # ... and every libflowops epilogue / concat fusion of the restated conv body: the oracle network must run
+    # stock torch layers only (conv -> bias -> LeakyReLU, torch.cat), like the reference's submodules.py
+    for m in flownet2.modules():
+        if type(m).__name__ == "ConvAct":
+            m.fusable = lambda x: False
     return flownet2
 
 

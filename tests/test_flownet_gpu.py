@@ -50,6 +50,26 @@ def test_flownet_matches_oracle_network(nets, kind):
     assert set(conf_new.unique().tolist()) <= {0.0, 1.0}
 
 
+def test_oracle_network_never_calls_libflowops(nets):
+    """The comparison network (and bench.py's reference arm) must run the reference's operators and stock torch layers
+    only: not one libflowops call may happen on that path."""
+    from ir2rgb_b200 import _lib
+    from oracle import ref_ext
+    from oracle.harness import OracleFlowNet
+    calls = []
+    prev = _lib.launch_hook
+    _lib.launch_hook = lambda what, n: calls.append(what)
+    try:
+        im = 2 * torch.rand(1, 3, 64, 64, device="cuda") - 1
+        for kind in ["torch"] + (["ref"] if ref_ext.available() else []):
+            OracleFlowNet(kind, "cuda", state_dict=nets.flowNet.state_dict())(im, im.flip(3))
+        assert calls == [], calls
+        nets(im, im.flip(3))
+        assert len(calls) > 0          # the hook does see the product path
+    finally:
+        _lib.launch_hook = prev
+
+
 def test_fused_glue_is_bit_identical_to_operator_chain(nets):
     from ir2rgb_b200 import functional as F
     from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm

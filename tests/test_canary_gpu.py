@@ -137,3 +137,75 @@ def test_fused_glue_stays_in_bounds(lib):
     check(nbuf, B * hw, "fused norm")
     check(cbuf, B * hw, "conf")
     check(ybuf, B * 5 * hw, "bias_lrelu", must_fill=False)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 13, 21), (2, 16, 8, 70), (1, 8, 6, 34)])
+def test_correlation_nhwc_store_stays_in_bounds(lib, shape):
+    """flowops_corr_planes_from_conv + flowops_corr_fwd_planes_nhwc on ragged shapes: the channels-last destination
+    (473 -> 480 channels) is written exactly in channels [32, 473)."""
+    B, C, H, W = shape
+    torch.manual_seed(3)
+    P = (20, 1, 20, 1, 2)
+    ya = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    yb = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(C, device="cuda")
+    ws_bytes = lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *P)
+    wbuf, ws = guarded((ws_bytes + 3) // 4 + 64)
+    ws = ws[(-ws.data_ptr()) % 256 // 4:]
+    for which, y in ((0, ya), (1, yb)):
+        rc = lib.flowops_corr_planes_from_conv(p(y), p(bias), ctypes.c_float(0.1), None, which, B, C, H, W, *P, p(ws), ws_bytes, None)
+        assert rc == 0, lib.flowops_last_error()
+    c_dst = 480
+    n_out = B * H * W * c_dst
+    obuf, out = guarded(n_out)
+    rc = lib.flowops_corr_fwd_planes_nhwc(p(out), c_dst, 32, ctypes.c_float(0.1), B, C, H, W, *P, p(ws), ws_bytes, None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    check(obuf, n_out, "corr_fwd_planes_nhwc out", must_fill=False)
+    check(wbuf, (ws_bytes + 3) // 4 + 64, "corr workspace", must_fill=False)
+    o = out.view(B * H * W, c_dst)
+    assert torch.all(o[:, :32] == SENT) and torch.all(o[:, 473:] == SENT), "wrote outside its channel slice"
+    assert not torch.any(o[:, 32:473] == SENT), "left part of its channel slice unwritten"
+    # values: LeakyReLU(correlation of the activated features)
+    act = lambda y: torch.nn.functional.leaky_relu(y + bias.view(1, -1, 1, 1), 0.1)
+    from ir2rgb_b200 import functional as F
+    want = torch.nn.functional.leaky_relu(F.correlation_forward(act(ya).contiguous(), act(yb).contiguous(), *P), 0.1)
+    got = o[:, 32:473].reshape(B, H, W, 441).permute(0, 3, 1, 2)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 5, 7), (2, 33, 65), (1, 64, 300)])
+def test_glue_kernels_stay_in_bounds(lib, B, H, W):
+    """flowops_flownet2_prep, flowops_warp_diff_norm_concat_nhwc, flowops_bias_lrelu_nhwc_to, flowops_fill_channels_nhwc."""
+    torch.manual_seed(4)
+    hw = H * W
+    inputs = torch.randn(B, 3, 2, H, W, device="cuda")
+    mean = inputs.view(B, 3, -1).mean(-1).contiguous()
+    bufs = [guarded(n) for n in (B * 6 * hw, B * 4 * hw, B * 4 * hw, B * 8 * hw)]
+    rc = lib.flowops_flownet2_prep(p(inputs), p(mean), ctypes.c_float(255.0), *[p(v) for _, v in bufs], B, H, W, None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    for (buf, v), name in zip(bufs, ("x", "xa", "xb", "x8")):
+        check(buf, v.numel(), "flownet2_prep " + name)
+
+    x = bufs[0][1].view(B, 6, H, W)
+    flow = 5 * torch.randn(B, 2, H, W, device="cuda")
+    cbuf, cat = guarded(B * hw * 16)
+    rc = lib.flowops_warp_diff_norm_concat_nhwc(p(x), p(flow), ctypes.c_float(20.0), p(cat), 16, B, H, W, None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    check(cbuf, cat.numel(), "warp_diff_norm_concat_nhwc")
+
+    C, c_dst, c_off = 12, 40, 20
+    y = torch.randn(B * hw, C, device="cuda")
+    bias = torch.randn(C, device="cuda")
+    dbuf, dst = guarded(B * hw * c_dst)
+    rc = lib.flowops_bias_lrelu_nhwc_to(p(y), p(bias), p(dst), B * hw, C, c_dst, c_off, ctypes.c_float(0.1), p(y), None)
+    assert rc == 0, lib.flowops_last_error()
+    rc = lib.flowops_fill_channels_nhwc(p(dst), B * hw, c_dst, 35, 5, ctypes.c_float(0.0), None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    check(dbuf, dst.numel(), "bias_lrelu_nhwc_to / fill_channels_nhwc", must_fill=False)
+    d = dst.view(B * hw, c_dst)
+    assert torch.all(d[:, :c_off] == SENT) and torch.all(d[:, c_off + C:35] == SENT) and torch.all(d[:, 35:] == 0)
+    assert torch.equal(d[:, c_off:c_off + C], y)              # `also` aliased y: y now holds the activated values too

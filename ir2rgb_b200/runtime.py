@@ -12,6 +12,11 @@ class GraphedFlowNet(torch.nn.Module):
     """Wraps a `FlowNet` (models/flownet.py API): same call signature and results, replayed from a CUDA graph.
 
     One graph per (shape, dtype) of the inputs.  Outputs are copies, so they stay valid across calls.
+
+    The graphs hold device pointers: weights updated IN PLACE (``load_state_dict``, optimizer steps) are picked up by the
+    next replay, but tensors derived from the weights on the host side are not -- the zero-padded weight copies that the
+    inference path of the conv body caches (networks/submodules.py ``padded_weight``).  Call ``reset()`` after loading
+    or changing weights.
     """
 
     accepts_host_inputs = True      # pinned host frames are copied straight into the graph's static inputs
@@ -38,6 +43,12 @@ class GraphedFlowNet(torch.nn.Module):
         with torch.cuda.graph(g):
             out = self.net(sa, sb)
         return g, sa, sb, out
+
+    def reset(self):
+        """Drop the captured graphs (and the padded-weight caches they point into); the next call captures again."""
+        self._graphs.clear()
+        for m in self.net.modules():
+            m.__dict__.pop("_flowops_wpad", None)
 
     @torch.no_grad()
     def forward(self, input_A, input_B):

@@ -184,6 +184,15 @@ def test_graphed_flownet_matches_eager(nets):
     assert torch.equal(flow_g, flow_e) and torch.equal(conf_g, conf_e)
     assert torch.equal(flow_g2, flow_e)
     assert torch.equal(flow_g3, flow_e3)
+    g.reset()                                                          # what a caller does after loading new weights
+    assert not g._graphs
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        flow_g4, _ = g(a, b)
+    finally:
+        torch.backends.cudnn.deterministic = prev
+    assert torch.equal(flow_g4, flow_e)
 
 
 def test_host_pipeline_matches_direct_calls(nets):

@@ -127,6 +127,30 @@ def test_resample2d_vs_oracle(ops, c_oracle, shape, sigma):
     assert maxrel(ft.grad, gf_ref) <= 1e-6
 
 
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 33, 65), 2.0), ((1, 3, 70, 130), 6.0), ((1, 2, 40, 100), 30.0), ((1, 1, 5, 7), 1.0),
+                                         ((1, 3, 64, 64), 0.0)])
+def test_warp_backward_ragged_frames_vs_oracle(ops, c_oracle, shape, sigma):
+    """The row-walking backward (lane hand-over, vertical pairing, zero skipping) on ragged frames, flows from zero to far
+    outside the frame, both coordinate conventions."""
+    from oracle import torch_ref as tr
+    rng = np.random.default_rng(31)
+    B, C, H, W = shape
+    img = rng.standard_normal(shape).astype(np.float32)
+    flow = (sigma * rng.standard_normal((B, 2, H, W))).astype(np.float32)
+    go = rng.standard_normal(shape).astype(np.float32)
+    it, ft = cu(img).requires_grad_(), cu(flow).requires_grad_()
+    ops.Resample2d()(it, ft).backward(cu(go))
+    gi_ref, gf_ref = c_oracle.resample2d_bwd(img, flow, go)
+    assert maxrel(it.grad, gi_ref) <= 1e-5 and maxrel(ft.grad, gf_ref) <= 1e-6
+    assert abs(it.grad.double().sum().item() - float(np.float64(go).sum())) <= 1e-3 * np.abs(go).sum() ** 0.5 + 1e-2 or sigma > 0
+    # grid_sample convention against autograd through the reference code path in fp64
+    i2, f2 = cu(img).requires_grad_(), cu(flow).requires_grad_()
+    ops.networks.resample(i2, f2).backward(cu(go))
+    i64, f64 = cu(img).double().requires_grad_(), cu(flow).double().requires_grad_()
+    tr.networks_resample(i64, f64).backward(cu(go).double())
+    assert maxrel(i2.grad, i64.grad) <= 1e-4
+
+
 def test_resample2d_golden(ops, golden_native):
     g = golden_native
     for name in ["res_small", "res_odd", "res_far"]:

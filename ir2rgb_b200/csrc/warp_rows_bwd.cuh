@@ -139,11 +139,14 @@ __global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_cons
                     gfx = __fmaf_rn((1 - gam_y) * g[c], br, gfx);
                     gfx = __fmaf_rn(-((1 - gam_y) * g[c]), bl, gfx);
                 } else {
-                    // ATen grid_sampler_2d_backward_kernel, bilinear branch
-                    gfx -= tl * ay * g[c]; gfy -= tl * ax * g[c];
-                    gfx += tr * ay * g[c]; gfy -= tr * bx * g[c];
-                    gfx -= bl * by * g[c]; gfy += bl * ax * g[c];
-                    gfx += br * by * g[c]; gfy += br * bx * g[c];
+                    // ATen grid_sampler_2d_backward_kernel, bilinear branch: gix -= nw * (iy_se - iy) * gOut, ... -- the same
+                    // eight terms, with the per-pixel products hoisted and each term one FMA (rounding differs from ATen's
+                    // mul-mul-sub by < 1 ulp per term; the backward is held to 1e-4, not to bit equality)
+                    const float ayg = ay * g[c], axg = ax * g[c], byg = by * g[c], bxg = bx * g[c];
+                    gfx = __fmaf_rn(-tl, ayg, gfx); gfy = __fmaf_rn(-tl, axg, gfy);
+                    gfx = __fmaf_rn(tr, ayg, gfx);  gfy = __fmaf_rn(-tr, bxg, gfy);
+                    gfx = __fmaf_rn(-bl, byg, gfx); gfy = __fmaf_rn(bl, axg, gfy);
+                    gfx = __fmaf_rn(br, byg, gfx);  gfy = __fmaf_rn(br, bxg, gfy);
                 }
             }
             if (valid_x) {

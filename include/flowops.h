@@ -6,7 +6,8 @@
  * /root/reference/models/flownet2_pytorch/networks/ unless they start with models/.
  *
  * Conventions
- *   - every tensor is fp32, contiguous NCHW, resident on the device the stream belongs to;
+ *   - every tensor is fp32, contiguous NCHW, resident on the device the stream belongs to (the *_16 entry points at
+ *     the end take fp16 / bf16 storage instead and say so);
  *   - the library never allocates, frees or retains a pointer; scratch space is passed in as
  *     `workspace` (query the size first), outputs are fully written (callers need not zero them);
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy default
@@ -32,6 +33,10 @@ extern "C" {
 /* memory layout of a [B,C,H,W] input */
 #define FLOWOPS_LAYOUT_NCHW 0      /* contiguous, what the reference extensions require                */
 #define FLOWOPS_LAYOUT_NHWC 1      /* torch.channels_last: element (n,c,y,x) at ((n*H+y)*W+x)*C+c      */
+
+/* storage type of the *_16 entry points ("16-bit storage, fp32 math") */
+#define FLOWOPS_DTYPE_F16 1        /* IEEE binary16 (torch.float16)                                    */
+#define FLOWOPS_DTYPE_BF16 2       /* bfloat16 (torch.bfloat16)                                        */
 
 /* warp coordinate conventions */
 #define FLOWOPS_WARP_RESAMPLE2D 0  /* resample2d_package: sample at (x+dx, y+dy), clamp corners      */
@@ -164,6 +169,50 @@ int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *flow, float 
 int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_max,
                           float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
                           int B, int H, int W, void *stream);
+
+/* ---- 16-bit storage variants (fp16 / bf16 in HBM, fp32 arithmetic) ----------------------------------------
+ * The reference's fp16 mode is "fp16 storage, fp32 math" (flownet2_pytorch/main.py:59).  As run it reaches the
+ * operators in three ways, and each entry point below reproduces exactly one of them in a single pass, with half the
+ * bytes of the fp32 operator and without the separate cast kernels:
+ *   - ChannelNorm is called on half tensors and dispatches its kernels for at::Half
+ *     (channelnorm_kernel.cu:111,152): own arithmetic, see flowops_cnorm_fwd_16;
+ *   - Resample2d and Correlation are fp32-only there and are wrapped in casts:
+ *     `resample(a.float(), b.float()).half()` (models.py:22-28), `corr(a.float(), b.float()).half()`
+ *     (FlowNetC.py:86-87);
+ *   - Model.resample builds its sampling grid in the flow's dtype and casts around F.grid_sample
+ *     (models/base_model.py:123-136).
+ * `dtype` is FLOWOPS_DTYPE_F16 or FLOWOPS_DTYPE_BF16 and applies to every `void *` tensor of the call; all of them
+ * are contiguous NCHW.  float -> 16-bit conversions round to nearest even (what `.half()` / `.bfloat16()` do).
+ * Backward passes of the cast-wrapped operators are the fp32 entry points above between two casts, which is what
+ * autograd makes of the reference's chain; only ChannelNorm has a 16-bit backward kernel of its own. */
+
+/* kernel_channelnorm_update_output<at::Half> (channelnorm_kernel.cu:19-60): the square of each element is rounded to
+ * the storage type before it is added (`val * val` on two at::Half values), the sum and the sqrt are fp32, the result is
+ * rounded to the storage type.  Not the same values as cast -> flowops_cnorm_fwd -> cast. */
+int flowops_cnorm_fwd_16(const void *x, void *y, int B, int C, int H, int W, int dtype, void *stream);
+
+/* kernel_channelnorm_backward_input1<at::Half> (channelnorm_kernel.cu:64-96):
+ * gx = T( float( (double)(float(gy) * float(x)) / ((double)float(y) + 1e-9) ) ). */
+int flowops_cnorm_bwd_16(const void *x, const void *y, const void *gy, void *gx,
+                         int B, int C, int H, int W, int dtype, void *stream);
+
+/* Mode RESAMPLE2D: fp16_resample2d (models.py:22-28) in one pass -- flowops_warp_fwd's fp32 arithmetic on the
+ * widened inputs, result rounded to the storage type; bit-identical to the cast chain.
+ * Mode GRIDSAMPLE: Model.resample with `opt['fp16']` on 16-bit tensors (models/base_model.py:123-136): the grid
+ * get_grid(..., dtype=flow.dtype), the normalised flow `flow / ((w-1)/2)` and their sum are each rounded to the
+ * storage type (that is where the reference evaluates them), F.grid_sample then runs in fp32 on the widened grid and
+ * image and its result is rounded to the storage type.  lin_x[W], lin_y[H]: fp32 tables holding
+ * linspace(-1,1,n) ROUNDED to the storage type. */
+int flowops_warp_fwd_16(const void *img, const void *flow, void *out, int B, int C, int H, int W, int mode,
+                        const float *lin_x, const float *lin_y, int dtype, void *stream);
+
+/* `corr(a.float(), b.float()).half()` (FlowNetC.py:86-87) in one pass: the layout pre-pass widens the 16-bit features
+ * into the fp32 workspace planes, the correlation proper is flowops_corr_fwd's, the store rounds to the storage type.
+ * Workspace: flowops_corr_fwd_workspace_bytes.  Parameter sets outside the FlowNetC configuration return
+ * FLOWOPS_EUNSUPPORTED (cast and call flowops_corr_fwd). */
+int flowops_corr_fwd_16(const void *in1, const void *in2, void *out, int B, int C, int H, int W,
+                        int pad, int k, int md, int s1, int s2, int dtype,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- Conv-body epilogue (FlowNet2 inference glue, not an operator of the reference's native surface) ---- */
 

@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get("FLOWOPS_LIB") or os.path.join(_HERE, "libflowops.so")
 
 WARP_RESAMPLE2D = 0
 WARP_GRIDSAMPLE = 1
+DTYPE_F16 = 1
+DTYPE_BF16 = 2
 
 _c_float_p = ctypes.c_void_p   # device pointers travel as plain addresses
 _int = ctypes.c_int
@@ -33,6 +35,10 @@ SIGNATURES = {
     "flowops_corr_fwd_planes": (_int, [_vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_fwd_planes_nhwc": (_int, [_vp, _int, _int, ctypes.c_float] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_cnorm_fwd_16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
+    "flowops_cnorm_bwd_16": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),
+    "flowops_warp_fwd_16": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _int, _vp]),
+    "flowops_corr_fwd_16": (_int, [_vp, _vp, _vp] + [_int] * 10 + [_vp, _sz, _vp]),
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
     "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "flowops_warp_diff_norm_concat_nhwc": (_int, [_vp, _vp, ctypes.c_float, _vp, _int, _int, _int, _int, _vp]),
@@ -73,7 +79,7 @@ def load():
 
 # kernels (and memsets) each library call launches, keyed by the name the wrappers pass to check();
 # bench.py's `gpu_launches` is counted from this table through `launch_hook`
-KERNELS_PER_CALL = {"corr_fwd": 2, "corr_bwd": 6, "warp_bwd": 2}
+KERNELS_PER_CALL = {"corr_fwd": 2, "corr_fwd_16": 2, "corr_bwd": 6, "warp_bwd": 2}
 launch_hook = None          # callable(what, n_kernels) or None
 
 

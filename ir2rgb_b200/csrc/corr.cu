@@ -75,6 +75,22 @@ extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, 
     return corr_fwd_generic_launch(in1, in2, out, g, st);
 }
 
+extern "C" int flowops_corr_fwd_16(const void *in1, const void *in2, void *out, int B, int C, int H, int W,
+                                   int pad, int k, int md, int s1, int s2, int dtype,
+                                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    FLOWOPS_REQUIRE(in1 && in2 && out, FLOWOPS_EINVAL, "corr_fwd_16: null pointer");
+    FLOWOPS_REQUIRE(dtype == FLOWOPS_DTYPE_F16 || dtype == FLOWOPS_DTYPE_BF16, FLOWOPS_EINVAL,
+                    "corr_fwd_16: dtype must be FLOWOPS_DTYPE_F16 or FLOWOPS_DTYPE_BF16, got %d", dtype);
+    CorrGeom g;
+    const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
+    if (rc) return rc;
+    FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED,
+                    "corr_fwd_16: FlowNetC configuration only (cast and call flowops_corr_fwd for other parameters)");
+    return corr_fast_fwd_launch(static_cast<const float *>(in1), static_cast<const float *>(in2), static_cast<float *>(out),
+                                g, FLOWOPS_LAYOUT_NCHW, workspace, workspace_bytes, (cudaStream_t)stream, dtype);
+}
+
 extern "C" int flowops_corr_planes_from_conv(const float *y, const float *bias, float slope, float *act, int which,
                                              int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                                              void *workspace, size_t workspace_bytes, void *stream)

@@ -25,11 +25,11 @@ int corr_bwd_generic_launch(const float *in1, const float *in2, const float *gou
 size_t corr_fast_fwd_workspace(const CorrGeom &g);
 size_t corr_fast_bwd_workspace(const CorrGeom &g);
 int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, int in_layout,
-                         void *ws, size_t ws_bytes, cudaStream_t st);
+                         void *ws, size_t ws_bytes, cudaStream_t st, int io_dtype = 0);
 int corr_fast_planes_nhwc(const float *in1, const float *in2, const CorrGeom &g, int only, const float *bias, float slope,
                           float *act, void *ws, size_t ws_bytes, cudaStream_t st);
 int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
-                   bool nhwc_out = false, int c_dst = 0, int c_off = 0, float slope = 1.f);
+                   bool nhwc_out = false, int c_dst = 0, int c_off = 0, float slope = 1.f, int out_dtype = 0);
 int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
                          const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
 

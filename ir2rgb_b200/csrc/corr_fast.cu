@@ -25,6 +25,7 @@
 // Roofline: FP32-FMA pipe.  Algorithmic work 2*B*H*W*441*C FLOP (dense count, taps that fall in
 // the zero padding included -- the kernel does not skip them).
 #include "corr.cuh"
+#include "io16.cuh"
 #include "tma.cuh"
 
 namespace flowops {
@@ -88,12 +89,45 @@ size_t corr_fast_fwd_workspace(const CorrGeom &g)
 // ---------------------------------------------------------------------------------------------
 // pre-pass: NCHW -> parity planes  P[n][py*2+px][c][Hp][pitch]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ in1, const float *__restrict__ in2,
+// TI = float: the inputs as the reference takes them.  TI = __half / __nv_bfloat16: 16-bit features widened on the
+// way in (the `.float()` of FlowNetC.py:86-87 folded into this pass; exact, so the planes hold the same values).
+template <typename TI>
+__device__ __forceinline__ float4 planarize_load4(const TI *src, int x, int W, int vec_ok)
+{
+    float4 v;
+    if constexpr (std::is_same<TI, float>::value) {
+        if (vec_ok) {
+            v = ldg_stream4(src);
+        } else {
+            v.x = src[0];
+            v.y = x + 1 < W ? src[1] : 0.f;
+            v.z = x + 2 < W ? src[2] : 0.f;
+            v.w = x + 3 < W ? src[3] : 0.f;
+        }
+    } else {
+        const unsigned short *s16 = reinterpret_cast<const unsigned short *>(src);
+        if (vec_ok) {                                  // four 16-bit elements: one 8-byte load
+            uint2 w;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(s16));
+            v.x = Io16<TI>::to_float((unsigned short)(w.x & 0xffffu)); v.y = Io16<TI>::to_float((unsigned short)(w.x >> 16));
+            v.z = Io16<TI>::to_float((unsigned short)(w.y & 0xffffu)); v.w = Io16<TI>::to_float((unsigned short)(w.y >> 16));
+        } else {
+            v.x = Io16<TI>::to_float(s16[0]);
+            v.y = x + 1 < W ? Io16<TI>::to_float(s16[1]) : 0.f;
+            v.z = x + 2 < W ? Io16<TI>::to_float(s16[2]) : 0.f;
+            v.w = x + 3 < W ? Io16<TI>::to_float(s16[3]) : 0.f;
+        }
+    }
+    return v;
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256) corr_planarize(const TI *__restrict__ in1, const TI *__restrict__ in2,
                                                       float *__restrict__ P1, float *__restrict__ P2,
                                                       int B, int C, int H, int W, int Hp, int pitch1, int pitch2, int vec_ok)
 {
     const bool second = blockIdx.y != 0;
-    const float *__restrict__ in = second ? in2 : in1;
+    const TI *__restrict__ in = second ? in2 : in1;
     float *__restrict__ P = second ? P2 : P1;
     const int pitch = second ? pitch2 : pitch1;
     const int shift = second ? kShift : 0;
@@ -106,16 +140,8 @@ __global__ void __launch_bounds__(256) corr_planarize(const float *__restrict__ 
         const int y = (int)(r % H); r /= H;
         const int c = (int)(r % C);
         const int n = (int)(r / C);
-        const float *src = in + (((size_t)n * C + c) * H + y) * W + x;
-        float4 v;
-        if (vec_ok) {
-            v = ldg_stream4(src);
-        } else {
-            v.x = src[0];
-            v.y = x + 1 < W ? src[1] : 0.f;
-            v.z = x + 2 < W ? src[2] : 0.f;
-            v.w = x + 3 < W ? src[3] : 0.f;
-        }
+        const TI *src = in + (((size_t)n * C + c) * H + y) * W + x;
+        const float4 v = planarize_load4<TI>(src, x, W, vec_ok);
         const int py = y & 1, yy = y >> 1, xx = (x >> 1) + shift;
         float *row0 = P + ((((size_t)n * 4 + py * 2 + 0) * C + c) * Hp + yy) * pitch;
         float *row1 = P + ((((size_t)n * 4 + py * 2 + 1) * C + c) * Hp + yy) * pitch;
@@ -213,7 +239,8 @@ static_assert(kTY * kNhwcRowPitch * 4 <= kSmemBytes, "NHWC epilogue staging must
 // NHWC_OUT: the cost volume is written channels-last into channels [c_off, c_off + 441) of a [B, H, W, c_dst]
 // tensor, with LeakyReLU(slope) applied (slope 1 = identity) -- FlowNetC's `corr_activation` and the concat with
 // conv_redir (FlowNetC.py:89-94) folded into the store, for a channels_last conv body.
-template <int UNROLL, bool NHWC_OUT>
+// OT: storage type of the (NCHW) output; 16-bit types round on the way out (the `.half()` of FlowNetC.py:87).
+template <int UNROLL, bool NHWC_OUT, typename OT = float>
 __global__ void __launch_bounds__(256, 1)
 corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
               float *__restrict__ out, int C, int H, int W, int row_tiles, int x_tiles,
@@ -405,9 +432,16 @@ corr_fwd_fast(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
             const int y = 2 * (y0 + ry) + py;
             if (y < H && x < W) {
                 const float *src = stage + (tjl * (kD * kTY) + ry) * kEpiPitch + lane;
-                float *dst = out_n + (size_t)((grp * kEpiGroup + tjl) * kD) * hw + (size_t)y * W + x;
+                if constexpr (std::is_same<OT, float>::value) {
+                    float *dst = out_n + (size_t)((grp * kEpiGroup + tjl) * kD) * hw + (size_t)y * W + x;
 #pragma unroll
-                for (int ti = 0; ti < kD; ++ti) dst[(size_t)ti * hw] = src[ti * (kTY * kEpiPitch)];
+                    for (int ti = 0; ti < kD; ++ti) dst[(size_t)ti * hw] = src[ti * (kTY * kEpiPitch)];
+                } else {
+                    unsigned short *dst = reinterpret_cast<unsigned short *>(out) + (size_t)n * (kD * kD) * hw +
+                                          (size_t)((grp * kEpiGroup + tjl) * kD) * hw + (size_t)y * W + x;
+#pragma unroll
+                    for (int ti = 0; ti < kD; ++ti) dst[(size_t)ti * hw] = Io16<OT>::from_float(src[ti * (kTY * kEpiPitch)]);
+                }
             }
         }
         __syncthreads();
@@ -464,7 +498,7 @@ int corr_fast_planes_nhwc(const float *in1, const float *in2, const CorrGeom &g,
 
 // the correlation proper, on planes already in the workspace
 int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
-                   bool nhwc_out, int c_dst, int c_off, float slope)
+                   bool nhwc_out, int c_dst, int c_off, float slope, int out_dtype)
 {
     float *P1, *P2;
     int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr_fwd");
@@ -480,6 +514,8 @@ int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cud
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, false, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
@@ -488,18 +524,25 @@ int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cud
     FLOWOPS_REQUIRE(grid < (1ull << 31), FLOWOPS_EUNSUPPORTED, "corr_fwd: grid too large");
     if (nhwc_out)
         corr_fwd_fast<2, true><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, c_dst, c_off, slope);
+    else if (out_dtype == FLOWOPS_DTYPE_F16)
+        corr_fwd_fast<2, false, __half><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, 0, 0, 1.f);
+    else if (out_dtype == FLOWOPS_DTYPE_BF16)
+        corr_fwd_fast<2, false, __nv_bfloat16><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, 0, 0, 1.f);
     else
         corr_fwd_fast<2, false><<<(unsigned)grid, 256, kSmemBytes, st>>>(tm1, tm2, out, g.C, g.H, g.W, row_tiles, x_tiles, 0, 0, 1.f);
     return check_launch("corr_fwd_fast");
 }
 
+// io_dtype 0: fp32 tensors (flowops_corr_fwd); FLOWOPS_DTYPE_F16 / _BF16: 16-bit inputs and output, NCHW only
+// (flowops_corr_fwd_16) -- in1, in2 and out then point at 16-bit elements
 int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const CorrGeom &g, int in_layout,
-                         void *ws, size_t ws_bytes, cudaStream_t st)
+                         void *ws, size_t ws_bytes, cudaStream_t st, int io_dtype)
 {
     float *P1, *P2;
     int rc = corr_fast_workspace_check(g, ws, ws_bytes, P1, P2, "corr_fwd");
     if (rc) return rc;
     if (in_layout == FLOWOPS_LAYOUT_NHWC) {
+        FLOWOPS_REQUIRE(io_dtype == 0, FLOWOPS_EUNSUPPORTED, "corr_fwd: channels-last inputs are fp32 only");
         rc = corr_fast_planes_nhwc(in1, in2, g, -1, nullptr, 0.f, nullptr, ws, ws_bytes, st);
         if (rc) return rc;
     } else {
@@ -508,15 +551,25 @@ int corr_fast_fwd_launch(const float *in1, const float *in2, float *out, const C
             cudaError_t e = cudaMemsetAsync(ws, 0, corr_fast_fwd_workspace(g), st);
             if (e != cudaSuccess) { set_error("corr_fwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
         }
-        const int vec_ok = (g.W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        // fp32 rows of W % 4 == 0 floats from a 16-byte-aligned base are 16-byte aligned; 16-bit rows are 8-byte aligned
+        const int vec_ok = (g.W % 4 == 0) && (io_dtype == 0 ? (aligned16(in1) && aligned16(in2))
+                                                            : ((((uintptr_t)in1 | (uintptr_t)in2) & 7u) == 0));
         const size_t total = (size_t)g.B * g.C * g.H * ((g.W + 3) / 4);
         size_t blocks = (total + 255) / 256;
         if (blocks > (size_t)kNumSMs * 8 * 8) blocks = (size_t)kNumSMs * 8 * 8;
-        corr_planarize<<<dim3((unsigned)blocks, 2), 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
+        const dim3 pgrid((unsigned)blocks, 2);
+        if (io_dtype == FLOWOPS_DTYPE_F16)
+            corr_planarize<__half><<<pgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(in1), reinterpret_cast<const __half *>(in2),
+                                                          P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
+        else if (io_dtype == FLOWOPS_DTYPE_BF16)
+            corr_planarize<__nv_bfloat16><<<pgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(in1), reinterpret_cast<const __nv_bfloat16 *>(in2),
+                                                                 P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
+        else
+            corr_planarize<float><<<pgrid, 256, 0, st>>>(in1, in2, P1, P2, g.B, g.C, g.H, g.W, p.Hp, p.pitch1, p.pitch2, vec_ok);
         rc = check_launch("corr_planarize");
         if (rc) return rc;
     }
-    return corr_fast_main(out, g, ws, ws_bytes, st);
+    return corr_fast_main(out, g, ws, ws_bytes, st, false, 0, 0, 1.f, io_dtype);
 }
 
 }  // namespace flowops

@@ -16,6 +16,7 @@
 //     leaves the XU pipe only the 20 F2F conversions per pixel that the reference's mixed precision forces.
 // Measured on B200, config 3, smooth flow: 110 -> 81 us (RESAMPLE2D), 114 -> 80 us (GRIDSAMPLE), bit-identical.
 #pragma once
+#include "io16.cuh"
 #include "warp.cuh"
 
 namespace flowops {
@@ -91,12 +92,16 @@ __device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q, co
     q.w.w_br = __fmul_rn(alpha, beta);
 }
 
-// models/networks.py:97-98 + ATen grid_sampler (align_corners=False, border); see gs_coords / gs_weights
+// models/networks.py:97-98 + ATen grid_sampler (align_corners=False, border); see gs_coords / gs_weights.
+// T is the dtype the reference evaluates the grid in (the flow's: networks.py:96-98, base_model.py:131-134): for
+// 16-bit flows the normalised flow and its sum with the (equally rounded) linspace table are rounded to T;
+// T = float leaves both as they are.
+template <typename T = float>
 __device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q, const WarpArgs &a, float /*xfl*/, float /*yfl*/,
                                          int x, int y, float dx, float dy)
 {
-    const float gx = __fadd_rn(__ldg(a.lin_x + x), __fmul_rn(dx, a.invx));
-    const float gy = __fadd_rn(__ldg(a.lin_y + y), __fmul_rn(dy, a.invy));
+    const float gx = round_io<T>(__fadd_rn(__ldg(a.lin_x + x), round_io<T>(__fmul_rn(dx, a.invx))));
+    const float gy = round_io<T>(__fadd_rn(__ldg(a.lin_y + y), round_io<T>(__fmul_rn(dy, a.invy))));
     float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), a.wm1 + 1.f, -1.f), 0.5f);
     float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), a.hm1 + 1.f, -1.f), 0.5f);
     ix = fminf(a.wm1, fmaxf(ix, 0.f));

@@ -1,7 +1,10 @@
 """Tensor-level calls into libflowops.so: argument checking, output allocation, stream and device
 handling.  PyTorch is plumbing here (device memory, streams); all arithmetic happens in the library.
 
-Every function requires CUDA fp32 tensors and raises otherwise -- by design there is no CPU path.
+Every function requires CUDA tensors and raises otherwise -- by design there is no CPU path.  fp32 is the
+operators' dtype (as in the reference); ChannelNorm, the forward warps and the Correlation forward also take
+fp16 / bf16 tensors and then run the library's "16-bit storage, fp32 math" entry points (flowops_*_16), which
+reproduce what the reference's fp16 mode computes (include/flowops.h).
 """
 import ctypes
 
@@ -10,19 +13,30 @@ import torch
 from . import _lib
 from ._lib import WARP_GRIDSAMPLE, WARP_RESAMPLE2D, check
 
+_DTYPE16 = {torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
 
-def _require(t, name, ndim=4):
+
+def _require(t, name, ndim=4, dtype=torch.float32):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor: the flow hot path has no CPU implementation "
                            "(got device %s)" % (name, t.device))
-    if t.dtype != torch.float32:
-        raise TypeError("%s must be float32 (the reference ops are fp32-only on this path; cast like "
-                        "FlowNetC.py:86-87 does), got %s" % (name, t.dtype))
+    if t.dtype != dtype:
+        if dtype == torch.float32:
+            raise TypeError("%s must be float32 (the reference ops are fp32-only on this path; cast like "
+                            "FlowNetC.py:86-87 does), got %s" % (name, t.dtype))
+        raise TypeError("%s must be %s like the other tensors of the call, got %s" % (name, dtype, t.dtype))
     if t.dim() != ndim:
         raise ValueError("%s must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
     return t
+
+
+def _io_dtype(t, name):
+    """fp32, or one of the 16-bit storage types the *_16 entry points take."""
+    if isinstance(t, torch.Tensor) and t.dtype in _DTYPE16:
+        return t.dtype
+    return torch.float32
 
 
 def _is_nhwc(t):
@@ -41,24 +55,34 @@ def _stream():
 # ChannelNorm
 # ---------------------------------------------------------------------------------------------
 def channelnorm_forward(x):
-    x = _require(x, "input1").contiguous()
+    """fp32, or fp16 / bf16: the reference kernel as instantiated for at::Half (channelnorm_kernel.cu:111)."""
+    dt = _io_dtype(x, "input1")
+    x = _require(x, "input1", dtype=dt).contiguous()
     B, C, H, W = x.shape
     with torch.cuda.device_of(x):
-        y = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+        y = torch.empty((B, 1, H, W), device=x.device, dtype=dt)
         if x.numel():
-            check(_lib.load().flowops_cnorm_fwd(_p(x), _p(y), B, C, H, W, _stream()), "cnorm_fwd")
+            if dt == torch.float32:
+                check(_lib.load().flowops_cnorm_fwd(_p(x), _p(y), B, C, H, W, _stream()), "cnorm_fwd")
+            else:
+                check(_lib.load().flowops_cnorm_fwd_16(_p(x), _p(y), B, C, H, W, _DTYPE16[dt], _stream()), "cnorm_fwd_16")
     return y
 
 
 def channelnorm_backward(x, y, gy):
-    x = _require(x, "input1").contiguous()
-    y = _require(y, "output").contiguous()
-    gy = _require(gy, "grad_output").contiguous()
+    dt = _io_dtype(x, "input1")
+    x = _require(x, "input1", dtype=dt).contiguous()
+    y = _require(y, "output", dtype=dt).contiguous()
+    gy = _require(gy, "grad_output", dtype=dt).contiguous()
     B, C, H, W = x.shape
     with torch.cuda.device_of(x):
         gx = torch.empty_like(x)
         if x.numel():
-            check(_lib.load().flowops_cnorm_bwd(_p(x), _p(y), _p(gy), _p(gx), B, C, H, W, _stream()), "cnorm_bwd")
+            if dt == torch.float32:
+                check(_lib.load().flowops_cnorm_bwd(_p(x), _p(y), _p(gy), _p(gx), B, C, H, W, _stream()), "cnorm_bwd")
+            else:
+                check(_lib.load().flowops_cnorm_bwd_16(_p(x), _p(y), _p(gy), _p(gx), B, C, H, W, _DTYPE16[dt], _stream()),
+                      "cnorm_bwd_16")
     return gx
 
 
@@ -68,41 +92,50 @@ def channelnorm_backward(x, y, gy):
 _LIN_CACHE = {}
 
 
-def _lin_tables(H, W, device):
+def _lin_tables(H, W, device, dtype=torch.float32):
     """torch.linspace(-1, 1, n) on the host in fp32, moved to the device: exactly the values
     get_grid produces (reference models/networks.py:15-28).  Cached per (H, W, device) -- the
     counterpart of the reference's `self.grid` cache (networks.py:95-96), 4*(H+W) bytes instead
-    of a [b,2,h,w] tensor."""
-    key = (H, W, device)
+    of a [b,2,h,w] tensor.  For a 16-bit flow the reference builds the grid in that dtype
+    (`get_grid(..., dtype=flow.dtype)`, networks.py:96): the tables then hold the rounded values (as fp32)."""
+    key = (H, W, device, dtype)
     t = _LIN_CACHE.get(key)
     if t is None:
-        t = (torch.linspace(-1.0, 1.0, W).to(device), torch.linspace(-1.0, 1.0, H).to(device))
+        t = tuple(torch.linspace(-1.0, 1.0, n).to(dtype).float().to(device) for n in (W, H))
         _LIN_CACHE[key] = t
     return t
 
 
-def _warp_args(img, flow, mode):
-    img = _require(img, "image")
-    flow = _require(flow, "flow")
+def _warp_args(img, flow, mode, dtype=torch.float32):
+    img = _require(img, "image", dtype=dtype)
+    flow = _require(flow, "flow", dtype=dtype)
     B, C, H, W = img.shape
     if flow.shape != (B, 2, H, W):
         raise ValueError("flow must be [B,2,H,W] matching the image %s, got %s" % (tuple(img.shape), tuple(flow.shape)))
     if flow.device != img.device:
         raise RuntimeError("image and flow must be on the same device")
     if mode == WARP_GRIDSAMPLE:
-        lx, ly = _lin_tables(H, W, img.device)
+        lx, ly = _lin_tables(H, W, img.device, dtype)
     else:
         lx = ly = None
     return img.contiguous(), flow.contiguous(), B, C, H, W, lx, ly
 
 
 def warp_forward(img, flow, mode=WARP_RESAMPLE2D):
-    img, flow, B, C, H, W, lx, ly = _warp_args(img, flow, mode)
+    """fp32 tensors, or image and flow both fp16 / both bf16 (1..3 channels): then one kernel does what the reference's
+    fp16 mode spreads over casts -- fp16_resample2d (models.py:22-28) for RESAMPLE2D, Model.resample with opt['fp16']
+    (base_model.py:123-136) for GRIDSAMPLE."""
+    dt = _io_dtype(img, "image")
+    img, flow, B, C, H, W, lx, ly = _warp_args(img, flow, mode, dt)
     with torch.cuda.device_of(img):
         out = torch.empty_like(img)
         if img.numel():
-            check(_lib.load().flowops_warp_fwd(_p(img), _p(flow), _p(out), B, C, H, W, mode, _p(lx), _p(ly), _stream()),
-                  "warp_fwd")
+            if dt == torch.float32:
+                check(_lib.load().flowops_warp_fwd(_p(img), _p(flow), _p(out), B, C, H, W, mode, _p(lx), _p(ly), _stream()),
+                      "warp_fwd")
+            else:
+                check(_lib.load().flowops_warp_fwd_16(_p(img), _p(flow), _p(out), B, C, H, W, mode, _p(lx), _p(ly),
+                                                      _DTYPE16[dt], _stream()), "warp_fwd_16")
     return out
 
 
@@ -299,13 +332,34 @@ def _workspace(nbytes, device):
     return torch.empty((max(nbytes, 1),), device=device, dtype=torch.uint8)
 
 
+def correlation_has_16bit_path(in1, pad_size, kernel_size, max_displacement, stride1, stride2):
+    """True when flowops_corr_fwd_16 takes this shape and parameter set (the FlowNetC configuration)."""
+    B, C, H, W = in1.shape
+    return _lib.load().flowops_corr_fwd_workspace_bytes(B, C, H, W, int(pad_size), int(kernel_size), int(max_displacement),
+                                                        int(stride1), int(stride2)) > 0
+
+
 def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
-    in1, in2 = _require(in1, "input1"), _require(in2, "input2")
+    """fp32 tensors, or both fp16 / both bf16 in the FlowNetC configuration: `corr(a.float(), b.float()).half()`
+    (FlowNetC.py:86-87) as one operator call."""
+    dt = _io_dtype(in1, "input1")
+    in1, in2 = _require(in1, "input1", dtype=dt), _require(in2, "input2", dtype=dt)
     if in1.shape != in2.shape or in1.device != in2.device:
         raise ValueError("input1 %s and input2 %s must have the same shape and device" % (tuple(in1.shape), tuple(in2.shape)))
     B, C, H, W = in1.shape
     params = (int(pad_size), int(kernel_size), int(max_displacement), int(stride1), int(stride2))
     lib = _lib.load()
+    if dt != torch.float32:
+        in1, in2 = in1.contiguous(), in2.contiguous()
+        oc, oh, ow = correlation_out_shape(H, W, *params)
+        with torch.cuda.device_of(in1):
+            out = torch.empty((B, oc, oh, ow), device=in1.device, dtype=dt)
+            nbytes = lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *params)
+            ws = _workspace(nbytes, in1.device)
+            if in1.numel():
+                check(lib.flowops_corr_fwd_16(_p(in1), _p(in2), _p(out), B, C, H, W, *params, _DTYPE16[dt], _p(ws), nbytes,
+                                              _stream()), "corr_fwd_16")
+        return out
     # channels_last features (a channels_last conv body) are taken as they are by the FlowNetC fast path
     layout = 1 if (_is_nhwc(in1) and _is_nhwc(in2) and lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *params) > 0) else 0
     if layout == 0:

@@ -78,7 +78,9 @@ class FlowNetC(nn.Module):
         else:
             c2a, c3a = self.tower(x[:, 0:3])
             _, c3b = self.tower(x[:, 3:])
-            if self.fp16:       # the operator is fp32-only, as in the reference (FlowNetC.py:86-87)
+            if self.fp16 and c3a.dtype == torch.float16 and c3b.dtype == torch.float16:
+                cost = self.corr(c3a, c3b)      # corr(a.float(), b.float()).half() (FlowNetC.py:86-87) as one operator call
+            elif self.fp16:
                 cost = self.corr(c3a.float(), c3b.float()).half()
             else:
                 cost = self.corr(c3a, c3b)

@@ -6,7 +6,13 @@ Same contract: ``input1`` (image) and ``input2`` (flow, pixels, ch0 = dx) must b
 ``kernel_size == 1`` exists: larger kernels read out of bounds in the reference and are never used.
 The gradient outputs are allocated by the library call (no separate zero-fill pass as in
 resample2d.py:17,29-30), and a gradient that is not needed is not computed.
+
+fp16 / bf16 tensors (image and flow of the same dtype, CUDA) are accepted as well: the forward is then the
+16-bit-storage kernel (flowops_warp_fwd_16), which equals ``Resample2d()(a.float(), b.float()).to(dtype)`` --
+the reference's fp16_resample2d (models.py:22-28) -- bit for bit, and the backward is what autograd makes of
+that chain (casts around the fp32 backward).
 """
+import torch
 from torch.autograd import Function
 from torch.nn.modules.module import Module
 
@@ -29,9 +35,13 @@ class Resample2dFunction(Function):
     @staticmethod
     def backward(ctx, grad_output):
         input1, input2 = ctx.saved_tensors
+        dtype = input1.dtype
         grad_input1, grad_input2 = _F.warp_backward(
-            input1, input2, grad_output.contiguous(),
+            input1.float(), input2.float(), grad_output.float().contiguous(),      # no-ops for fp32 tensors
             need_img=ctx.needs_input_grad[0], need_flow=ctx.needs_input_grad[1], mode=_F.WARP_RESAMPLE2D)
+        if dtype != torch.float32:                                                 # 16-bit storage: cast back
+            grad_input1 = grad_input1.to(dtype) if grad_input1 is not None else None
+            grad_input2 = grad_input2.to(dtype) if grad_input2 is not None else None
         return grad_input1, grad_input2, None
 
 

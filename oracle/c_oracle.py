@@ -112,3 +112,39 @@ def gridwarp_fwd(img, flow, lin_x, lin_y, inv_mode=1, fma_mode=1):
     lib().oracle_gridwarp_fwd(_p(img), _p(flow), _p(out), _p(lin_x), _p(lin_y),
                               _I(B), _I(C), _I(H), _I(W), _I(inv_mode), _I(fma_mode))
     return out
+
+
+# ---- 16-bit storage (values travel as float32 arrays holding representable values) ----
+DTYPE_F16, DTYPE_BF16 = 1, 2
+
+
+def round16(a, dtype):
+    a = _f32(a)
+    out = np.empty_like(a)
+    lib().oracle_round16(_p(a), _p(out), ctypes.c_longlong(a.size), _I(dtype))
+    return out
+
+
+def cnorm_fwd_16(x, dtype):
+    x = _f32(x)
+    B, C, H, W = x.shape
+    y = np.empty((B, 1, H, W), np.float32)
+    lib().oracle_cnorm_fwd_16(_p(x), _p(y), _I(B), _I(C), _I(H), _I(W), _I(dtype))
+    return y
+
+
+def cnorm_bwd_16(x, y, gy, dtype):
+    x, y, gy = _f32(x), _f32(y), _f32(gy)
+    B, C, H, W = x.shape
+    gx = np.empty_like(x)
+    lib().oracle_cnorm_bwd_16(_p(x), _p(y), _p(gy), _p(gx), _I(B), _I(C), _I(H), _I(W), _I(dtype))
+    return gx
+
+
+def gridwarp_fwd_16(img, flow, lin_x, lin_y, dtype, inv_mode=1, fma_mode=1):
+    img, flow, lin_x, lin_y = _f32(img), _f32(flow), _f32(lin_x), _f32(lin_y)
+    B, C, H, W = img.shape
+    out = np.empty_like(img)
+    lib().oracle_gridwarp_fwd_16(_p(img), _p(flow), _p(out), _p(lin_x), _p(lin_y),
+                                 _I(B), _I(C), _I(H), _I(W), _I(inv_mode), _I(fma_mode), _I(dtype))
+    return out

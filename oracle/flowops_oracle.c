@@ -390,4 +390,119 @@ void oracle_gridwarp_fwd(const float *img, const float *flow, float *out,
             }
 }
 
-int oracle_abi_version(void) { return 1; }
+/* ------------------------------------------------------------------------------------------ */
+/* 16-bit storage (fp16 / bf16): the reference's fp16 mode                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* Tensors cross this interface as float arrays whose values are representable in the storage type;
+ * `dtype` is 1 (IEEE binary16) or 2 (bfloat16), as FLOWOPS_DTYPE_F16 / _BF16 in include/flowops.h.
+ * round16() is float -> storage type -> float with round-to-nearest-even, i.e. what c10::Half's /
+ * c10::BFloat16's float constructor and `.half()` / `.bfloat16()` do (cvt.rn.f16.f32 /
+ * cvt.rn.bf16.f32 on the device); written out on the bit pattern so that it does not depend on the
+ * compiler's _Float16 support.  tests/test_oracle.py pins it against numpy.float16 and torch.bfloat16. */
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static float round_half(float f)
+{
+    const uint32_t u = f2u(f), sign = u & 0x80000000u, a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return u2f(sign | 0x7fc00000u);          /* NaN */
+    if (a >= 0x477ff000u) return u2f(sign | 0x7f800000u);         /* >= 65520 rounds to inf (inf stays inf) */
+    if (a < 0x33000001u) return u2f(sign);                        /* <= 2^-25 rounds to zero (ties to even) */
+    if (a >= 0x38800000u) {                                       /* normal half: drop 13 mantissa bits */
+        const uint32_t r = a + 0xfffu + ((a >> 13) & 1u);          /* nearest, ties to even; a carry moves the exponent */
+        return u2f(sign | (r & ~0x1fffu));
+    }
+    /* subnormal half: a multiple of 2^-24.  |f| = m * 2^(e-150) with the implicit one in m, so the number of
+     * quanta is m >> (126 - e), 14 <= shift <= 24 here */
+    const uint32_t m = (a & 0x007fffffu) | 0x00800000u, sh = 126u - (a >> 23);
+    const uint32_t q = (m + ((1u << (sh - 1)) - 1u) + ((m >> sh) & 1u)) >> sh;
+    return (sign ? -1.0f : 1.0f) * (float)q * 5.9604644775390625e-08f;          /* exact: q <= 1024 */
+}
+
+static float round_bf16(float f)
+{
+    const uint32_t u = f2u(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return u2f((u & 0x80000000u) | 0x7fc00000u);     /* NaN */
+    const uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);                                  /* may carry into inf: correct */
+    return u2f(r & 0xffff0000u);
+}
+
+static inline float round16(float f, int dtype) { return dtype == 1 ? round_half(f) : round_bf16(f); }
+
+void oracle_round16(const float *in, float *out, long long n, int dtype)
+{
+    for (long long i = 0; i < n; ++i) out[i] = round16(in[i], dtype);
+}
+
+/* kernel_channelnorm_update_output<at::Half> (channelnorm_kernel.cu:19-60): `val * val` multiplies two
+ * at::Half values -- a float product rounded back to half (c10/util/Half-inl.h operator*) -- before
+ * static_cast<float> and the fp32 `result +=` (:55-56); sqrt in fp32 (:58), rounded to half on store (:59). */
+void oracle_cnorm_fwd_16(const float *x, float *y, int B, int C, int H, int W, int dtype)
+{
+    const size_t hw = (size_t)H * W;
+    for (long long i = 0; i < (long long)B * (long long)hw; ++i) {
+        const size_t b = (size_t)i / hw, p = (size_t)i % hw;
+        float result = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const float val = x[(b * C + c) * hw + p];
+            result = result + round16(val * val, dtype);
+        }
+        y[i] = round16(sqrtf(result), dtype);
+    }
+}
+
+/* kernel_channelnorm_backward_input1<at::Half> (channelnorm_kernel.cu:64-96): fp32 product of the widened
+ * operands, fp64 divide (the 1e-9 literal), `val` is a float, the store rounds it to half (:93-94). */
+void oracle_cnorm_bwd_16(const float *x, const float *y, const float *gy, float *gx,
+                         int B, int C, int H, int W, int dtype)
+{
+    const size_t hw = (size_t)H * W;
+    for (long long i = 0; i < (long long)B * C * (long long)hw; ++i) {
+        const size_t b = (size_t)i / (hw * C), p = (size_t)i % hw;
+        const float prod = gy[b * hw + p] * x[i];
+        const float val = (float)((double)prod / ((double)y[b * hw + p] + 1e-9));
+        gx[i] = round16(val, dtype);
+    }
+}
+
+/* Model.resample with opt['fp16'] on 16-bit tensors (models/base_model.py:123-136):
+ *   grid  = get_grid(..., dtype=flow.dtype)            -> lin_x / lin_y arrive rounded to the storage type
+ *   nflow = flow / ((w-1)/2)                           -> rounded to the storage type (CUDA: multiply by the fp32
+ *                                                         reciprocal, inv_mode 1; CPU: true divide, inv_mode 0)
+ *   g     = grid + nflow                               -> rounded to the storage type
+ *   out   = grid_sample(image.float(), g.float(), bilinear, border).half()      -> fp32 chain as above, rounded */
+void oracle_gridwarp_fwd_16(const float *img, const float *flow, float *out,
+                            const float *lin_x, const float *lin_y,
+                            int B, int C, int H, int W, int inv_mode, int fma_mode, int dtype)
+{
+    const float sx = (float)((W - 1.0) / 2.0), sy = (float)((H - 1.0) / 2.0);
+    const float invx = 1.0f / sx, invy = 1.0f / sy;
+    for (int b = 0; b < B; ++b)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const float dx = flow[IDX4(b, 0, y, x, 2, H, W)];
+                const float dy = flow[IDX4(b, 1, y, x, 2, H, W)];
+                const float gx = round16(lin_x[x] + round16(inv_mode ? dx * invx : dx / sx, dtype), dtype);
+                const float gy = round16(lin_y[y] + round16(inv_mode ? dy * invy : dy / sy, dtype), dtype);
+                float ix = fma_mode ? fmaf(gx + 1.f, (float)W, -1.f) / 2 : ((gx + 1.f) * W - 1) / 2;
+                float iy = fma_mode ? fmaf(gy + 1.f, (float)H, -1.f) / 2 : ((gy + 1.f) * H - 1) / 2;
+                ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+                iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+                const float fx = floorf(ix), fy = floorf(iy);
+                const int ix_nw = (int)fx, iy_nw = (int)fy;
+                const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
+                const float nw = ((float)ix_se - ix) * ((float)iy_se - iy);
+                const float ne = (ix - (float)ix_nw) * ((float)iy_se - iy);
+                const float sw = ((float)ix_se - ix) * (iy - (float)iy_nw);
+                const float se = (ix - (float)ix_nw) * (iy - (float)iy_nw);
+                for (int c = 0; c < C; ++c) {
+                    float acc = fmaf(img[IDX4(b, c, iy_nw, ix_nw, C, H, W)], nw, 0.f);     /* nw is always inside after the clip */
+                    if (ix_se < W) acc = fmaf(img[IDX4(b, c, iy_nw, ix_se, C, H, W)], ne, acc);
+                    if (iy_se < H) acc = fmaf(img[IDX4(b, c, iy_se, ix_nw, C, H, W)], sw, acc);
+                    if (iy_se < H && ix_se < W) acc = fmaf(img[IDX4(b, c, iy_se, ix_se, C, H, W)], se, acc);
+                    out[IDX4(b, c, y, x, C, H, W)] = round16(acc, dtype);
+                }
+            }
+}
+
+int oracle_abi_version(void) { return 2; }

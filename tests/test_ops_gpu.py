@@ -71,6 +71,33 @@ def test_cnorm_vs_oracle_bitexact(ops, c_oracle, shape):
     assert (gx == gx_ref).mean() >= 0.9999       # reciprocal + correction reproduces the fp64 divide
 
 
+def test_cnorm_special_values_bit_exact(ops, c_oracle):
+    """Zeros of either sign, squares that overflow to inf, inf and NaN inputs: forward and backward equal the
+    restated reference kernels bit for bit, sign of zero included ((-0) / d is -0; finite / inf is 0, not NaN)."""
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((2, 3, 8, 16)).astype(np.float32)
+    x[0, :, 0, 0] = 0.0
+    x[0, 1, 0, 1] = -0.0
+    x[0, 0, 0, 2] = 1e30            # square overflows: y = inf, every gradient of the pixel is 0
+    x[0, 2, 0, 3] = np.inf
+    x[0, 1, 0, 4] = np.nan
+    x[1, :, 1, :] = 0.0
+    gy = rng.standard_normal((2, 1, 8, 16)).astype(np.float32)
+    gy[0, 0, 0, 5] = 0.0
+    gy[0, 0, 0, 6] = -0.0
+    gy[0, 0, 0, 7] = 3e38           # product overflows: the quotient is inf
+    x[0, 0, 0, 7] = 7.0
+    xt = cu(x).requires_grad_()
+    y = ops.ChannelNorm()(xt)
+    y_ref = c_oracle.cnorm_fwd(x)
+    assert np.array_equal(y.detach().cpu().numpy(), y_ref, equal_nan=True)
+    y.backward(cu(gy))
+    gx, gx_ref = xt.grad.cpu().numpy(), c_oracle.cnorm_bwd(x, y_ref, gy)
+    assert np.array_equal(gx, gx_ref, equal_nan=True)
+    ok = ~np.isnan(gx_ref)            # the sign of a NaN is not defined (x86 and the GPU generate different ones)
+    assert np.array_equal(np.signbit(gx[ok]), np.signbit(gx_ref[ok]))
+
+
 def test_cnorm_golden(ops, golden_native):
     g = golden_native
     for name in ["cn3", "cn2", "cn5"]:
@@ -101,7 +128,7 @@ def test_cnorm_empty_and_errors(ops):
     with pytest.raises(RuntimeError):
         ops.ChannelNorm()(torch.zeros(1, 3, 4, 4))              # CPU tensor: no fallback
     with pytest.raises(TypeError):
-        ops.ChannelNorm()(torch.zeros(1, 3, 4, 4, device="cuda", dtype=torch.float16))
+        ops.ChannelNorm()(torch.zeros(1, 3, 4, 4, device="cuda", dtype=torch.float64))    # fp32, fp16 and bf16 only
 
 
 # =============================================================================================

@@ -165,3 +165,65 @@ def test_correlation_channel_order_dy_outer(c_oracle):
     out = c_oracle.corr_fwd(a, b, 20, 1, 20, 1, 2)
     tc = (1 + 10) * 21 + (-2 + 10)
     assert out[0, tc, 4, 4] == 1.0 and np.count_nonzero(out) == 1
+
+
+# ---- (c) 16-bit storage: the reference's fp16 mode ------------------------------------------------
+def test_round16_matches_numpy_float16_and_torch_bfloat16(c_oracle):
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 2 ** 32, size=500_000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    special = np.array([0.0, -0.0, 65504, 65519.99, 65520, 65536, 2.0 ** -24, 2.0 ** -25, 2.0 ** -25 * 1.000001, 3 * 2.0 ** -25,
+                        2.0 ** -14, 6.1e-5, np.inf, -np.inf, np.nan], np.float32)
+    x = np.concatenate([x, special, rng.standard_normal(200_000).astype(np.float32),
+                        (1e-5 * rng.standard_normal(200_000)).astype(np.float32)])
+    with np.errstate(all="ignore"):
+        want = x.astype(np.float16).astype(np.float32)
+    got = c_oracle.round16(x, c_oracle.DTYPE_F16)
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(np.signbit(got), np.signbit(want))
+    want = torch.from_numpy(x.copy()).bfloat16().float().numpy()
+    got = c_oracle.round16(x, c_oracle.DTYPE_BF16)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["small", "odd", "border", "wide"])
+def test_gridwarp16_oracle_vs_reference_python_fp16_golden(c_oracle, name):
+    """Model.resample with opt['fp16'] on half tensors, run by the reference's own code on the CPU
+    (tests/golden/make_golden_cpu_fp16.py): the oracle's CPU form (true divide) must reproduce it bit for bit."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "resample_fp16_cpu.npz"))
+    img, flow = g[name + "_img"], g[name + "_flow"]
+    H, W = img.shape[2:]
+    lx = torch.linspace(-1, 1, W).half().float().numpy()
+    ly = torch.linspace(-1, 1, H).half().float().numpy()
+    out = c_oracle.gridwarp_fwd_16(img, flow, lx, ly, c_oracle.DTYPE_F16, inv_mode=0, fma_mode=1)
+    assert np.array_equal(out, g[name + "_out"])
+    # the CUDA form (reciprocal multiply) differs from it only where the 16-bit rounding of flow / scale flips
+    out_cuda_form = c_oracle.gridwarp_fwd_16(img, flow, lx, ly, c_oracle.DTYPE_F16, inv_mode=1, fma_mode=1)
+    assert np.mean(out_cuda_form != g[name + "_out"]) < 0.02
+
+
+@pytest.mark.parametrize("dtype_name", ["float16", "bfloat16"])
+def test_cnorm16_oracle_vs_torch_emulation(c_oracle, dtype_name):
+    """channelnorm_kernel.cu:55-59 instantiated for a 16-bit type, emulated with torch CPU tensors of that type:
+    square rounded to the type, fp32 sum in channel order, fp32 sqrt, rounded to the type."""
+    dt = getattr(torch, dtype_name)
+    code = c_oracle.DTYPE_F16 if dt == torch.float16 else c_oracle.DTYPE_BF16
+    torch.manual_seed(3)
+    x = (3 * torch.randn(2, 3, 9, 11)).to(dt)
+    x[0, :, 0, 0] = 0
+    x[0, 0, 0, 1] = 300.0                       # 300^2 overflows fp16: the reference kernel yields inf there
+    acc = torch.zeros(2, 9, 11)
+    for c in range(3):
+        v = x[:, c].float()
+        acc = acc + (v * v).to(dt).float()
+    want = acc.sqrt().to(dt).float().numpy()[:, None]
+    got = c_oracle.cnorm_fwd_16(x.float().numpy(), code)
+    assert np.array_equal(got, want)
+    if dt == torch.float16:
+        assert np.isinf(got[0, 0, 0, 1])
+    gy = torch.randn(2, 1, 9, 11).to(dt)
+    y = torch.from_numpy(got)
+    q = (gy.float() * x.float()).double() / (y.double() + 1e-9)
+    want_gx = q.float().to(dt).float().numpy()
+    got_gx = c_oracle.cnorm_bwd_16(x.float().numpy(), got, gy.float().numpy(), code)
+    assert np.array_equal(got_gx, want_gx, equal_nan=True)

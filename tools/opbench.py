@@ -72,7 +72,7 @@ def time_rotating(fns, launches=100, warmup=1):
     return e0.elapsed_time(e1) / launches * 1e3
 
 
-def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
+def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None):
     torch.manual_seed(0)
     pk = peaks()
     flush = L2Flusher()
@@ -88,6 +88,8 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
         """fn(*args) is the new operator, ref_fn(*args) the reference's.  Primary timing: back-to-back
         launches rotating among clones of `args` whose combined footprint exceeds 2x L2 (L2-cold, launch gap
         amortised); also reported: one launch per event pair with an L2 flush in between, and L2-warm."""
+        if only and only not in name:
+            return
         foot = sum(t.numel() * t.element_size() for t in args)
         nsets = int(min(64, max(2, -(-(300 << 20) // max(foot, 1)))))
         sets = [args] + [tuple(t.clone() for t in args) for _ in range(nsets - 1)]
@@ -174,14 +176,44 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None):
         t0 = _time.perf_counter()
         for _ in range(20):
             _tr.networks_resample(img1, flow1)
-        res["ops"]["gridsample_fwd_c1"]["cpu_reference_us"] = (_time.perf_counter() - t0) / 20 * 1e6
-        res["ops"]["gridsample_fwd_c1"]["cpu_threads"] = torch.get_num_threads()
+        if "gridsample_fwd_c1" in res["ops"]:
+            res["ops"]["gridsample_fwd_c1"]["cpu_reference_us"] = (_time.perf_counter() - t0) / 20 * 1e6
+            res["ops"]["gridsample_fwd_c1"]["cpu_threads"] = torch.get_num_threads()
     y = F.channelnorm_forward(img)
     gy = torch.randn_like(y)
     add("cnorm_fwd_c3", lambda x: F.channelnorm_forward(x), (img,),
         (lambda x: ref.channelnorm_forward(x)) if ref else None, alg_bytes=4 * plane)
     add("cnorm_bwd_c3", lambda x, y, gy: F.channelnorm_backward(x, y, gy), (img, y, gy),
         (lambda x, y, gy: ref.channelnorm_backward(x, y, gy)) if ref else None, alg_bytes=8 * plane)
+    # ---- 16-bit storage variants: same shapes, half the algorithmic bytes; "ref" is the chain the
+    # reference's fp16 mode runs on the same tensors (casts around its fp32 extension, or its at::Half kernels) ----
+    img16, gout16 = img.half(), gout.half()
+    y16 = F.channelnorm_forward(img16)
+    gy16 = gy.half()
+    add("cnorm_fwd_c3_f16", lambda x: F.channelnorm_forward(x), (img16,),
+        (lambda x: ref.channelnorm_forward(x)) if ref else None, alg_bytes=2 * plane)
+    add("cnorm_bwd_c3_f16", lambda x, y, g: F.channelnorm_backward(x, y, g), (img16, y16, gy16),
+        (lambda x, y, g: ref.channelnorm_backward(x, y, g)) if ref else None, alg_bytes=4 * plane)
+    for fl in ("smooth", "nearest"):
+        flow16 = flows[fl].half()
+        add("resample2d_fwd_%s_f16" % fl, lambda i, f: F.warp_forward(i, f, R2D), (img16, flow16),
+            (lambda i, f: ref.resample2d_forward(i.float(), f.float()).half()) if ref else None, alg_bytes=4 * plane)
+
+    def _chain16(i, f):      # models/base_model.py:123-136 with opt['fp16'], torch ops
+        b, c, h, w = i.shape
+        grid = torch.cat([torch.linspace(-1.0, 1.0, w, device=i.device).view(1, 1, 1, w).expand(b, 1, h, w),
+                          torch.linspace(-1.0, 1.0, h, device=i.device).view(1, 1, h, 1).expand(b, 1, h, w)], 1).to(f.dtype)
+        nf = torch.cat([f[:, 0:1] / ((w - 1.0) / 2.0), f[:, 1:2] / ((h - 1.0) / 2.0)], dim=1)
+        return torch.nn.functional.grid_sample(i.float(), (grid + nf).permute(0, 2, 3, 1).float(), mode="bilinear",
+                                               padding_mode="border", align_corners=False).half()
+    add("gridsample_fwd_smooth_f16", lambda i, f: F.warp_forward(i, f, GS), (img16, flows["smooth"].half()), _chain16,
+        alg_bytes=4 * plane)
+    del img16, gout16, y16, gy16
+    B, C, H, W = (2, 64, 24, 32) if small else (8, 256, 48, 64)
+    a16, b16 = torch.randn(B, C, H, W, device="cuda").half(), torch.randn(B, C, H, W, device="cuda").half()
+    add("corr_fwd_c2_f16", lambda a, b: F.correlation_forward(a, b, *P), (a16, b16),
+        (lambda a, b: ref.correlation_forward(a.float(), b.float(), *P).half()) if ref else None,
+        alg_flop=2.0 * B * H * W * 441 * C)
     return res
 
 
@@ -191,8 +223,9 @@ if __name__ == "__main__":
     ap.add_argument("--json", default=None)
     ap.add_argument("--skip-ref", action="store_true")
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--only", default=None, help="run only the rows whose name contains this substring")
     args = ap.parse_args()
-    out = run(args.iters, args.skip_ref, args.small)
+    out = run(args.iters, args.skip_ref, args.small, only=args.only)
     if args.json:
         os.makedirs(os.path.dirname(args.json) or ".", exist_ok=True)
         json.dump(out, open(args.json, "w"), indent=1)

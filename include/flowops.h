@@ -162,6 +162,18 @@ int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow,
 int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *flow, float div_flow, float *out, int c_dst,
                                        int B, int H, int W, void *stream);
 
+/* The input of the fusion network, models.py:129-152, in one pass, channels-last:
+ *   out[b,y,x, 0:11] = (frame 0, flow_sd, flow_s2, ChannelNorm(flow_sd), ChannelNorm(flow_s2),
+ *                       ChannelNorm(frame 0 - Resample2d(frame 1, flow_sd)), ChannelNorm(frame 0 - Resample2d(frame 1, flow_s2))),
+ *   out[b,y,x, 11:c_dst] = 0,
+ * with flow_s2 = nearest-x4(flow2_s2 * div_flow) (models.py:130) and flow_sd = nearest-x4(flow2_sd / div_flow)
+ * (models.py:143, the division reproduced as is, evaluated like ATen: a multiply by the fp32 reciprocal).
+ * x: [B,6,H,W] planar stack of both frames; flow2_s2, flow2_sd: [B,2,H/4,W/4], the quarter-resolution outputs of
+ * FlowNetS2 and FlowNetSD; out: [B,H,W,c_dst] (c_dst a multiple of 4, >= 12).  Same values as the two scalings, two
+ * nn.Upsample, two ChannelNorm, two Resample2d -> subtract -> ChannelNorm chains and the torch.cat, bit for bit. */
+int flowops_flownet2_fusion_input_nhwc(const float *x, const float *flow2_s2, const float *flow2_sd, float div_flow,
+                                       float *out, int c_dst, int B, int H, int W, void *stream);
+
 /* FlowNet2 input preparation (models.py:97-101): x = (inputs - rgb_mean) / rgb_max with the two frames stacked
  * along channels.  inputs: [B,3,2,H,W]; rgb_mean: [B,3] (the caller computes the mean).  Outputs, each optional:
  * x_planar [B,6,H,W]; channels-last copies padded with zero channels -- xa_nhwc4 / xb_nhwc4 [B,H,W,4] (frame 0 / 1,

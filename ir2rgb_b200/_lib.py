@@ -42,6 +42,7 @@ SIGNATURES = {
     "flowops_warp_diff_norm_fwd": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _int, _int, _int, _int, _vp]),
     "flowops_warp_conf_fwd": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
     "flowops_warp_diff_norm_concat_nhwc": (_int, [_vp, _vp, ctypes.c_float, _vp, _int, _int, _int, _int, _vp]),
+    "flowops_flownet2_fusion_input_nhwc": (_int, [_vp, _vp, _vp, ctypes.c_float, _vp, _int, _int, _int, _int, _vp]),
     "flowops_flownet2_prep": (_int, [_vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "flowops_bias_lrelu": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_bias_lrelu_nhwc_to": (_int, [_vp, _vp, _vp, _sz, _int, _int, _int, ctypes.c_float, _vp, _vp]),

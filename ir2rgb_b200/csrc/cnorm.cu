@@ -103,11 +103,18 @@ __global__ void __launch_bounds__(256) cnorm_bwd_v4(const float *__restrict__ x,
         const double d2 = (double)yo.z + 1e-9, d3 = (double)yo.w + 1e-9;
         const double r0 = recip_fast(d0), r1 = recip_fast(d1), r2 = recip_fast(d2), r3 = recip_fast(d3);
         const size_t base = (b * c_n * hw4 + p) * 4;
+        // compile-time channel counts: every load of the pixel group is in flight before the guard's branch (the kernel
+        // is bound by memory latency per thread: with the x loads behind the branch it runs 9 % slower)
+        float4 xv[CT > 0 ? CT : 1];
+        if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) xv[c] = ldg_stream4(x + base + (size_t)c * hw4 * 4);
+        }
         if (__builtin_expect(bwd_fast_ok(g.x, yo.x) && bwd_fast_ok(g.y, yo.y) && bwd_fast_ok(g.z, yo.z) && bwd_fast_ok(g.w, yo.w), 1)) {
 #pragma unroll 4
             for (int c = 0; c < c_n; ++c) {
                 const size_t off = base + (size_t)c * hw4 * 4;
-                const float4 v = ldg_stream4(x + off);
+                const float4 v = CT > 0 ? xv[CT > 0 ? c : 0] : ldg_stream4(x + off);
                 float4 o;
                 o.x = div_by_recip(__fmul_rn(g.x, v.x), d0, r0);
                 o.y = div_by_recip(__fmul_rn(g.y, v.y), d1, r1);
@@ -116,10 +123,10 @@ __global__ void __launch_bounds__(256) cnorm_bwd_v4(const float *__restrict__ x,
                 stg_stream4(gx + off, o);
             }
         } else {
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < c_n; ++c) {
                 const size_t off = base + (size_t)c * hw4 * 4;
-                const float4 v = ldg_stream4(x + off);
+                const float4 v = CT > 0 ? xv[CT > 0 ? c : 0] : ldg_stream4(x + off);
                 stg_stream4(gx + off, make_float4(div_literal(__fmul_rn(g.x, v.x), d0), div_literal(__fmul_rn(g.y, v.y), d1),
                                                   div_literal(__fmul_rn(g.z, v.z), d2), div_literal(__fmul_rn(g.w, v.w), d3)));
             }
@@ -223,25 +230,30 @@ __global__ void __launch_bounds__(256) cnorm16_bwd_v8(const uint4 *__restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) { d[k] = (double)yo[k] + 1e-9; r[k] = recip_fast(d[k]); }
         const size_t base = b * c_n * hw8 + p;
+        uint4 xv[CT > 0 ? CT : 1];                 // as in cnorm_bwd_v4: loads in flight before the guard's branch
+        if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) xv[c] = ldg_stream_u4(x + base + (size_t)c * hw8);
+        }
         bool fast = true;
 #pragma unroll
         for (int k = 0; k < 8; ++k) fast = fast && bwd_fast_ok(g[k], yo[k]);
         if (__builtin_expect(fast, 1)) {
-#pragma unroll 2
+#pragma unroll(CT > 0 ? CT : 2)
             for (int c = 0; c < c_n; ++c) {
                 const size_t off = base + (size_t)c * hw8;
                 float v[8], o[8];
-                unpack8<T>(ldg_stream_u4(x + off), v);
+                unpack8<T>(CT > 0 ? xv[CT > 0 ? c : 0] : ldg_stream_u4(x + off), v);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] = div_by_recip(__fmul_rn(g[k], v[k]), d[k], r[k]);
                 stg_stream_u4(gx + off, pack8<T>(o));
             }
         } else {
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < c_n; ++c) {
                 const size_t off = base + (size_t)c * hw8;
                 float v[8], o[8];
-                unpack8<T>(ldg_stream_u4(x + off), v);
+                unpack8<T>(CT > 0 ? xv[CT > 0 ? c : 0] : ldg_stream_u4(x + off), v);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] = div_literal(__fmul_rn(g[k], v[k]), d[k]);
                 stg_stream_u4(gx + off, pack8<T>(o));

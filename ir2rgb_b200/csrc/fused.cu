@@ -199,6 +199,104 @@ extern "C" int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *f
 }
 
 // ---------------------------------------------------------------------------------------------
+// Input of the fusion network (models.py:129-152), one pass, channels-last:
+//   flow_s2 = upsample4(flow2_s2 * div_flow)      flow_sd = upsample3(flow2_sd / div_flow)        (nearest, x4)
+//   concat3 = (frame 0, flow_sd, flow_s2, ChannelNorm(flow_sd), ChannelNorm(flow_s2),
+//              ChannelNorm(frame 0 - Resample2d(frame 1, flow_sd)), ChannelNorm(frame 0 - Resample2d(frame 1, flow_s2)))
+// The reference runs 2 scalings, 2 upsamplings, 2 ChannelNorms, 2 Resample2d + subtract + ChannelNorm chains and a
+// torch.cat, and cuDNN then converts the 11-channel NCHW result to padded NHWC; here a thread walks `rows` rows of one
+// column, reads the two quarter-resolution flows (L1/L2-resident), gathers frame 1 twice and writes the pixel's 11
+// values plus zero padding as float4s.  Same arithmetic, operation for operation (pix_prep / pix_blend of
+// warp_rows.cuh; FFMA chain + IEEE sqrt of cnorm.cu), so the values equal the operator chain bit for bit.
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+struct FusionInputArgs {
+    WarpArgs g;                          // geometry (B, H, W, rows, wm1, hm1); tensor pointers unused
+    const float *x;                      // [B,6,H,W] planar frame stack
+    const float *lo_s2, *lo_sd;          // [B,2,H/4,W/4] flow2 outputs of FlowNetS2 / FlowNetSD (network units)
+    float mul_s2, mul_sd;                // div_flow and the fp32 reciprocal of div_flow (models.py:130,143)
+    float *out;                          // [B,H,W,c_dst]
+    int c_dst;
+};
+
+__global__ void __launch_bounds__(256, 3) fusion_input_kernel(const __grid_constant__ FusionInputArgs a)
+{
+    const WarpArgs &g = a.g;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * g.rows;
+    if (x >= g.W || y0 >= g.H) return;
+    const int y1 = min(y0 + g.rows, g.H);
+    const unsigned hw = (unsigned)g.H * g.W, W = (unsigned)g.W;
+    const unsigned Wl = W >> 2, hwl = (unsigned)(g.H >> 2) * Wl;
+    const size_t b = blockIdx.z;
+    const float *frame0 = a.x + b * 6 * hw;
+    const float *src = frame0 + 3 * (size_t)hw;                       // frame 1: the gather source
+    asm("" : "+l"(src));
+    const float *ls2 = a.lo_s2 + b * 2 * hwl + (unsigned)(x >> 2);
+    const float *lsd = a.lo_sd + b * 2 * hwl + (unsigned)(x >> 2);
+    const float xfl = small_int_as_float(x);
+    for (int y = y0; y < y1; ++y) {
+        const unsigned p = (unsigned)y * W + (unsigned)x, pl = (unsigned)(y >> 2) * Wl;
+        // nearest x4 upsampling: source index floor(dst * 0.25) (ATen upsample_nearest2d with scale_factor 4)
+        const float s2x = __fmul_rn(__ldg(ls2 + pl), a.mul_s2), s2y = __fmul_rn(__ldg(ls2 + pl + hwl), a.mul_s2);
+        const float sdx = __fmul_rn(__ldg(lsd + pl), a.mul_sd), sdy = __fmul_rn(__ldg(lsd + pl + hwl), a.mul_sd);
+        const float yfl = small_int_as_float(y);
+        PixPrep<FLOWOPS_WARP_RESAMPLE2D> qd, q2;
+        pix_prep(qd, g, xfl, yfl, x, y, sdx, sdy);
+        pix_prep(q2, g, xfl, yfl, x, y, s2x, s2y);
+        PixVals<3> vd, v2;
+        pix_gather<3, true, false>(vd, qd, src, frame0 + p, nullptr, hw);      // also loads frame 0 at this pixel (vd.r)
+        pix_gather<3, false, false>(v2, q2, src, nullptr, nullptr, hw);
+        float ed = 0.f, e2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float dd = __fsub_rn(vd.r[c], pix_blend(qd, vd.v[c]));       // models.py:110
+            const float d2 = __fsub_rn(vd.r[c], pix_blend(q2, v2.v[c]));
+            ed = __fmaf_rn(dd, dd, ed);                                        // channelnorm_kernel.cu:55-56
+            e2 = __fmaf_rn(d2, d2, e2);
+        }
+        const float nd = __fsqrt_rn(__fmaf_rn(sdy, sdy, __fmaf_rn(sdx, sdx, 0.f)));
+        const float n2 = __fsqrt_rn(__fmaf_rn(s2y, s2y, __fmaf_rn(s2x, s2x, 0.f)));
+        float4 *dst = reinterpret_cast<float4 *>(a.out + (b * hw + p) * (size_t)a.c_dst);
+        dst[0] = make_float4(vd.r[0], vd.r[1], vd.r[2], sdx);
+        dst[1] = make_float4(sdy, s2x, s2y, nd);
+        dst[2] = make_float4(n2, __fsqrt_rn(ed), __fsqrt_rn(e2), 0.f);
+        for (int q4 = 3; q4 < a.c_dst / 4; ++q4) dst[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_flownet2_fusion_input_nhwc(const float *x, const float *flow2_s2, const float *flow2_sd, float div_flow,
+                                                  float *out, int c_dst, int B, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(x && flow2_s2 && flow2_sd && out, FLOWOPS_EINVAL, "flownet2_fusion_input_nhwc: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 3) == 0 && (W & 3) == 0, FLOWOPS_EINVAL,
+                    "flownet2_fusion_input_nhwc: bad shape %dx%dx%d (H and W must be multiples of 4)", B, H, W);
+    FLOWOPS_REQUIRE(c_dst >= 12 && (c_dst & 3) == 0 && aligned16(out), FLOWOPS_EINVAL,
+                    "flownet2_fusion_input_nhwc: c_dst must be a multiple of 4 and at least 12, out 16-byte aligned");
+    FLOWOPS_REQUIRE((size_t)6 * H * W < (1ull << 31) && H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED,
+                    "flownet2_fusion_input_nhwc: frame too large for int32 indexing");
+    FusionInputArgs a{};
+    a.x = x; a.lo_s2 = flow2_s2; a.lo_sd = flow2_sd; a.mul_s2 = div_flow; a.mul_sd = 1.0f / div_flow;
+    a.out = out; a.c_dst = c_dst;
+    a.g.B = B; a.g.C = 3; a.g.H = H; a.g.W = W; a.g.rows = warp_rows_pick(B, H, W);
+    a.g.wm1 = (float)(W - 1); a.g.hm1 = (float)(H - 1);
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        FusionInputArgs c = a;
+        c.g.B = B - b0 < 65535 ? B - b0 : 65535;
+        c.x = x + (size_t)b0 * 6 * hw; c.out = out + (size_t)b0 * hw * c_dst;
+        c.lo_s2 = flow2_s2 + (size_t)b0 * 2 * (hw / 16); c.lo_sd = flow2_sd + (size_t)b0 * 2 * (hw / 16);
+        dim3 grid, block;
+        warp_rows_shape(c.g.B, H, W, c.g.rows, grid, block);
+        fusion_input_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(c);
+    }
+    return check_launch("flownet2_fusion_input_nhwc");
+}
+
+// ---------------------------------------------------------------------------------------------
 // FlowNet2 input preparation (models.py:97-101): x = (inputs - rgb_mean) / rgb_max, frames stacked along
 // channels -- written once in every layout its consumers want: planar [B,6,H,W] for the warp kernels, and
 // channels-last copies padded to 4 / 4 / 8 channels for the first convolutions of FlowNetC (per frame) and

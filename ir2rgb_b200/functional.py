@@ -206,6 +206,26 @@ def warp_diff_norm_concat(x, flow, div_flow, c_pad=16):
     return out
 
 
+def flownet2_fusion_input(x, flow2_s2, flow2_sd, div_flow, c_pad=16):
+    """concat3 of models.py:129-152 in one pass: a channels_last [B, c_pad, H, W] tensor whose first 11 channels are
+    (frame 0, flow_sd, flow_s2, |flow_sd|, |flow_s2|, warp error under flow_sd, warp error under flow_s2), the rest zero.
+    x: [B,6,H,W] planar; flow2_s2 / flow2_sd: the quarter-resolution outputs of FlowNetS2 / FlowNetSD in network units
+    (the scaling by div_flow and the nearest x4 upsampling happen inside)."""
+    x = _require(x, "x").contiguous()
+    flow2_s2 = _require(flow2_s2, "flow2_s2").contiguous()
+    flow2_sd = _require(flow2_sd, "flow2_sd").contiguous()
+    B, C6, H, W = x.shape
+    if C6 != 6 or H % 4 or W % 4 or tuple(flow2_s2.shape) != (B, 2, H // 4, W // 4) or flow2_sd.shape != flow2_s2.shape:
+        raise ValueError("expected x [B,6,H,W] with H, W multiples of 4 and two [B,2,H/4,W/4] flows, got %s, %s, %s"
+                         % (tuple(x.shape), tuple(flow2_s2.shape), tuple(flow2_sd.shape)))
+    with torch.cuda.device_of(x):
+        out = torch.empty((B, c_pad, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if x.numel():
+            check(_lib.load().flowops_flownet2_fusion_input_nhwc(_p(x), _p(flow2_s2), _p(flow2_sd), ctypes.c_float(div_flow), _p(out),
+                                                                 c_pad, B, H, W, _stream()), "flownet2_fusion_input_nhwc")
+    return out
+
+
 def flownet2_prep(inputs, rgb_mean, rgb_max):
     """x = (inputs - rgb_mean) / rgb_max for inputs [B,3,2,H,W] (models.py:97-101), in the four layouts its consumers
     read: (x planar [B,6,H,W], frame 0 and frame 1 as channels_last [B,4,H,W], both frames as channels_last [B,8,H,W]);

@@ -20,6 +20,7 @@ from ... import functional as _F
 from .networks import FlowNetC, FlowNetFusion, FlowNetS, FlowNetSD
 from .networks.channelnorm_package.channelnorm import ChannelNorm
 from .networks.resample2d_package.resample2d import Resample2d
+from .networks import submodules as _sm
 from .networks.submodules import reference_init
 
 'Parameter count = 162,518,834'
@@ -57,6 +58,7 @@ class FlowNet2(nn.Module):
         self.rgb_max = args.rgb_max
         self.args = args
         self.fuse_glue = True          # use the fused warp/diff/norm kernel when autograd is off
+        self.fuse_fusion_input = True  # channels_last body: concat3 (models.py:129-152) from one kernel
 
         self.channelnorm = ChannelNorm()
         self.flownetc = FlowNetC.FlowNetC(args, batchNorm=self.batchNorm)
@@ -96,11 +98,17 @@ class FlowNet2(nn.Module):
         concat1 = _F.warp_diff_norm_concat(x, flownetc_flow, self.div_flow)
         flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
         concat2 = _F.warp_diff_norm_concat(x, flownets1_flow, self.div_flow)
-        flownets2_flow = self.upsample4(self.flownets_2(concat2)[0] * self.div_flow)
+        flow2_s2 = self.flownets_2(concat2)[0]
+        flow2_sd = self.flownets_d(x8)[0]
+        if self.fuse_fusion_input and _sm.PAD_CHANNELS > 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
+            # scalings, nearest upsamplings, both ChannelNorms, both warp-error chains and the concat of models.py:129-152
+            # as one kernel writing the 16-channel channels-last tensor conv0 of the fusion network reads
+            return self.flownetfusion(_F.flownet2_fusion_input(x, flow2_s2, flow2_sd, self.div_flow))
+        flownets2_flow = self.upsample4(flow2_s2 * self.div_flow)
         norm_flownets2_flow = self.channelnorm(flownets2_flow)
         _, diff_flownets2_img1 = self.warp_error(x, flownets2_flow)
 
-        flownetsd_flow = self.upsample3(self.flownets_d(x8)[0] / self.div_flow)
+        flownetsd_flow = self.upsample3(flow2_sd / self.div_flow)
         norm_flownetsd_flow = self.channelnorm(flownetsd_flow)
         _, diff_flownetsd_img1 = self.warp_error(x, flownetsd_flow)
 

@@ -125,6 +125,62 @@ def test_input_prep_and_concat_assembly_are_bit_identical(nets):
     assert torch.equal(cat[:, :12], want) and (cat[:, 12:] == 0).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 128, 320), (3, 8, 12)])
+def test_fusion_input_is_bit_identical_to_operator_chain(nets, shape):
+    """flowops_flownet2_fusion_input_nhwc against models.py:129-152 spelled out with the separate operators."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm
+    torch.manual_seed(18)
+    B, H, W = shape
+    x = (2 * torch.rand(B, 6, H, W, device="cuda") - 1).contiguous()
+    lo_s2 = 0.3 * torch.randn(B, 2, H // 4, W // 4, device="cuda")          # network units: * div_flow -> pixels
+    lo_sd = 60.0 * torch.randn(B, 2, H // 4, W // 4, device="cuda")         # / div_flow -> pixels
+    lo_s2[0, :, 0, 0] = 0.0
+    lo_sd[0, 0, 0, 1] = 1e4                                                 # far outside the frame: clamped corners
+    up = torch.nn.Upsample(scale_factor=4, mode='nearest')
+    flow_s2, flow_sd = up(lo_s2 * 20.0), up(lo_sd / 20.0)
+    _, diff_s2 = F.warp_diff_norm_forward(x, flow_s2)
+    _, diff_sd = F.warp_diff_norm_forward(x, flow_sd)
+    want = torch.cat((x[:, :3], flow_sd, flow_s2, ChannelNorm()(flow_sd), ChannelNorm()(flow_s2), diff_sd, diff_s2), dim=1)
+    got = F.flownet2_fusion_input(x, lo_s2, lo_sd, 20.0)
+    assert got.shape == (B, 16, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got[:, :11], want) and (got[:, 11:] == 0).all()
+    got12 = F.flownet2_fusion_input(x, lo_s2, lo_sd, 20.0, c_pad=12)
+    assert torch.equal(got12[:, :11], want) and (got12[:, 11:] == 0).all()
+    with pytest.raises(ValueError):
+        F.flownet2_fusion_input(x, lo_s2[:, :, :-1], lo_sd, 20.0)
+
+
+def test_fused_fusion_input_does_not_change_the_network_output(flowops_lib):
+    """channels_last FlowNet2 with and without the one-pass concat3: same flow up to cuDNN's summation order on the
+    padded channel count of the fusion network's first convolution."""
+    from ir2rgb_b200.models.flownet import FlowNet
+    torch.manual_seed(19)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, True, False
+    try:
+        net = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[0], checkpoints_dir=".", name="t").eval()
+        net.flowNet = net.flowNet.to(memory_format=torch.channels_last)
+        a = 2 * torch.rand(2, 3, 128, 192, device="cuda") - 1
+        b = (a + 0.05 * torch.randn_like(a)).clamp(-1, 1)
+        from ir2rgb_b200 import _lib
+        calls = []
+        prev_hook = _lib.launch_hook
+        _lib.launch_hook = lambda what, n: calls.append(what)
+        try:
+            flow_fused, conf_fused = net(a, b)
+        finally:
+            _lib.launch_hook = prev_hook
+        assert "flownet2_fusion_input_nhwc" in calls
+        net.flowNet.fuse_fusion_input = False
+        flow_plain, conf_plain = net(a, b)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = prev
+    rel = ((flow_fused - flow_plain).abs().max() / flow_plain.abs().max()).item()
+    assert rel <= 1e-4, rel
+    assert (conf_fused != conf_plain).float().mean().item() <= 1e-3
+
+
 def test_flownet_wrapper_shapes_and_resize_path(nets):
     # 5-D input (b, n, c, h, w) and a height that is not a multiple of 64 (flownet.py:27-33,41-47,51-53)
     a = 2 * torch.rand(1, 2, 3, 96, 128, device="cuda") - 1

@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from .... import functional as _F
 from . import submodules as _sm
-from .submodules import add_layers, apply_conv, deconv, flow_upsampler, i_conv, predict_flow, reference_init
+from .submodules import Skip, add_layers, apply_conv, deconv, flow_upsampler, i_conv, predict_flow, reference_init
 
 ENCODER = [("conv0", 11, 64, 3, 1), ("conv1", 64, 64, 3, 2), ("conv1_1", 64, 128, 3, 1), ("conv2", 128, 128, 3, 2),
            ("conv2_1", 128, 128, 3, 1)]
@@ -21,13 +21,24 @@ class FlowNetFusion(nn.Module):
         self.upsampled_flow2_to_1, self.upsampled_flow1_to_0 = flow_upsampler(), flow_upsampler()
         reference_init(self)
 
+    def _concat(self, sk, skip, deconv_lv, feat, up):
+        """torch.cat((skip, deconv(feat), up), 1) (FlowNetFusion.py:54,60).  Inference on a channels_last body: the encoder
+        layer already wrote `skip` into the level's concat buffer (sk.buf, channels rounded up to a multiple of 8:
+        162 -> 168, 82 -> 88), the deconvolution's epilogue writes its slice, only the 2-channel flow is copied."""
+        if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _F._cat_fast((skip, up)):
+            off = skip.shape[1]
+            deconv_lv(feat, into=(sk.buf, off))
+            sk.buf.copy_in(up, off + deconv_lv[0].out_channels)
+            return sk.buf.tensor
+        return _F.cat_channels((skip, apply_conv(deconv_lv, feat), up), pad_to=_sm.PAD_CHANNELS)
+
     def forward(self, x):
-        c0 = self.conv0(x)
-        c1 = self.conv1_1(self.conv1(c0))
+        sk0, sk1 = Skip(self, 0), Skip(self, 1)
+        c0 = self.conv0(x, skip=sk0)
+        c1 = self.conv1_1(self.conv1(c0), skip=sk1)
         c2 = self.conv2_1(self.conv2(c1))
-        flow2 = self.predict_flow2(c2)
-        # inference: the concat buffers carry zero pad channels up to a multiple of 8 (162 -> 168, 82 -> 88)
-        cat1 = _F.cat_channels((c1, self.deconv1(c2), self.upsampled_flow2_to_1(flow2)), pad_to=_sm.PAD_CHANNELS)
-        flow1 = self.predict_flow1(apply_conv(self.inter_conv1, cat1))
-        cat0 = _F.cat_channels((c0, apply_conv(self.deconv0, cat1), self.upsampled_flow1_to_0(flow1)), pad_to=_sm.PAD_CHANNELS)
-        return self.predict_flow0(apply_conv(self.inter_conv0, cat0))
+        flow2 = apply_conv(self.predict_flow2, c2)
+        cat1 = self._concat(sk1, c1, self.deconv1, c2, apply_conv(self.upsampled_flow2_to_1, flow2))
+        flow1 = apply_conv(self.predict_flow1, apply_conv(self.inter_conv1, cat1))
+        cat0 = self._concat(sk0, c0, self.deconv0, cat1, apply_conv(self.upsampled_flow1_to_0, flow1))
+        return apply_conv(self.predict_flow0, apply_conv(self.inter_conv0, cat0))

@@ -53,9 +53,20 @@ def apply_conv(mod, x):
         return mod(x)
     conv = mod[0] if isinstance(mod, nn.Sequential) else mod
     cin = conv.weight.shape[0 if isinstance(conv, nn.ConvTranspose2d) else 1] * conv.groups
-    if x.shape[1] == cin:
+    if (FUSE_EPILOGUE and conv.bias is not None and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+            and isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d))):
+        # a bare convolution with bias (the 2-channel flow heads, the flow upsamplers, inter_conv): ATen adds the bias
+        # with a generic strided elementwise kernel after cuDNN's bias-free convolution; the library's epilogue with
+        # slope 1 (t > 0 ? t : t * 1 == t) is the same add, bit for bit, in one vectorised pass
+        y = _raw_conv(conv, x, None)
+        if y.is_contiguous() or _F._is_nhwc(y):
+            _F.bias_lrelu_(y, conv.bias, 1.0)
+        else:
+            y += conv.bias.view(1, -1, 1, 1)
+    elif x.shape[1] == cin:
         return mod(x)
-    y = _raw_conv(conv, x, conv.bias)
+    else:
+        y = _raw_conv(conv, x, conv.bias)
     if isinstance(mod, nn.Sequential):
         for layer in list(mod)[1:]:
             y = layer(y)
@@ -172,7 +183,7 @@ def refine(net, skips, top, levels, inter=False, skip_bufs=None):
     feat = top
     flows = [apply_conv(getattr(net, "predict_flow%d" % (levels[0] + 1)), top)]
     for lv in levels:
-        up = getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv))(flows[0])
+        up = apply_conv(getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv)), flows[0])
         deconv_lv = getattr(net, "deconv%d" % lv)
         skip = skips[lv]
         if deconv_lv.fusable(feat) and _F._cat_fast((skip, up)) and _F._is_nhwc(feat):

@@ -54,7 +54,7 @@ def apply_conv(mod, x):
     conv = mod[0] if isinstance(mod, nn.Sequential) else mod
     cin = conv.weight.shape[0 if isinstance(conv, nn.ConvTranspose2d) else 1] * conv.groups
     if (FUSE_EPILOGUE and conv.bias is not None and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
-            and isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d))):
+            and isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)) and not conv.__dict__.get("_flowops_stock", False)):
         # a bare convolution with bias (the 2-channel flow heads, the flow upsamplers, inter_conv): ATen adds the bias
         # with a generic strided elementwise kernel after cuDNN's bias-free convolution; the library's epilogue with
         # slope 1 (t > 0 ? t : t * 1 == t) is the same add, bit for bit, in one vectorised pass

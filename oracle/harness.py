@@ -61,6 +61,8 @@ def swap_ops(flownet2, kind):
     for m in flownet2.modules():
         if type(m).__name__ == "ConvAct":
             m.fusable = lambda x: False
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            m.__dict__["_flowops_stock"] = True          # submodules.apply_conv: bias stays inside the torch convolution
     return flownet2
 
 

@@ -209,3 +209,80 @@ def test_glue_kernels_stay_in_bounds(lib, B, H, W):
     d = dst.view(B * hw, c_dst)
     assert torch.all(d[:, :c_off] == SENT) and torch.all(d[:, c_off + C:35] == SENT) and torch.all(d[:, 35:] == 0)
     assert torch.equal(d[:, c_off:c_off + C], y)              # `also` aliased y: y now holds the activated values too
+
+
+# ---- 16-bit storage entry points and the fusion-network input: sentinel guard bands in the storage type ----
+SENT16 = 12345.0          # representable in fp16 and bf16
+
+
+def guarded16(numel, dt):
+    buf = torch.full((numel + 2 * GUARD,), SENT16, device="cuda", dtype=dt)
+    return buf, buf[GUARD:GUARD + numel]
+
+
+def check16(buf, numel, name):
+    assert torch.all(buf[:GUARD] == SENT16), name + ": wrote before the buffer"
+    assert torch.all(buf[GUARD + numel:] == SENT16), name + ": wrote past the buffer"
+    assert not torch.any(buf[GUARD:GUARD + numel] == SENT16), name + ": left part of the output unwritten"
+
+
+@pytest.mark.parametrize("dt,code", [(torch.float16, 1), (torch.bfloat16, 2)])
+@pytest.mark.parametrize("shape", [(2, 3, 17, 23), (1, 2, 8, 16), (1, 1, 5, 7), (3, 3, 33, 40)])
+def test_16bit_entry_points_stay_in_bounds(lib, dt, code, shape):
+    B, C, H, W = shape
+    torch.manual_seed(1)
+    x = torch.randn(shape, device="cuda").to(dt)
+    flow = (3 * torch.randn(B, 2, H, W, device="cuda")).to(dt)
+    ybuf, y = guarded16(B * H * W, dt)
+    assert lib.flowops_cnorm_fwd_16(p(x), p(y), B, C, H, W, code, None) == 0, lib.flowops_last_error()
+    gy = torch.randn(B, 1, H, W, device="cuda").to(dt)
+    gbuf, gx = guarded16(x.numel(), dt)
+    assert lib.flowops_cnorm_bwd_16(p(x), p(y), p(gy), p(gx), B, C, H, W, code, None) == 0, lib.flowops_last_error()
+    lx = torch.linspace(-1, 1, W).to(dt).float().cuda()
+    ly = torch.linspace(-1, 1, H).to(dt).float().cuda()
+    for mode in (0, 1):
+        obuf, out = guarded16(x.numel(), dt)
+        assert lib.flowops_warp_fwd_16(p(x), p(flow), p(out), B, C, H, W, mode, p(lx), p(ly), code, None) == 0, lib.flowops_last_error()
+        torch.cuda.synchronize()
+        check16(obuf, x.numel(), "warp_fwd_16 mode %d" % mode)
+    torch.cuda.synchronize()
+    check16(ybuf, B * H * W, "cnorm_fwd_16")
+    check16(gbuf, x.numel(), "cnorm_bwd_16")
+
+
+@pytest.mark.parametrize("dt,code", [(torch.float16, 1), (torch.bfloat16, 2)])
+@pytest.mark.parametrize("shape", [(2, 16, 8, 12), (1, 5, 7, 9), (1, 40, 6, 70)])
+def test_correlation_16bit_stays_in_bounds(lib, dt, code, shape):
+    B, C, H, W = shape
+    torch.manual_seed(2)
+    a, b = torch.randn(shape, device="cuda").to(dt), torch.randn(shape, device="cuda").to(dt)
+    P = (20, 1, 20, 1, 2)
+    n_out = B * 441 * H * W
+    obuf, out = guarded16(n_out, dt)
+    ws_bytes = lib.flowops_corr_fwd_workspace_bytes(B, C, H, W, *P)
+    wbuf, ws = guarded((ws_bytes + 3) // 4 + 64)
+    ws = ws[(-ws.data_ptr()) % 256 // 4:]
+    rc = lib.flowops_corr_fwd_16(p(a), p(b), p(out), B, C, H, W, *P, code, p(ws), ws_bytes, None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    check16(obuf, n_out, "corr_fwd_16 out")
+    check(wbuf, (ws_bytes + 3) // 4 + 64, "corr_fwd_16 workspace", must_fill=False)
+    assert lib.flowops_corr_fwd_16(p(a), p(b), p(out), B, C, H, W, 4, 1, 4, 1, 1, code, None, 0, None) == -2     # FlowNetC configuration only
+
+
+@pytest.mark.parametrize("B,H,W,c_dst", [(2, 8, 12, 16), (1, 36, 52, 12), (3, 4, 4, 16)])
+def test_fusion_input_stays_in_bounds(lib, B, H, W, c_dst):
+    torch.manual_seed(3)
+    x = torch.randn(B, 6, H, W, device="cuda")
+    lo1, lo2 = torch.randn(B, 2, H // 4, W // 4, device="cuda"), 50 * torch.randn(B, 2, H // 4, W // 4, device="cuda")
+    n = B * H * W * c_dst
+    obuf, out = guarded(n)
+    off = (-out.data_ptr()) % 16 // 4
+    assert off == 0, "guard size keeps the window 16-byte aligned"
+    rc = lib.flowops_flownet2_fusion_input_nhwc(p(x), p(lo1), p(lo2), ctypes.c_float(20.0), p(out), c_dst, B, H, W, None)
+    assert rc == 0, lib.flowops_last_error()
+    torch.cuda.synchronize()
+    check(obuf, n, "flownet2_fusion_input_nhwc", must_fill=False)
+    v = out.view(B, H, W, c_dst)
+    assert not torch.any(v[..., :11] == SENT) and torch.all(v[..., 11:] == 0)
+    assert lib.flowops_flownet2_fusion_input_nhwc(p(x), p(lo1), p(lo2), ctypes.c_float(20.0), p(out), c_dst, B, H + 1, W, None) == -1

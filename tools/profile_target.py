@@ -1,5 +1,5 @@
 """Tiny launcher for ncu: runs ONE operator a few times at its BASELINE config.
-    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_fwd_c4b16|corr_fwd_nhwc_b16|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused> [reps]
+    python tools/profile_target.py <corr_fwd|corr_fwd_c4|corr_fwd_c4b16|corr_fwd_nhwc_b16|corr_bwd|warp_fwd|warp_bwd|cnorm_fwd|cnorm_bwd|fused|fusion_input|cnorm_fwd_f16|cnorm_bwd_f16|warp_fwd_f16> [reps]
 """
 import os
 import sys
@@ -48,6 +48,22 @@ else:
         y = F.channelnorm_forward(img)
         gy = torch.randn_like(y)
         fn = lambda: F.channelnorm_backward(img, y, gy)
+    elif op == "fusion_input":       # concat3 of the FlowNet2 step, one micro-batch of 16 pairs
+        x = torch.cat([img, img.flip(0)], 1).contiguous()
+        lo_s2 = flow[:, :, ::4, ::4].contiguous() / 20.0
+        lo_sd = flow[:, :, ::4, ::4].flip(0).contiguous() * 20.0
+        fn = lambda: F.flownet2_fusion_input(x, lo_s2, lo_sd, 20.0)
+    elif op == "cnorm_fwd_f16":
+        img16 = img.half()
+        fn = lambda: F.channelnorm_forward(img16)
+    elif op == "cnorm_bwd_f16":
+        img16 = img.half()
+        y16 = F.channelnorm_forward(img16)
+        gy16 = torch.randn_like(y16)
+        fn = lambda: F.channelnorm_backward(img16, y16, gy16)
+    elif op == "warp_fwd_f16":
+        img16, flow16 = img.half(), flow.half()
+        fn = lambda: F.warp_forward(img16, flow16, F.WARP_RESAMPLE2D)
     elif op == "fused":
         x = torch.cat([img, img.flip(0)], 1).contiguous()
         fn = lambda: F.warp_diff_norm_forward(x, flow)

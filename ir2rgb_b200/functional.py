@@ -32,7 +32,7 @@ def _require(t, name, ndim=4, dtype=torch.float32):
     return t
 
 
-def _io_dtype(t, name):
+def _io_dtype(t):
     """fp32, or one of the 16-bit storage types the *_16 entry points take."""
     if isinstance(t, torch.Tensor) and t.dtype in _DTYPE16:
         return t.dtype
@@ -56,7 +56,7 @@ def _stream():
 # ---------------------------------------------------------------------------------------------
 def channelnorm_forward(x):
     """fp32, or fp16 / bf16: the reference kernel as instantiated for at::Half (channelnorm_kernel.cu:111)."""
-    dt = _io_dtype(x, "input1")
+    dt = _io_dtype(x)
     x = _require(x, "input1", dtype=dt).contiguous()
     B, C, H, W = x.shape
     with torch.cuda.device_of(x):
@@ -70,7 +70,7 @@ def channelnorm_forward(x):
 
 
 def channelnorm_backward(x, y, gy):
-    dt = _io_dtype(x, "input1")
+    dt = _io_dtype(x)
     x = _require(x, "input1", dtype=dt).contiguous()
     y = _require(y, "output", dtype=dt).contiguous()
     gy = _require(gy, "grad_output", dtype=dt).contiguous()
@@ -125,7 +125,7 @@ def warp_forward(img, flow, mode=WARP_RESAMPLE2D):
     """fp32 tensors, or image and flow both fp16 / both bf16 (1..3 channels): then one kernel does what the reference's
     fp16 mode spreads over casts -- fp16_resample2d (models.py:22-28) for RESAMPLE2D, Model.resample with opt['fp16']
     (base_model.py:123-136) for GRIDSAMPLE."""
-    dt = _io_dtype(img, "image")
+    dt = _io_dtype(img)
     img, flow, B, C, H, W, lx, ly = _warp_args(img, flow, mode, dt)
     with torch.cuda.device_of(img):
         out = torch.empty_like(img)
@@ -362,7 +362,7 @@ def correlation_has_16bit_path(in1, pad_size, kernel_size, max_displacement, str
 def correlation_forward(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
     """fp32 tensors, or both fp16 / both bf16 in the FlowNetC configuration: `corr(a.float(), b.float()).half()`
     (FlowNetC.py:86-87) as one operator call."""
-    dt = _io_dtype(in1, "input1")
+    dt = _io_dtype(in1)
     in1, in2 = _require(in1, "input1", dtype=dt), _require(in2, "input2", dtype=dt)
     if in1.shape != in2.shape or in1.device != in2.device:
         raise ValueError("input1 %s and input2 %s must have the same shape and device" % (tuple(in1.shape), tuple(in2.shape)))

@@ -97,3 +97,42 @@ def test_flownet_resample_resolves_to_the_method_like_the_reference():
     p = Probe()
     assert isinstance(p._modules["resample"], torch.nn.Identity)
     assert getattr(p.resample, "__func__", None) is Model.resample
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_16bit_tensors_have_no_cpu_fallback_either(dt):
+    """fp16 / bf16 tensors select the *_16 entry points; off-GPU they fail as loudly as fp32 ones."""
+    from ir2rgb_b200 import functional as F
+    for call in (lambda: F.channelnorm_forward(torch.zeros(1, 3, 4, 4, dtype=dt)),
+                 lambda: F.warp_forward(torch.zeros(1, 3, 4, 4, dtype=dt), torch.zeros(1, 2, 4, 4, dtype=dt)),
+                 lambda: F.correlation_forward(torch.zeros(1, 4, 8, 8, dtype=dt), torch.zeros(1, 4, 8, 8, dtype=dt), 20, 1, 20, 1, 2)):
+        with pytest.raises(RuntimeError, match="no CPU implementation"):
+            call()
+
+
+def test_fp16_modules_keep_the_reference_layout():
+    """models.py:22-28,63: FlowNet2(fp16=True) swaps in fp16_resample2d, which wraps a Resample2d submodule named
+    `resample`; neither holds parameters, so reference checkpoints load unchanged in fp16 mode too."""
+    from ir2rgb_b200.models.flownet2_pytorch import models as fn2
+    m = fn2.fp16_resample2d()
+    assert isinstance(m.resample, Resample2d) and list(m.state_dict().keys()) == []
+    assert defaults(fn2.fp16_resample2d.forward) == [("input1", inspect._empty), ("input2", inspect._empty)]
+    assert defaults(fn2.FlowNet2.__init__) == [("args", None), ("batchNorm", False), ("div_flow", 20.), ("fp16", False)]
+
+
+def test_model_resample_fp16_option_leaves_other_dtypes_alone(monkeypatch):
+    """Model.resample takes the one-pass 16-bit kernel only for fp16 tensors under opt['fp16'] (base_model.py:123-136);
+    everything else goes where it went before."""
+    from ir2rgb_b200.models import base_model
+    seen = []
+    monkeypatch.setattr(base_model.networks, "resample", lambda image, flow: seen.append((image.dtype, flow.dtype)) or image)
+
+    class M(base_model.Model):
+        def save(self, label):
+            pass
+    m = M(fp16=True, gpu_ids=[], checkpoints_dir=".", name="t")
+    img, flow = torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)
+    m.resample(img, flow)                       # fp32 under the fp16 option
+    m.resample(img.half(), flow.half())         # fp16 but on the CPU: not the kernel's business
+    m.resample(img.bfloat16(), flow.bfloat16())
+    assert seen == [(torch.float32, torch.float32), (torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)]

@@ -148,3 +148,15 @@ def gridwarp_fwd_16(img, flow, lin_x, lin_y, dtype, inv_mode=1, fma_mode=1):
     lib().oracle_gridwarp_fwd_16(_p(img), _p(flow), _p(out), _p(lin_x), _p(lin_y),
                                  _I(B), _I(C), _I(H), _I(W), _I(inv_mode), _I(fma_mode), _I(dtype))
     return out
+
+
+def quotient_model(prod, d, delta):
+    """(got, want) of oracle_quotient_model: the product kernel's reciprocal-and-correct quotient vs the reference's fp64 divide."""
+    prod = _f32(prod)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    got, want = np.empty_like(prod), np.empty_like(prod)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib().oracle_quotient_model(_p(prod), d.ctypes.data_as(dp), delta.ctypes.data_as(dp), _p(got), _p(want),
+                                ctypes.c_longlong(prod.size))
+    return got, want

@@ -505,4 +505,26 @@ void oracle_gridwarp_fwd_16(const float *img, const float *flow, float *out,
             }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Model of the product's ChannelNorm-backward quotient (ir2rgb_b200/csrc/cnorm.cu)             */
+/* ------------------------------------------------------------------------------------------ */
+/* Not a restatement of the reference: a CPU model of the arithmetic the CUDA kernel uses INSTEAD of the reference's
+ * fp64 divide, so that its exactness argument can be tested without a GPU.  The kernel starts from a hardware
+ * reciprocal seed r0 = (1/d)(1 + delta) -- delta is an input here, the test sweeps |delta| up to 2^-16, far worse than
+ * MUFU.RCP64H -- applies two Newton steps, forms q = p*r, corrects it with one residual step and rounds to float;
+ * `want` is what the reference computes, (float)((double)prod / d) (channelnorm_kernel.cu:93). */
+void oracle_quotient_model(const float *prod, const double *d, const double *delta, float *got, float *want, long long n)
+{
+    for (long long i = 0; i < n; ++i) {
+        const double p = (double)prod[i];
+        double r = (1.0 / d[i]) * (1.0 + delta[i]);
+        r = fma(r, fma(-d[i], r, 1.0), r);
+        r = fma(r, fma(-d[i], r, 1.0), r);
+        double q = p * r;
+        q = fma(fma(-q, d[i], p), r, q);
+        got[i] = copysignf((float)q, prod[i]);
+        want[i] = (float)(p / d[i]);
+    }
+}
+
 int oracle_abi_version(void) { return 2; }

@@ -227,3 +227,23 @@ def test_cnorm16_oracle_vs_torch_emulation(c_oracle, dtype_name):
     want_gx = q.float().to(dt).float().numpy()
     got_gx = c_oracle.cnorm_bwd_16(x.float().numpy(), got, gy.float().numpy(), code)
     assert np.array_equal(got_gx, want_gx, equal_nan=True)
+
+
+def test_cnorm_backward_quotient_model(c_oracle):
+    """The product's ChannelNorm backward replaces the reference's fp64 divide by a reciprocal seed + two Newton steps +
+    one residual correction (csrc/cnorm.cu).  CPU model of that arithmetic against (float)((double)prod / d) for seeds far
+    worse than the hardware's: the fp32 results agree everywhere (the double quotient may differ in its last place, which
+    survives the rounding to fp32 only once in ~2^29 cases)."""
+    rng = np.random.default_rng(5)
+    n = 4_000_000
+    y = np.abs(rng.standard_normal(n)).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 6, n).astype(np.float32)
+    y[:1000] = 0.0                                                   # d = 1e-9
+    d = y.astype(np.float64) + 1e-9
+    prod = (rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n)).astype(np.float32)
+    prod[1000:2000] = 0.0
+    prod[2000:2100] = -0.0
+    delta = rng.uniform(-1.0, 1.0, n) * 2.0 ** -16
+    got, want = c_oracle.quotient_model(prod, d, delta)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+    assert (got != want).sum() <= 2, (got != want).sum()
+    assert np.abs(got.astype(np.float64) - want).max() <= np.abs(want).max() * 2.0 ** -23

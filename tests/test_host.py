@@ -136,3 +136,32 @@ def test_model_resample_fp16_option_leaves_other_dtypes_alone(monkeypatch):
     m.resample(img.half(), flow.half())         # fp16 but on the CPU: not the kernel's business
     m.resample(img.bfloat16(), flow.bfloat16())
     assert seen == [(torch.float32, torch.float32), (torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)]
+
+
+def test_magic_number_floor_and_int_conversions_model():
+    """csrc/warp_rows.cuh replaces floorf / (int) / (float) -- XU-pipe instructions on sm_100 -- by FP32-pipe arithmetic with
+    the constant 1.5 * 2^23 and claims exactness for |v| < 2^22.  numpy float32 model of the same operation sequence against
+    np.floor / integer casts on random values, every integer and half-integer neighbourhood near the range ends, and zeros."""
+    import numpy as np
+    M = np.float32(12582912.0)
+    rng = np.random.default_rng(9)
+    v = np.concatenate([
+        (rng.uniform(-1, 1, 3_000_000) * 2.0 ** rng.integers(-30, 22, 3_000_000)).astype(np.float32),
+        np.arange(-4096, 4096, dtype=np.float32) / np.float32(8.0),
+        np.nextafter(np.arange(-2048, 2048, dtype=np.float32), np.float32(np.inf)),
+        np.nextafter(np.arange(-2048, 2048, dtype=np.float32), np.float32(-np.inf)),
+        np.float32(4194304.0) - np.arange(1, 4096, dtype=np.float32) / np.float32(2.0),
+        -np.float32(4194304.0) + np.arange(1, 4096, dtype=np.float32) / np.float32(2.0),
+        np.array([0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -1.5, -2.5], np.float32)])
+    v = v[np.abs(v) < 4194304.0]
+    f = (v + M) - M                                   # round to nearest integer (ulp is 1 on [2^23, 2^24))
+    f = np.where(f > v, f - np.float32(1.0), f)       # step down if that rounded up
+    assert f.dtype == np.float32 and np.array_equal(f, np.floor(v))
+    # small_float_as_int: integer-valued float in [0, 2^22) -> int through the mantissa of v + 1.5 * 2^23
+    iv = np.floor(np.abs(v)).astype(np.float32)
+    as_int = (iv + M).view(np.int32) - np.int32(0x4B400000)
+    assert np.array_equal(as_int, iv.astype(np.int32))
+    # small_int_as_float: i in [0, 2^23) -> float by planting i in the mantissa of 2^23
+    i = rng.integers(0, 1 << 23, 1_000_000).astype(np.int32)
+    as_float = (np.int32(0x4B000000) | i).view(np.float32) - np.float32(8388608.0)
+    assert np.array_equal(as_float, i.astype(np.float32))

@@ -1,6 +1,10 @@
 """Build libflowops.so (the C-ABI library of hand-written sm_100a kernels) in-tree with nvcc.
 
-    python -m ir2rgb_b200.build [--force] [-v]
+    python -m ir2rgb_b200.build [--force] [-v] [--out PATH -DNAME=VALUE ...]
+
+`--out` with `-D` flags builds a VARIANT of the library (own object directory next to PATH) for A/B timing with
+tools/ab_ops.py; the kernels expose a few tuning macros for that (grep FLOWOPS_TUNE in csrc/).  The default build
+takes no -D flags.
 
 The library links only against the CUDA runtime (shared, so that it uses the runtime instance -- and
 therefore the current device and streams -- of the hosting process, e.g. PyTorch's); there are no
@@ -30,16 +34,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defines=()):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
-    os.makedirs(OBJ, exist_ok=True)
+    lib_path, obj_dir = LIB, OBJ
+    if out is not None:                       # a variant build: never touches the in-tree library or its objects
+        lib_path = os.path.abspath(out)
+        obj_dir = lib_path + ".obj"
+        force = True
+    os.makedirs(obj_dir, exist_ok=True)
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs):
-            jobs.append([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            jobs.append([NVCC] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -52,12 +61,14 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in srcs]
-    if force or jobs or _stale(LIB, objs):
-        run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", LIB] + objs +
+    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in srcs]
+    if force or jobs or _stale(lib_path, objs):
+        run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", lib_path] + objs +
             ["-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"])
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    argv = sys.argv[1:]
+    out = argv[argv.index("--out") + 1] if "--out" in argv else None
+    print(build(force="--force" in argv, verbose="-v" in argv, out=out, defines=[a for a in argv if a.startswith("-D")]))

@@ -220,7 +220,10 @@ struct FusionInputArgs {
     int c_dst;
 };
 
-__global__ void __launch_bounds__(256, 3) fusion_input_kernel(const __grid_constant__ FusionInputArgs a)
+#ifndef FLOWOPS_TUNE_FUSION_MINBLOCKS       // variant builds: python -m ir2rgb_b200.build --out ... -DFLOWOPS_TUNE_FUSION_MINBLOCKS=4
+#define FLOWOPS_TUNE_FUSION_MINBLOCKS 3     // 80 registers, 3 CTAs per SM (ncu: latency-bound at 34 % occupancy)
+#endif
+__global__ void __launch_bounds__(256, FLOWOPS_TUNE_FUSION_MINBLOCKS) fusion_input_kernel(const __grid_constant__ FusionInputArgs a)
 {
     const WarpArgs &g = a.g;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;

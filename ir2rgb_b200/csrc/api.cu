@@ -22,13 +22,17 @@ void set_error(const char *fmt, ...)
 // does likewise.
 int check_launch(const char *what)
 {
-    cudaError_t e = cudaGetLastError();
+    // peek, do not clear: a pending error left by an earlier launch of the host framework stays visible to it
+    cudaError_t e = cudaPeekAtLastError();
     // FLOWOPS_DEBUG_SYNC=1: synchronise after every launch so that an execution error is attributed
     // to the kernel that caused it (development aid; never set in production or under graph capture)
     static const bool debug_sync = getenv("FLOWOPS_DEBUG_SYNC") != nullptr;
     if (e == cudaSuccess && debug_sync) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        set_error("%s: %s", what, cudaGetErrorString(e));
+        // reported to the caller here, so take it off the runtime's error state (non-sticky errors would otherwise be
+        // reported again by the next call); it may stem from an earlier launch on this thread, hence the wording
+        (void)cudaGetLastError();
+        set_error("%s: %s (reported after this launch; a pending error of an earlier launch is reported here too)", what, cudaGetErrorString(e));
         return (int)e;
     }
     return 0;

@@ -275,11 +275,9 @@ int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, 
     float *WP = reinterpret_cast<float *>(ws);
     float *G = WP + b.win_floats;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, bSmemBytes);
+    {   // per-device attribute: set before every launch (see corr_fast.cu), not once per process
+        const cudaError_t e = cudaFuncSetAttribute(corr_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, bSmemBytes);
         if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", bSmemBytes, cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
 
     CUtensorMap tmG, tmW;

@@ -173,16 +173,19 @@ constexpr int kNhwcPix = 64, kNhwcCh = 32;
 // and v is written back in NHWC order only where another consumer needs it (`act`; frame 1 feeds conv_redir,
 // frame 2 feeds nothing else).  That replaces  bias+LeakyReLU (read+write)  +  planarize (read+write)  by one read
 // and one or two writes, and leaves the correlation proper with no pre-pass of its own.
-__global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restrict__ in1, const float *__restrict__ in2,
+// `act` may be the input itself (in-place epilogue, CorrelationPlanes.fill_from_conv_(write_act=True)): in1 / in2 / act
+// are therefore not __restrict__ and the feature loads are plain ld.global, not the non-coherent .nc form, which PTX
+// leaves undefined for memory the kernel also writes.
+__global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *in1, const float *in2,
                                                            float *__restrict__ P1, float *__restrict__ P2,
                                                            int C, int H, int W, int Hp, int Wp, int pitch1, int pitch2,
                                                            int only, const float *__restrict__ bias, float slope,
-                                                           float *__restrict__ act)
+                                                           float *act)
 {
     __shared__ float tile[2][kNhwcPix / 2][kNhwcCh + 1];       // [column parity][plane column][channel]
     const bool second = only < 0 ? (blockIdx.z & 1) : (only == 1);
     const int n = only < 0 ? (blockIdx.z >> 1) : blockIdx.z;
-    const float *__restrict__ in = second ? in2 : in1;
+    const float *in = second ? in2 : in1;
     float *__restrict__ P = second ? P2 : P1;
     const int pitch = second ? pitch2 : pitch1, shift = second ? kShift : 0;
     const int c_tiles = (C + kNhwcCh - 1) / kNhwcCh;
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256) corr_planarize_nhwc(const float *__restri
         const int px = warp + 8 * i, x = x0 + px, c = c0 + lane;
         float v = 0.f;
         if (x < W && c < C) {
-            v = ldg_stream(row + (size_t)x * C + c);
+            v = row[(size_t)x * C + c];
             if (bias) {
                 const float t = __fadd_rn(v, b);
                 v = t > 0.f ? t : __fmul_rn(t, slope);
@@ -510,14 +513,16 @@ int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cud
     rc = make_plane_map(&tm2, P2, g, p.Hp, p.pitch2, kF2W, kF2H);
     if (rc) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(corr_fwd_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, false, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_fwd_fast<2, false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: a process that runs the
+    // operator on several GPUs must set it on each of them, so it is set before every launch (a host-side call that
+    // is cheap, thread-safe and legal during stream capture) for the instantiation about to run.
+    const void *fn = nhwc_out ? (const void *)corr_fwd_fast<2, true>
+                   : out_dtype == FLOWOPS_DTYPE_F16 ? (const void *)corr_fwd_fast<2, false, __half>
+                   : out_dtype == FLOWOPS_DTYPE_BF16 ? (const void *)corr_fwd_fast<2, false, __nv_bfloat16>
+                                                     : (const void *)corr_fwd_fast<2, false>;
+    {
+        const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     const int row_tiles = (p.Hp + kTY - 1) / kTY, x_tiles = (p.Wp + kTX - 1) / kTX;
     const size_t grid = (size_t)g.B * row_tiles * x_tiles * 4;

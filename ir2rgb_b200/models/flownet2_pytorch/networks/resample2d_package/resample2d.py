@@ -30,6 +30,12 @@ class Resample2dFunction(Function):
                                       "bounds for larger kernels, resample2d_kernel.cu:53-58)")
         ctx.save_for_backward(input1, input2)
         ctx.kernel_size = kernel_size
+        dtype = input1.dtype
+        if dtype == torch.float64 or (dtype in (torch.float16, torch.bfloat16) and input1.shape[1] > 3):
+            # the reference kernel is dispatched for Half / double and any channel count (resample2d_kernel.cu:213);
+            # the one-pass 16-bit kernel covers the 1..3-channel frames of the hot path, everything else takes the
+            # fp32 kernel between two casts -- the arithmetic the reference's fp16 mode runs anyway (models.py:22-28)
+            return _F.warp_forward(input1.float(), input2.float(), _F.WARP_RESAMPLE2D).to(dtype)
         return _F.warp_forward(input1, input2, _F.WARP_RESAMPLE2D)
 
     @staticmethod

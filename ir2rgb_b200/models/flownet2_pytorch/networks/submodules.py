@@ -26,6 +26,14 @@ def padded_weight(conv, cin):
     axis = 0 if isinstance(conv, nn.ConvTranspose2d) else 1
     if w.shape[axis] == cin:
         return w
+    if torch.is_grad_enabled() and w.requires_grad:
+        # differentiable zero-padding: the cached copy below is detached and would give conv.weight no gradient
+        shape = list(w.shape)
+        shape[axis] = cin - w.shape[axis]
+        return torch.cat((w, w.new_zeros(shape)), axis)
+    # the cache is keyed on the tensor's version counter: in-place updates through `.data` (w.data.copy_(), the
+    # reference's init_deconv_bilinear) do NOT bump it -- call reset_padded_weights(net) after such an update
+    # (load_state_dict goes through Tensor.copy_ and is seen)
     key = (w.data_ptr(), w._version, cin)
     cache = conv.__dict__.get("_flowops_wpad")
     if cache is None or cache[0] != key:
@@ -37,6 +45,12 @@ def padded_weight(conv, cin):
         cache = (key, wp)
         conv.__dict__["_flowops_wpad"] = cache
     return cache[1]
+
+
+def reset_padded_weights(net):
+    """Drop every cached zero-padded weight of `net` (needed after weight updates made through `.data`)."""
+    for m in net.modules():
+        m.__dict__.pop("_flowops_wpad", None)
 
 
 def _raw_conv(conv, x, bias):

@@ -8,7 +8,10 @@ throw-away directory under /tmp because two mechanical patches are needed (SURVE
      -gencode arch=compute_100,code=sm_100 (passed here on the command line; setup.py is not used);
   2. `.type()` -> `.scalar_type()` inside the AT_DISPATCH_* calls (removed API in torch >= 2.x).
 
-Only the built .so files are written into the repo tree (oracle/_ref/), never the sources.
+Only built artefacts are written into the repo tree (oracle/_ref/, git-ignored), never the sources: the three .so
+files, and -- so that bench.py's reference arm and the GPU tests can run the reference's OWN `FlowNet2` class and its
+OWN operator wrappers on the GPU box, where /root/reference does not exist -- the byte-compiled (.pyc, sourceless)
+form of the unmodified Python modules of models/flownet2_pytorch that class needs (oracle/_ref/refpy/).
 Run:  python oracle/build_ref.py          (needs /root/reference; ~2-5 min on 8 cores, no GPU needed)
 """
 import glob
@@ -29,8 +32,36 @@ EXTS = {
 }
 
 
+# the reference's unmodified Python modules that define FlowNet2 and the three operator wrappers (paths below
+# models/flownet2_pytorch); byte-compiled into PYC_OUT as sourceless modules
+PYC_OUT = os.path.join(OUT, "refpy")
+PY_MODULES = ["__init__.py", "models.py", "networks/__init__.py", "networks/submodules.py", "networks/FlowNetC.py",
+              "networks/FlowNetS.py", "networks/FlowNetSD.py", "networks/FlowNetFusion.py",
+              "networks/correlation_package/__init__.py", "networks/correlation_package/correlation.py",
+              "networks/resample2d_package/__init__.py", "networks/resample2d_package/resample2d.py",
+              "networks/channelnorm_package/__init__.py", "networks/channelnorm_package/channelnorm.py"]
+
+
 def available():
     return os.path.isdir(NETS)
+
+
+def pyc_built():
+    return all(os.path.exists(os.path.join(PYC_OUT, "flownet2_pytorch", m + "c")) for m in PY_MODULES)
+
+
+def build_pyc(force=False):
+    """Byte-compile the reference's FlowNet2 package (unmodified) into oracle/_ref/refpy/flownet2_pytorch/**.pyc."""
+    import py_compile
+    if pyc_built() and not force:
+        return PYC_OUT
+    src_root = os.path.join(REF_ROOT, "models", "flownet2_pytorch")
+    for m in PY_MODULES:
+        dst = os.path.join(PYC_OUT, "flownet2_pytorch", m + "c")          # legacy location: imported without source
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        py_compile.compile(os.path.join(src_root, m), cfile=dst, dfile="reference:models/flownet2_pytorch/" + m,
+                           doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    return PYC_OUT
 
 
 def built():
@@ -40,6 +71,7 @@ def built():
 def build(force=False, verbose=False):
     if not available():
         raise RuntimeError("reference sources not found under %s" % NETS)
+    build_pyc(force)
     if built() and not force:
         return OUT
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")

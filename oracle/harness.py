@@ -3,8 +3,12 @@
 ``make_flownet(kind)`` returns the ``FlowNet`` wrapper (models/flownet.py semantics) whose three custom
 operators are replaced by
     kind="torch"  the pure-PyTorch oracle (runs on CPU: bench.py's cpu_baseline leg, CPU integration tests)
-    kind="ref"    the reference's own CUDA extensions from oracle/_ref (GPU: bench.py --impl reference,
-                  GPU integration tests)
+    kind="ref"    the reference's own CUDA extensions from oracle/_ref (GPU integration tests)
+    kind="refclass"  the reference's OWN `FlowNet2` class (models/flownet2_pytorch/models.py:30-161, unmodified,
+                  byte-compiled by oracle/build_ref.py into oracle/_ref/refpy because /root/reference does not
+                  exist on the GPU box) with its own Python operator wrappers importing its own rebuilt CUDA
+                  extensions -- nothing of this repo's architecture restatement is on that path
+                  (GPU: bench.py --impl reference, GPU integration tests)
 and whose glue is the reference's unfused chain (models.py:109-150, flownet.py:50).  The conv body is
 the same stock-PyTorch architecture in all arms; weights are shared by passing ``state_dict``.
 """
@@ -66,16 +70,43 @@ def swap_ops(flownet2, kind):
     return flownet2
 
 
+def reference_flownet2_available():
+    from . import build_ref, ref_ext
+    return ref_ext.available() and build_ref.pyc_built()
+
+
+def load_reference_flownet2_module():
+    """Import the reference's unmodified `flownet2_pytorch.models` from oracle/_ref/refpy with the three compiled
+    extension modules it imports (`correlation_cuda`, `resample2d_cuda`, `channelnorm_cuda`) resolved to the
+    reference's own rebuilt .so files in oracle/_ref."""
+    import importlib
+    import sys
+    from . import build_ref, ref_ext
+    if not reference_flownet2_available():
+        raise RuntimeError("oracle/_ref is incomplete: run `python oracle/build_ref.py` where /root/reference exists")
+    for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
+        sys.modules[name] = ref_ext._load(name)
+    if build_ref.PYC_OUT not in sys.path:
+        sys.path.insert(0, build_ref.PYC_OUT)
+    return importlib.import_module("flownet2_pytorch.models")
+
+
 class OracleFlowNet(nn.Module):
     """models/flownet.py:20-57 with oracle operators (no libflowops anywhere on this path)."""
 
     def __init__(self, kind, device, state_dict=None):
         super().__init__()
-        from ir2rgb_b200.models.flownet2_pytorch import models as m   # architecture definition only
-        net = m.FlowNet2()
-        if state_dict is not None:
-            net.load_state_dict(state_dict)
-        self.flowNet = swap_ops(net, kind).to(device).eval()
+        if kind == "refclass":
+            net = load_reference_flownet2_module().FlowNet2()             # the reference's class, ops and glue as they are
+            if state_dict is not None:
+                net.load_state_dict(state_dict)
+            self.flowNet = net.to(device).eval()
+        else:
+            from ir2rgb_b200.models.flownet2_pytorch import models as m   # architecture definition only
+            net = m.FlowNet2()
+            if state_dict is not None:
+                net.load_state_dict(state_dict)
+            self.flowNet = swap_ops(net, kind).to(device).eval()
         # flownet.py:50 calls `self.resample`, which in the reference resolves to the METHOD Model.resample
         # (base_model.py:129: get_grid + F.grid_sample), not to the Resample2d submodule of the same name
         self.resample = tr.networks_resample

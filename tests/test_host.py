@@ -165,3 +165,29 @@ def test_magic_number_floor_and_int_conversions_model():
     i = rng.integers(0, 1 << 23, 1_000_000).astype(np.int32)
     as_float = (np.int32(0x4B000000) | i).view(np.float32) - np.float32(8388608.0)
     assert np.array_equal(as_float, i.astype(np.float32))
+
+
+def test_ctypes_shims_have_the_pybind_signatures():
+    """ir2rgb_b200/shims mirrors the reference's three pybind11 modules (correlation_cuda.cc:169-172,
+    resample2d_cuda.cc:25-28, channelnorm_cuda.cc:28-31): same function names and positional parameters."""
+    import inspect
+    import sys
+    import ir2rgb_b200.shims as shims
+    want = {
+        "correlation_cuda": {"forward": 11, "backward": 13},
+        "resample2d_cuda": {"forward": 4, "backward": 6},
+        "channelnorm_cuda": {"forward": 3, "backward": 5},
+    }
+    for mod, fns in want.items():
+        for fn, nargs in fns.items():
+            assert len(inspect.signature(getattr(getattr(shims, mod), fn)).parameters) == nargs, (mod, fn)
+    saved = {n: sys.modules.get(n) for n in shims.NAMES}
+    try:
+        shims.install()
+        import correlation_cuda
+        assert correlation_cuda is shims.correlation_cuda
+    finally:
+        shims.uninstall()
+        for n, m in saved.items():
+            if m is not None:
+                sys.modules[n] = m

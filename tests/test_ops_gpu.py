@@ -110,7 +110,7 @@ def test_cnorm_golden(ops, golden_native):
 
 def test_cnorm_vs_reference_ext_full_size(ops, ref):
     torch.manual_seed(0)
-    x = (2 * torch.rand(4, 3, 512, 1024, device="cuda") - 1)
+    x = (2 * torch.rand(16, 3, 512, 1024, device="cuda") - 1)          # BASELINE config 3 at its stated size
     y = ops.ChannelNorm()(x)
     assert torch.equal(y, ref.channelnorm_forward(x))
     gy = torch.randn_like(y)
@@ -266,9 +266,9 @@ def test_networks_resample_special_values_match_aten(ops):
 
 @pytest.mark.parametrize("flavour", ["randn", "bilinear_up", "nearest_up"])
 def test_resample2d_vs_reference_ext_full_size(ops, ref, flavour):
-    """SURVEY 8d C3 shapes (batch 4 of the 16 to bound test time), the three flow flavours."""
+    """SURVEY 8d C3 at its stated size (16 x 3 x 512 x 1024), the three flow flavours."""
     torch.manual_seed(0)
-    B, H, W = 4, 512, 1024
+    B, H, W = 16, 512, 1024
     img = 2 * torch.rand(B, 3, H, W, device="cuda") - 1
     if flavour == "randn":
         flow = 4 * torch.randn(B, 2, H, W, device="cuda")
@@ -408,6 +408,28 @@ def test_correlation_config2_vs_reference_ext_and_fp64(ops, ref):
     go = torch.randn_like(out)
     out.backward(go)
     ga_ref, gb_ref = ref.correlation_backward(a, b, go, *FLOWNETC)
+    assert maxrel(at.grad, ga_ref) <= BWD_TOL
+    assert maxrel(bt.grad, gb_ref) <= BWD_TOL
+
+
+def test_correlation_flownet2_shape_vs_reference_ext(ops, ref):
+    """The FlowNet2 operating point of BASELINE config 4 (conv3 features of 512x1024 frames, 16 pairs): forward
+    against the reference's own kernel at the full size, backward on a batch slice of 2 (the reference backward
+    launches 2*B single-warp-block kernels and takes seconds per item)."""
+    torch.manual_seed(2)
+    a = torch.randn(16, 256, 64, 128, device="cuda")
+    b = torch.randn(16, 256, 64, 128, device="cuda")
+    out = ops.Correlation(*FLOWNETC, 1)(a, b)
+    out_ref = ref.correlation_forward(a, b, *FLOWNETC)
+    assert out.shape == out_ref.shape == (16, 441, 64, 128)
+    assert maxrel(out, out_ref) <= FWD_TOL
+    del out_ref
+    at, bt = a[:2].clone().requires_grad_(), b[:2].clone().requires_grad_()
+    o2 = ops.Correlation(*FLOWNETC, 1)(at, bt)
+    assert torch.equal(o2.detach(), out[:2])                  # batch rows are independent: a slice gives the same bits
+    go = torch.randn_like(o2)
+    o2.backward(go)
+    ga_ref, gb_ref = ref.correlation_backward(a[:2].contiguous(), b[:2].contiguous(), go, *FLOWNETC)
     assert maxrel(at.grad, ga_ref) <= BWD_TOL
     assert maxrel(bt.grad, gb_ref) <= BWD_TOL
 

@@ -29,14 +29,25 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _per_pair_work(frames):
+    """The hot path's operators on a batch chunk, through the CPU oracle (there is no CPU product path): the warp /
+    brightness-error stage (Resample2d -> subtract -> ChannelNorm, models.py:109-111) and a small Correlation.  Every
+    operator treats batch rows independently, so the sharded result must equal the unsharded one bit for bit."""
+    from oracle import torch_ref as tr
+    flow = 2 * torch.tanh(frames[:, :2].flip(2))
+    warped = tr.resample2d(frames.contiguous(), flow.contiguous())
+    err = tr.channelnorm(frames - warped)
+    corr = tr.correlation(frames, warped, 2, 1, 2, 1, 2)
+    return torch.cat((err.flatten(1), corr.flatten(1)), 1).sum(1)
+
+
 def _worker(rank, world, port, n_items, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)                                   # every rank sees the same synthetic batch
     frames = torch.randn(n_items, 3, 8, 8)
     mine = shard(frames, rank, world)
-    # stand-in for the per-pair work: any per-item function; sharded result must equal the unsharded one
-    local = (mine * 2 + 1).flatten(1).sum(1)
+    local = _per_pair_work(mine)
     sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([local.numel()]))
     parts = [torch.zeros(int(s.item())) for s in sizes]
@@ -47,7 +58,7 @@ def _worker(rank, world, port, n_items, ret):
     dist.barrier()
     if rank == 0:
         ok_sizes = sum(int(s) for s in sizes) == n_items
-        full = (frames * 2 + 1).flatten(1).sum(1)
+        full = _per_pair_work(frames)
         same = True
         if len(set(int(s) for s in sizes)) == 1:
             same = torch.equal(torch.cat(parts), full)

@@ -122,6 +122,17 @@ int flowops_corr_fwd_planes_nhwc(float *out, int c_dst, int c_off, float lrelu_s
                                  int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* Which kernel family flowops_corr_fwd* uses for the FlowNetC configuration (process-wide switch, read at every call):
+ *   bit 0 = 1  the tcgen05 tensor-core kernel (3xTF32, csrc/corr_tc.cu) when the shape allows it (C % 32 == 0, H and W
+ *              even) -- the default; max-relative error ~1e-6 against the reference kernel
+ *   bit 0 = 0  the FP32-FMA kernel (csrc/corr_fast.cu; also selected by the environment variable FLOWOPS_CORR_IMPL=ffma)
+ * bits 1-2 are debugging aids of the tensor-core kernel (2: rewrite the hi operand tile truncated, 4: single TF32
+ * product -- NOT within tolerance).  The two halves of the split form (flowops_corr_planes_from_conv, then
+ * flowops_corr_fwd_planes*) must run under the same setting: they share the workspace layout.  No reference
+ * counterpart. */
+int flowops_corr_set_impl(int flags);
+int flowops_corr_get_impl(void);
+
 /* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).
  * gout: [B,oC,oH,oW]; gin1, gin2: [B,C,H,W] (either may be NULL). */
 int flowops_corr_bwd(const float *in1, const float *in2, const float *gout,

@@ -46,7 +46,10 @@ extern "C" size_t flowops_corr_fwd_workspace_bytes(int B, int C, int H, int W, i
 {
     CorrGeom g;
     if (corr_geometry(g, B, C, H, W, pad, k, md, s1, s2)) return 0;
-    return corr_fast_supported(g) ? corr_fast_fwd_workspace(g) : 0;
+    if (!corr_fast_supported(g)) return 0;
+    size_t n = corr_fast_fwd_workspace(g);             // also what the 16-bit entry point uses
+    if (corr_tc_supported(g)) { const size_t t = corr_tc_fwd_workspace(g, true); if (t > n) n = t; }
+    return n;
 }
 
 extern "C" size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2)
@@ -69,6 +72,14 @@ extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, 
     FLOWOPS_REQUIRE(pad >= md + g.kr || k == 1, FLOWOPS_EUNSUPPORTED,
                     "corr_fwd: pad_size < max_displacement + kernel_radius reads outside the padded scratch in the reference");
     cudaStream_t st = (cudaStream_t)stream;
+    if (corr_tc_supported(g)) {                         // tcgen05 path: layout pass -> UMMA kernel -> NCHW store pass
+        int r2 = in_layout == FLOWOPS_LAYOUT_NCHW ? corr_tc_planes_nchw(in1, in2, g, workspace, workspace_bytes, st)
+                                                  : corr_tc_planes_nhwc(in1, 0, g, nullptr, 1.f, nullptr, workspace, workspace_bytes, st);
+        if (!r2 && in_layout == FLOWOPS_LAYOUT_NHWC)
+            r2 = corr_tc_planes_nhwc(in2, 1, g, nullptr, 1.f, nullptr, workspace, workspace_bytes, st);
+        if (r2) return r2;
+        return corr_tc_main(out, g, workspace, workspace_bytes, st, true, 0, 0, 1.f);
+    }
     if (corr_fast_supported(g)) return corr_fast_fwd_launch(in1, in2, out, g, in_layout, workspace, workspace_bytes, st);
     FLOWOPS_REQUIRE(in_layout == FLOWOPS_LAYOUT_NCHW, FLOWOPS_EUNSUPPORTED,
                     "corr_fwd: channels-last inputs are only taken by the FlowNetC configuration");
@@ -101,6 +112,8 @@ extern "C" int flowops_corr_planes_from_conv(const float *y, const float *bias, 
     const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
     if (rc) return rc;
     FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_planes_from_conv: FlowNetC configuration only");
+    if (corr_tc_supported(g))
+        return corr_tc_planes_nhwc(y, which, g, bias, slope, act, workspace, workspace_bytes, (cudaStream_t)stream);
     return corr_fast_planes_nhwc(which == 0 ? y : nullptr, which == 1 ? y : nullptr, g, which, bias, slope, act,
                                  workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -113,6 +126,7 @@ extern "C" int flowops_corr_fwd_planes(float *out, int B, int C, int H, int W, i
     const int rc = corr_geometry(g, B, C, H, W, pad, k, md, s1, s2);
     if (rc) return rc;
     FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_fwd_planes: FlowNetC configuration only");
+    if (corr_tc_supported(g)) return corr_tc_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream, true, 0, 0, 1.f);
     return corr_fast_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -144,5 +158,7 @@ extern "C" int flowops_corr_fwd_planes_nhwc(float *out, int c_dst, int c_off, fl
     FLOWOPS_REQUIRE(corr_fast_supported(g), FLOWOPS_EUNSUPPORTED, "corr_fwd_planes_nhwc: FlowNetC configuration only");
     FLOWOPS_REQUIRE(c_off >= 0 && c_off + g.D * g.D <= c_dst, FLOWOPS_EINVAL,
                     "corr_fwd_planes_nhwc: channels [%d, %d) do not fit in %d", c_off, c_off + g.D * g.D, c_dst);
+    if (corr_tc_supported(g))
+        return corr_tc_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream, false, c_dst, c_off, lrelu_slope);
     return corr_fast_main(out, g, workspace, workspace_bytes, (cudaStream_t)stream, true, c_dst, c_off, lrelu_slope);
 }

@@ -33,4 +33,15 @@ int corr_fast_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cud
 int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
                          const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
 
+// Tensor-core (tcgen05, 3xTF32) forward for the FlowNetC configuration: csrc/corr_tc.cu.  Selected when supported
+// unless FLOWOPS_CORR_IMPL=ffma (or flowops_corr_set_impl(0)); the FP32-FMA kernel above stays the general path.
+int corr_impl_flags();
+bool corr_tc_supported(const CorrGeom &g);
+size_t corr_tc_fwd_workspace(const CorrGeom &g, bool nchw_out);
+int corr_tc_planes_nchw(const float *in1, const float *in2, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
+int corr_tc_planes_nhwc(const float *in, int which, const CorrGeom &g, const float *bias, float slope, float *act,
+                        void *ws, size_t ws_bytes, cudaStream_t st);
+int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
+                 bool nchw_out, int c_dst, int c_off, float slope);
+
 }  // namespace flowops

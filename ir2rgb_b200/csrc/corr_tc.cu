@@ -1,0 +1,560 @@
+// corr_tc.cu -- FlowNetC Correlation forward on the Blackwell tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+//   out[n, tj*21+ti, y, x] = (1/C) * sum_c f1[n,c,y,x] * f2pad[n,c, y + 2(tj-10), x + 2(ti-10)]
+//   (reference correlation_cuda_kernel.cu:74-147; FlowNetC.py:31: pad 20, k 1, md 20, s1 1, s2 2)
+//
+// The contraction as a GEMM.  stride2 = 2 splits the problem into four parity planes in which the displacement is a
+// dense +-10 x +-10 window (see corr_fast.cu).  Inside one plane, for a tile of 16 x 8 = 128 pixels,
+//       D[m, n] = sum_c  A[m, c] * B[n, c]        A = the tile's f1 pixels (M = 128 rows),
+//                                                  B = the (16+20) x (8+20) = 36 x 28 window of f2 positions,
+// holds every output of the tile: pixel (r, c) needs the 21 x 21 window positions (r..r+20, c..c+20), i.e. 441 of the
+// 1008 columns of its row of D (43.75 % of the dense tile is useful -- the price of running a band-structured
+// contraction on a dense MMA; the FLOP counts reported for this kernel are the useful ones, 2*441*C per pixel).
+// TMEM holds 128 lanes x 512 fp32 columns, so a work item is (pixel tile, half of the window): N = 18 rows x 28 = 504
+// columns, issued as two UMMA N = 256 instructions (the last 8 columns are padding).
+//
+// Precision: 3xTF32.  x = hi + lo with hi = x truncated to TF32 (what the tensor core reads from an fp32 word) and
+// lo = x - hi (exact), D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulation in TMEM: max-relative error ~1e-6
+// against the fp32 reference kernel (tolerance 1e-5; tools/split_mma_probe.py, tests/test_corr_tc_gpu.py).  The raw
+// fp32 tile brought in by TMA *is* the hi operand; "splitter" warps derive the lo tile from it in shared memory, so
+// L2 -> SM traffic is one fp32 copy of the data.
+//
+// Data layout.  Operands must be K-major (channels contiguous) for the tf32 UMMA; the producer of the features writes
+// "P8" planes  P[n*4 + parity][c/8][Y][X][c%8]  (32-byte rows = the K = 8 of one tf32 UMMA; consecutive X contiguous,
+// so a TMA box row is one 32-byte sector and a box line is a contiguous run).  Zero padding of the window comes from
+// TMA's out-of-bounds fill.  A box lands in shared memory as consecutive 32-byte rows with the 32-byte swizzle, which is
+// the canonical K-major SWIZZLE_32B UMMA layout (8-row core matrices, SBO = 256 B).
+//
+// Roles (one persistent CTA per SM, 448 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + UMMA issue (one
+// thread), warps 2-5 = splitters, warps 6-13 = epilogue (tcgen05.ld -> scale / LeakyReLU -> shared-memory transpose ->
+// channels-last store: each pixel's run of channels is contiguous).  mbarrier pipelines: full (TMA -> splitters),
+// split (splitters -> UMMA), empty (tcgen05.commit -> TMA), tmem_full / tmem_empty (UMMA <-> epilogue).
+#include "corr.cuh"
+#include "tma.cuh"
+
+namespace flowops {
+namespace tc {
+
+constexpr int kD = 21, kR = 10;
+constexpr int TH = 16, TW = 8;                  // pixel tile (plane rows x plane columns)
+constexpr int M = TH * TW;                      // 128 = UMMA M
+constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;   // 36 x 28 window
+constexpr int HALF = WH / 2;                    // 18 window rows per work item
+constexpr int NUSED = HALF * WW;                // 504 accumulator columns in use
+constexpr int NPAD = 512;                       // two UMMA N = 256
+constexpr int KC = 8;                           // channels per pipeline stage = K of one tf32 UMMA (32 bytes)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = M * KC * 4;             // 4096
+constexpr int B_BYTES = NPAD * KC * 4;          // 16384 (the TMA box fills NUSED rows = 16128 bytes)
+constexpr int B_TX = NUSED * KC * 4;
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // 20480: raw (= hi) tile of A, then of B
+constexpr int STAGE_BYTES = 2 * RAW_BYTES;      // raw + lo
+constexpr int SPLIT_CHUNKS = (A_BYTES + B_TX) / 16;   // 1264 16-byte chunks to split per stage
+constexpr int N_SPLIT_WARPS = 4, N_EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + N_SPLIT_WARPS + N_EPI_WARPS);     // 448
+constexpr int EPI_STG_BYTES = 32 * kD * 4;      // one window row of a warp's 32 pixels: 32 x 21 floats
+constexpr int SMEM_BARRIERS = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + N_EPI_WARPS * EPI_STG_BYTES + SMEM_BARRIERS + 1024;   // + alignment slack
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol error traps (and surfaces as a launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > (1ll << 32)) __trap();
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
+{
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v)
+{
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_32B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits 0-13,
+// leading byte offset (unused for swizzled K-major, 1) in 16-29, stride byte offset = 256 B (one 8-row core matrix
+// of 32-byte rows) >> 4 in 32-45, descriptor version 1 (Blackwell) in 46-47, layout type SWIZZLE_32B = 6 in 61-63.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = fp32 (1 << 4), A and B = TF32 (2 << 7, 2 << 10),
+// both K-major (bits 15, 16 = 0), N >> 3 in bits 17-22, M >> 4 in bits 24-28.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Params {
+    float *out;
+    int CB;                 // channel blocks of 8
+    int H, W, PH, PW;       // image and plane extents (H, W even)
+    int tilesY, tilesX, n_items;
+    int c_dst, c_off;       // channels-last destination: [B, H, W, c_dst], channels [c_off, c_off + 441)
+    float slope, nelems, inv_nelems;
+    int flags;              // bit 0: splitters also rewrite the hi tile with its low 13 mantissa bits cleared
+                            // bit 1: single TF32 product (layout debugging; not within tolerance)
+};
+
+struct Item { int plane, Y0, X0, h; };
+__device__ __forceinline__ Item decode_item(int item, const Params &p)
+{
+    Item it;
+    it.h = item & 1;
+    int t = item >> 1;
+    const int tx = t % p.tilesX; t /= p.tilesX;
+    const int ty = t % p.tilesY;
+    it.plane = t / p.tilesY;
+    it.Y0 = ty * TH; it.X0 = tx * TW;
+    return it;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));           // generic-address view of the aligned base
+    const uint32_t stg_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = stg_base + N_EPI_WARPS * EPI_STG_BYTES;
+    // barriers: full[s], split[s], empty[s], tmem_full, tmem_empty; then the TMEM base address
+    auto bar_full = [&](int s) { return bar_base + 8u * s; };
+    auto bar_split = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    const uint32_t bar_tfull = bar_base + 8u * (3 * STAGES), bar_tempty = bar_tfull + 8u;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + (bar_tempty + 8u - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_split(s), N_SPLIT_WARPS);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, N_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(bar_tempty + 8u), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && warp < 2 + N_SPLIT_WARPS) {
+        // the 8 padding rows of every B tile (raw and lo) are read by the second UMMA and never written by TMA: keep
+        // them finite so that the (unused) padding columns of the accumulator cannot hold NaNs
+        const int t = threadIdx.x - 64;
+        for (int i = t; i < STAGES * 2 * (B_BYTES - B_TX) / 4; i += 32 * N_SPLIT_WARPS) {
+            const int per = (B_BYTES - B_TX) / 4;                    // floats per padding block
+            const int blk = i / per, o = i - blk * per;
+            const int s = blk >> 1, which = blk & 1;
+            *reinterpret_cast<float *>(gen + s * STAGE_BYTES + which * RAW_BYTES + A_BYTES + B_TX + o * 4) = 0.f;
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item w = decode_item(item, p);
+                for (int kb = 0; kb < p.CB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t u = it / STAGES;
+                    mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
+                    mbar_expect_tx(bar_full(s), A_BYTES + B_TX);
+                    const uint32_t dst = base + s * STAGE_BYTES;
+                    // A: dims (c%8, Y, X, c/8, plane): rows land in shared memory as m = x_local * 16 + y_local
+                    tma_load_5d(dst, &tmA, 0, w.Y0, w.X0, kb, w.plane, bar_full(s));
+                    // B: dims (c%8, X, Y, c/8, plane): rows n = wy_local * 28 + wx_local; zero fill outside the plane
+                    tma_load_5d(dst + A_BYTES, &tmB, 0, w.X0 - kR, w.Y0 - kR + HALF * w.h, kb, w.plane, bar_full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= UMMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, j = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+                mbar_wait_b(bar_tempty, (j & 1) ^ 1);                // the epilogue has drained the previous item
+                tc_fence_after();
+                for (int kb = 0; kb < p.CB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t u = it / STAGES;
+                    mbar_wait_b(bar_split(s), u & 1);
+                    tc_fence_after();
+                    const uint32_t sb = base + s * STAGE_BYTES;
+                    const uint64_t a_hi = smem_desc_sw32(sb), b_hi = smem_desc_sw32(sb + A_BYTES);
+                    const uint64_t a_lo = smem_desc_sw32(sb + RAW_BYTES), b_lo = smem_desc_sw32(sb + RAW_BYTES + A_BYTES);
+                    const uint64_t b_step = (uint64_t)((256 * KC * 4) >> 4);       // second N = 256 block of the window
+                    const uint32_t first = kb == 0 ? 0u : 1u;
+                    if (!(p.flags & 2)) {
+                        umma_tf32(tmem, a_lo, b_hi, kIdesc, first);
+                        umma_tf32(tmem + 256, a_lo, b_hi + b_step, kIdesc, first);
+                        umma_tf32(tmem, a_hi, b_lo, kIdesc, 1u);
+                        umma_tf32(tmem + 256, a_hi, b_lo + b_step, kIdesc, 1u);
+                        umma_tf32(tmem, a_hi, b_hi, kIdesc, 1u);
+                        umma_tf32(tmem + 256, a_hi, b_hi + b_step, kIdesc, 1u);
+                    } else {
+                        umma_tf32(tmem, a_hi, b_hi, kIdesc, first);
+                        umma_tf32(tmem + 256, a_hi, b_hi + b_step, kIdesc, first);
+                    }
+                    tc_commit(bar_empty(s));                         // stage reusable when these UMMAs have read it
+                }
+                tc_commit(bar_tfull);                                // accumulator complete
+            }
+        }
+    } else if (warp < 2 + N_SPLIT_WARPS) {
+        // ================= splitters: lo = x - trunc_tf32(x), same position in the lo tile =================
+        const int t = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (int kb = 0; kb < p.CB; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t u = it / STAGES;
+                mbar_wait_b(bar_full(s), u & 1);
+                uint8_t *raw = gen + s * STAGE_BYTES;
+#pragma unroll 2
+                for (int i = t; i < SPLIT_CHUNKS; i += 32 * N_SPLIT_WARPS) {
+                    float4 v = *reinterpret_cast<const float4 *>(raw + i * 16);
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    // the residual has at most 13 significant bits; the tensor core keeps 11 of them by truncation:
+                    // round to nearest first (+ half an ulp of TF32 on the bit pattern)
+                    l.x = __uint_as_float(__float_as_uint(__fsub_rn(v.x, h.x)) + 0x1000u);
+                    l.y = __uint_as_float(__float_as_uint(__fsub_rn(v.y, h.y)) + 0x1000u);
+                    l.z = __uint_as_float(__float_as_uint(__fsub_rn(v.z, h.z)) + 0x1000u);
+                    l.w = __uint_as_float(__float_as_uint(__fsub_rn(v.w, h.w)) + 0x1000u);
+                    *reinterpret_cast<float4 *>(raw + RAW_BYTES + i * 16) = l;
+                    if (p.flags & 1) *reinterpret_cast<float4 *>(raw + i * 16) = h;
+                }
+                fence_proxy_async();                                 // generic-proxy writes -> visible to the UMMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_split(s));
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int ew = warp - (2 + N_SPLIT_WARPS);                   // 0..7
+        const int q = warp & 3;                                      // TMEM lane quarter this warp may read
+        const int eh = ew >> 2;                                      // which half of the item's window rows
+        const int m = 32 * q + lane;                                 // accumulator row = x_local * 16 + y_local
+        const int r = m & 15, c = m >> 4, sel = lane >> 4;           // c = 2q + sel
+        float *stg = reinterpret_cast<float *>(gen + (stg_base - base) + ew * EPI_STG_BYTES);
+        uint32_t j = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+            const Item w = decode_item(item, p);
+            const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
+            const int Y = w.Y0 + r, X = w.X0 + c;
+            const bool pix_ok = Y < p.PH && X < p.PW;
+            const int pix_ofs = ((n * p.H + 2 * Y + py) * p.W + 2 * X + px) * p.c_dst + p.c_off;
+            mbar_wait_b(bar_tfull, j & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int k = 0; k < HALF / 2; ++k) {
+                const int wl = 2 * k + eh;                           // window row of this item handled now
+                const int tj = HALF * w.h + wl - r;                  // vertical displacement index of that row for my pixel
+                float v[24];
+                const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW + 2 * q);
+                tmem_ld16(taddr, v);
+                tmem_ld8(taddr + 16, v + 16);
+                tmem_ld_wait();
+                __syncwarp();                                        // previous row's staging fully read
+#pragma unroll
+                for (int i = 0; i < kD; ++i) {
+                    float t = sel ? v[i + 1] : v[i];
+                    t = div_nelems(t, p.nelems, p.inv_nelems);
+                    t = t > 0.f ? t : __fmul_rn(t, p.slope);
+                    stg[lane * kD + i] = t;
+                }
+                const int my_ofs = (pix_ok && tj >= 0 && tj < kD) ? pix_ofs + tj * kD : -1;
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < kD; ++e) {                       // 32 x 21 values, 32 per trip, pixel-major
+                    const int f = e * 32 + lane;
+                    const int pl = f / kD, i = f - pl * kD;
+                    const int ofs = __shfl_sync(0xffffffffu, my_ofs, pl);
+                    if (ofs >= 0) p.out[ofs + i] = stg[f];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plane writers: P[n*4 + py*2 + px][c/8][Y][X][c%8]
+// ---------------------------------------------------------------------------------------------------------------
+// NCHW -> P8.  A thread owns one pixel and one block of 8 channels: 8 coalesced row reads (lane = x), one 32-byte write;
+// even and odd lanes write two contiguous 512-byte runs (the two column parities).
+__global__ void __launch_bounds__(256) planes8_from_nchw(const float *__restrict__ in1, const float *__restrict__ in2,
+                                                         float *__restrict__ P1, float *__restrict__ P2,
+                                                         int C, int H, int W)
+{
+    const int CB = C >> 3, PH = H >> 1, PW = W >> 1;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int z = blockIdx.z;                                    // (input, n, cb)
+    const int cb = z % CB, n = (z / CB) >> 1, second = (z / CB) & 1;
+    if (x >= W || y >= H) return;
+    const float *in = (second ? in2 : in1) + (((size_t)n * C + cb * 8) * H + y) * W + x;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ldg_stream(in + (size_t)k * H * W);
+    const int par = (y & 1) * 2 + (x & 1);
+    float *dst = (second ? P2 : P1) + (((((size_t)n * 4 + par) * CB + cb) * PH + (y >> 1)) * PW + (x >> 1)) * 8;
+    stg_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
+    stg_stream4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// NHWC -> P8, optionally as the bias + LeakyReLU epilogue of the convolution that produced the features (and writing
+// the activated features back in NHWC order for another consumer).  A CTA transposes 64 pixels of one image row x 32
+// channels through shared memory: 128-byte coalesced reads per pixel, 1 KB contiguous writes per (parity, channel block).
+// `in` / `act` may alias (in-place epilogue): no __restrict__, plain loads.
+constexpr int kPix = 64, kCh = 32, kTilePitch = 36;
+__global__ void __launch_bounds__(256) planes8_from_nhwc(const float *in, float *__restrict__ P, int C, int H, int W,
+                                                         const float *__restrict__ bias, float slope, float *act)
+{
+    __shared__ __align__(16) float tile[2][kPix / 2][kTilePitch];   // [column parity][plane column][channel]
+    const int c_tiles = C / kCh;
+    const int ct = blockIdx.x % c_tiles, xt = blockIdx.x / c_tiles;
+    const int y = blockIdx.y, n = blockIdx.z, c0 = ct * kCh, x0 = xt * kPix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t row_off = ((size_t)n * H + y) * W * C;
+    const float b = bias ? __ldg(bias + c0 + lane) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPix / 8; ++i) {
+        const int pxl = warp + 8 * i, x = x0 + pxl;
+        float v = 0.f;
+        if (x < W) {
+            v = in[row_off + (size_t)x * C + c0 + lane];
+            if (bias) {
+                const float t = __fadd_rn(v, b);
+                v = t > 0.f ? t : __fmul_rn(t, slope);
+                if (act) act[row_off + (size_t)x * C + c0 + lane] = v;
+            }
+        }
+        tile[pxl & 1][pxl >> 1][lane] = v;
+    }
+    __syncthreads();
+    // warp = (column parity, channel block of 8): lane = plane column, one 32-byte row each
+    const int par_x = warp >> 2, cbl = warp & 3;
+    const int CB = C >> 3, PH = H >> 1, PW = W >> 1;
+    const int X = (x0 >> 1) + lane;
+    if (X < PW) {
+        const float4 lo = *reinterpret_cast<const float4 *>(&tile[par_x][lane][cbl * 8]);
+        const float4 hi = *reinterpret_cast<const float4 *>(&tile[par_x][lane][cbl * 8 + 4]);
+        float *dst = P + (((((size_t)n * 4 + (y & 1) * 2 + par_x) * CB + (c0 >> 3) + cbl) * PH + (y >> 1)) * PW + X) * 8;
+        stg_stream4(dst, lo);
+        stg_stream4(dst + 4, hi);
+    }
+}
+
+// channels-last cost volume [B, HW, 441] -> the reference's NCHW layout [B, 441, HW] (only the NCHW entry points need it)
+__global__ void __launch_bounds__(256) nhwc441_to_nchw(const float *__restrict__ in, float *__restrict__ out, int HW)
+{
+    __shared__ float t[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const float *src = in + (size_t)n * HW * (kD * kD);
+    float *dst = out + (size_t)n * HW * (kD * kD);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pix = p0 + ly + 8 * i, ch = c0 + lx;
+        t[ly + 8 * i][lx] = (pix < HW && ch < kD * kD) ? ldg_stream(src + (size_t)pix * (kD * kD) + ch) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = c0 + ly + 8 * i, pix = p0 + lx;
+        if (pix < HW && ch < kD * kD) stg_stream(dst + (size_t)ch * HW + pix, t[lx][ly + 8 * i]);
+    }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int g_corr_impl = -1;      // -1: not read yet; bit 0: tensor-core path on; bits 1-2 -> kernel flags (debug)
+
+int corr_impl_flags()
+{
+    if (g_corr_impl < 0) {
+        const char *e = getenv("FLOWOPS_CORR_IMPL");
+        g_corr_impl = (e && (e[0] == 'f' || e[0] == '0')) ? 0 : 1;       // "ffma" / "0" selects the FP32-FMA kernel
+    }
+    return g_corr_impl;
+}
+
+bool corr_tc_supported(const CorrGeom &g)
+{
+    return (corr_impl_flags() & 1) && corr_fast_supported(g) && (g.C % 32) == 0 && (g.H % 2) == 0 && (g.W % 2) == 0 &&
+           (size_t)g.B * g.H * g.W * 512 < (1ull << 31);
+}
+
+static size_t tc_plane_bytes(const CorrGeom &g) { return sizeof(float) * (size_t)g.B * g.C * g.H * g.W; }
+
+size_t corr_tc_fwd_workspace(const CorrGeom &g, bool nchw_out)
+{
+    return 2 * tc_plane_bytes(g) + (nchw_out ? sizeof(float) * (size_t)g.B * g.H * g.W * g.oC : 0);
+}
+
+static int encode_map5_sw32(CUtensorMap *tm, const void *base, const cuuint64_t dims[5], const cuuint64_t strides[4],
+                            const cuuint32_t box[5], const char *who)
+{
+    EncodeTiledFn enc = get_encoder();
+    FLOWOPS_REQUIRE(enc, FLOWOPS_EUNSUPPORTED, "%s: cuTensorMapEncodeTiled is not available from the driver", who);
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLOWOPS_REQUIRE(r == CUDA_SUCCESS, FLOWOPS_EINVAL, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
+    return 0;
+}
+
+static int tc_ws(const CorrGeom &g, void *ws, size_t ws_bytes, bool nchw_out, float *&P1, float *&P2, float *&tmp, const char *who)
+{
+    const size_t need = corr_tc_fwd_workspace(g, nchw_out);
+    FLOWOPS_REQUIRE(ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0, FLOWOPS_EWORKSPACE,
+                    "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, ws_bytes);
+    P1 = reinterpret_cast<float *>(ws);
+    P2 = P1 + tc_plane_bytes(g) / 4;
+    tmp = P2 + tc_plane_bytes(g) / 4;
+    return 0;
+}
+
+int corr_tc_planes_nchw(const float *in1, const float *in2, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    float *P1, *P2, *tmp;
+    int rc = tc_ws(g, ws, ws_bytes, false, P1, P2, tmp, "corr planes");
+    if (rc) return rc;
+    const dim3 grid((g.W + 31) / 32, (g.H + 7) / 8, 2 * g.B * (g.C / 8));
+    FLOWOPS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, FLOWOPS_EUNSUPPORTED, "corr planes: input too large for the layout grid");
+    tc::planes8_from_nchw<<<grid, 256, 0, st>>>(in1, in2, P1, P2, g.C, g.H, g.W);
+    return check_launch("planes8_from_nchw");
+}
+
+int corr_tc_planes_nhwc(const float *in, int which, const CorrGeom &g, const float *bias, float slope, float *act,
+                        void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    float *P1, *P2, *tmp;
+    int rc = tc_ws(g, ws, ws_bytes, false, P1, P2, tmp, "corr planes");
+    if (rc) return rc;
+    const dim3 grid((g.C / tc::kCh) * ((g.W + tc::kPix - 1) / tc::kPix), g.H, g.B);
+    FLOWOPS_REQUIRE(g.H <= 65535 && g.B <= 65535, FLOWOPS_EUNSUPPORTED, "corr planes: NHWC input too large for the transpose grid");
+    tc::planes8_from_nhwc<<<grid, 256, 0, st>>>(in, which ? P2 : P1, g.C, g.H, g.W, bias, slope, act);
+    return check_launch("planes8_from_nhwc");
+}
+
+// the correlation proper on P8 planes in the workspace; out is channels-last [B, H, W, c_dst] (channels c_off..c_off+440)
+// or, with nchw_out, the reference's [B, 441, H, W] (through a channels-last temporary in the workspace)
+int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
+                 bool nchw_out, int c_dst, int c_off, float slope)
+{
+    float *P1, *P2, *tmp;
+    int rc = tc_ws(g, ws, ws_bytes, nchw_out, P1, P2, tmp, "corr_fwd");
+    if (rc) return rc;
+    const int PH = g.H / 2, PW = g.W / 2, CB = g.C / 8;
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t row = 32, line = (cuuint64_t)PW * row, img = line * PH, plane = img * CB;
+        const cuuint64_t dimsA[5] = {8, (cuuint64_t)PH, (cuuint64_t)PW, (cuuint64_t)CB, (cuuint64_t)g.B * 4};
+        const cuuint64_t strA[4] = {line, row, img, plane};
+        const cuuint32_t boxA[5] = {8, tc::TH, tc::TW, 1, 1};
+        rc = encode_map5_sw32(&tmA, P1, dimsA, strA, boxA, "corr_fwd");
+        if (rc) return rc;
+        const cuuint64_t dimsB[5] = {8, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)CB, (cuuint64_t)g.B * 4};
+        const cuuint64_t strB[4] = {row, line, img, plane};
+        const cuuint32_t boxB[5] = {8, tc::WW, tc::HALF, 1, 1};
+        rc = encode_map5_sw32(&tmB, P2, dimsB, strB, boxB, "corr_fwd");
+        if (rc) return rc;
+    }
+    tc::Params p;
+    p.out = nchw_out ? tmp : out;
+    p.CB = CB; p.H = g.H; p.W = g.W; p.PH = PH; p.PW = PW;
+    p.tilesY = (PH + tc::TH - 1) / tc::TH; p.tilesX = (PW + tc::TW - 1) / tc::TW;
+    p.n_items = g.B * 4 * p.tilesY * p.tilesX * 2;
+    p.c_dst = nchw_out ? g.oC : c_dst; p.c_off = nchw_out ? 0 : c_off;
+    p.slope = nchw_out ? 1.f : slope;
+    p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
+    p.flags = (corr_impl_flags() >> 1) & 3;
+
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(tc::corr_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", tc::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+    const int grid = p.n_items < sms ? p.n_items : sms;
+    tc::corr_fwd_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
+    rc = check_launch("corr_fwd_tc");
+    if (rc || !nchw_out) return rc;
+    const int HW = g.H * g.W;
+    tc::nhwc441_to_nchw<<<dim3((HW + 31) / 32, (g.oC + 31) / 32, g.B), 256, 0, st>>>(tmp, out, HW);
+    return check_launch("nhwc441_to_nchw");
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_corr_set_impl(int flags)
+{
+    flowops::g_corr_impl = flags;
+    return 0;
+}
+
+extern "C" int flowops_corr_get_impl(void) { return flowops::corr_impl_flags(); }

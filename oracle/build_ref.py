@@ -46,8 +46,43 @@ def available():
     return os.path.isdir(NETS)
 
 
+PYC_EXT = ".rpyc"          # not ".pyc": snapshot tools commonly drop *.pyc / __pycache__; loaded by RefpyFinder below
+
+
+def _pyc_path(m):
+    return os.path.join(PYC_OUT, "flownet2_pytorch", m[:-3] + PYC_EXT)
+
+
 def pyc_built():
-    return all(os.path.exists(os.path.join(PYC_OUT, "flownet2_pytorch", m + "c")) for m in PY_MODULES)
+    return all(os.path.exists(_pyc_path(m)) for m in PY_MODULES)
+
+
+class RefpyFinder:
+    """sys.meta_path finder for the byte-compiled reference package: flownet2_pytorch[.sub.module] ->
+    oracle/_ref/refpy/flownet2_pytorch/sub/module.rpyc (packages: .../__init__.rpyc)."""
+
+    @staticmethod
+    def find_spec(fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname != "flownet2_pytorch" and not fullname.startswith("flownet2_pytorch."):
+            return None
+        rel = fullname.split(".")
+        base = os.path.join(PYC_OUT, *rel)
+        pkg_init = os.path.join(base, "__init__" + PYC_EXT)
+        if os.path.exists(pkg_init):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, pkg_init)
+            return importlib.util.spec_from_file_location(fullname, pkg_init, loader=loader, submodule_search_locations=[base])
+        if os.path.exists(base + PYC_EXT):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + PYC_EXT)
+            return importlib.util.spec_from_file_location(fullname, base + PYC_EXT, loader=loader)
+        return None
+
+
+def install_finder():
+    import sys
+    if not any(f is RefpyFinder for f in sys.meta_path):
+        sys.meta_path.insert(0, RefpyFinder)
 
 
 def build_pyc(force=False):
@@ -57,7 +92,7 @@ def build_pyc(force=False):
         return PYC_OUT
     src_root = os.path.join(REF_ROOT, "models", "flownet2_pytorch")
     for m in PY_MODULES:
-        dst = os.path.join(PYC_OUT, "flownet2_pytorch", m + "c")          # legacy location: imported without source
+        dst = _pyc_path(m)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(os.path.join(src_root, m), cfile=dst, dfile="reference:models/flownet2_pytorch/" + m,
                            doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -86,8 +86,7 @@ def load_reference_flownet2_module():
         raise RuntimeError("oracle/_ref is incomplete: run `python oracle/build_ref.py` where /root/reference exists")
     for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
         sys.modules[name] = ref_ext._load(name)
-    if build_ref.PYC_OUT not in sys.path:
-        sys.path.insert(0, build_ref.PYC_OUT)
+    build_ref.install_finder()
     return importlib.import_module("flownet2_pytorch.models")
 
 

@@ -29,7 +29,7 @@ SCRIPT = textwrap.dedent('''
     else:
         for name in ("correlation_cuda", "resample2d_cuda", "channelnorm_cuda"):
             sys.modules[name] = ref_ext._load(name)
-    sys.path.insert(0, build_ref.PYC_OUT)
+    build_ref.install_finder()
     from flownet2_pytorch.networks.correlation_package.correlation import Correlation
     from flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d
     from flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm

@@ -78,6 +78,16 @@ int flowops_warp_bwd(const float *img, const float *flow, const float *gout,
                      int B, int C, int H, int W, int mode,
                      const float *lin_x, const float *lin_y, void *stream);
 
+/* Process-wide switches of the warp kernels (read at every call; environment variable FLOWOPS_WARP_IMPL sets the
+ * initial value):
+ *   bit 0 (default 1)  flowops_warp_bwd accumulates the image gradient in per-warp shared-memory windows that each warp
+ *                      owns (plain adds, dense vector reductions on flush) instead of one L2 reduction per contribution;
+ *                      same values up to the summation order (backward tolerance 1e-4).  Needs C <= 3, W % 4 == 0.
+ *   bit 1 (default 0)  reserved for the tolerance-mode forward blend.
+ * No reference counterpart. */
+int flowops_warp_set_impl(int flags);
+int flowops_warp_get_impl(void);
+
 /* ---- Correlation --------------------------------------------------------------------------- */
 
 /* Output shape, correlation_cuda.cc:19-34. */
@@ -132,6 +142,9 @@ int flowops_corr_fwd_planes_nhwc(float *out, int c_dst, int c_off, float lrelu_s
  * counterpart. */
 int flowops_corr_set_impl(int flags);
 int flowops_corr_get_impl(void);
+/* Debugging aid of the tensor-core kernel: a device buffer of 8 x (number of SMs) uint64 that subsequent launches fill
+ * with per-CTA wait / work cycle counters (see csrc/corr_tc.cu); NULL switches it off.  Not thread-safe. */
+int flowops_corr_tc_trace(void *device_buffer);
 
 /* Replaces correlation_cuda.backward (correlation_cuda.cc:89-167 -> correlation_cuda_kernel.cu:429-564).
  * gout: [B,oC,oH,oW]; gin1, gin2: [B,C,H,W] (either may be NULL). */

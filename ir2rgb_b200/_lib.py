@@ -34,8 +34,11 @@ SIGNATURES = {
     "flowops_corr_planes_from_conv": (_int, [_vp, _vp, ctypes.c_float, _vp, _int] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_fwd_planes": (_int, [_vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_corr_fwd_planes_nhwc": (_int, [_vp, _int, _int, ctypes.c_float] + [_int] * 9 + [_vp, _sz, _vp]),
+    "flowops_warp_set_impl": (_int, [_int]),
+    "flowops_warp_get_impl": (_int, []),
     "flowops_corr_set_impl": (_int, [_int]),
     "flowops_corr_get_impl": (_int, []),
+    "flowops_corr_tc_trace": (_int, [_vp]),
     "flowops_corr_bwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _sz, _vp]),
     "flowops_cnorm_fwd_16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "flowops_cnorm_bwd_16": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),

@@ -10,8 +10,9 @@
 // holds every output of the tile: pixel (r, c) needs the 21 x 21 window positions (r..r+20, c..c+20), i.e. 441 of the
 // 1008 columns of its row of D (43.75 % of the dense tile is useful -- the price of running a band-structured
 // contraction on a dense MMA; the FLOP counts reported for this kernel are the useful ones, 2*441*C per pixel).
-// TMEM holds 128 lanes x 512 fp32 columns, so a work item is (pixel tile, half of the window): N = 18 rows x 28 = 504
-// columns, issued as two UMMA N = 256 instructions (the last 8 columns are padding).
+// A work item is (pixel tile, quarter of the window): N = 9 rows x 28 = 252 columns = one UMMA N = 256 (4 padding
+// columns), so TMEM (128 lanes x 512 fp32 columns) holds two accumulators and the epilogue of one item overlaps the
+// UMMAs of the next.
 //
 // Precision: 3xTF32.  x = hi + lo with hi = x truncated to TF32 (what the tensor core reads from an fp32 word) and
 // lo = x - hi (exact), D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 accumulation in TMEM: max-relative error ~1e-6
@@ -25,10 +26,10 @@
 // TMA's out-of-bounds fill.  A box lands in shared memory as consecutive 32-byte rows with the 32-byte swizzle, which is
 // the canonical K-major SWIZZLE_32B UMMA layout (8-row core matrices, SBO = 256 B).
 //
-// Roles (one persistent CTA per SM, 448 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + UMMA issue (one
-// thread), warps 2-5 = splitters, warps 6-13 = epilogue (tcgen05.ld -> scale / LeakyReLU -> shared-memory transpose ->
+// Roles (one persistent CTA per SM, 576 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + UMMA issue (one
+// thread), warps 2-9 = splitters, warps 10-17 = epilogue (tcgen05.ld -> scale / LeakyReLU -> shared-memory transpose ->
 // channels-last store: each pixel's run of channels is contiguous).  mbarrier pipelines: full (TMA -> splitters),
-// split (splitters -> UMMA), empty (tcgen05.commit -> TMA), tmem_full / tmem_empty (UMMA <-> epilogue).
+// split (splitters -> UMMA), empty (tcgen05.commit -> TMA), tmem_full[2] / tmem_empty[2] (UMMA <-> epilogue).
 #include "corr.cuh"
 #include "tma.cuh"
 
@@ -39,21 +40,22 @@ constexpr int kD = 21, kR = 10;
 constexpr int TH = 16, TW = 8;                  // pixel tile (plane rows x plane columns)
 constexpr int M = TH * TW;                      // 128 = UMMA M
 constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;   // 36 x 28 window
-constexpr int HALF = WH / 2;                    // 18 window rows per work item
-constexpr int NUSED = HALF * WW;                // 504 accumulator columns in use
-constexpr int NPAD = 512;                       // two UMMA N = 256
+constexpr int QROWS = WH / 4;                   // 9 window rows per work item
+constexpr int NUSED = QROWS * WW;               // 252 accumulator columns in use
+constexpr int NPAD = 256;                       // one UMMA N = 256
 constexpr int KC = 8;                           // channels per pipeline stage = K of one tf32 UMMA (32 bytes)
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int A_BYTES = M * KC * 4;             // 4096
-constexpr int B_BYTES = NPAD * KC * 4;          // 16384 (the TMA box fills NUSED rows = 16128 bytes)
+constexpr int B_BYTES = NPAD * KC * 4;          // 8192 (the TMA box fills NUSED rows = 8064 bytes)
 constexpr int B_TX = NUSED * KC * 4;
-constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // 20480: raw (= hi) tile of A, then of B
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // 12288: raw (= hi) tile of A, then of B
 constexpr int STAGE_BYTES = 2 * RAW_BYTES;      // raw + lo
-constexpr int SPLIT_CHUNKS = (A_BYTES + B_TX) / 16;   // 1264 16-byte chunks to split per stage
-constexpr int N_SPLIT_WARPS = 4, N_EPI_WARPS = 8;
-constexpr int THREADS = 32 * (2 + N_SPLIT_WARPS + N_EPI_WARPS);     // 448
+constexpr int SPLIT_CHUNKS = (A_BYTES + B_TX) / 16;   // 760 16-byte chunks to split per stage
+constexpr int N_SPLIT_WARPS = 8, N_EPI_WARPS = 8;
+constexpr int SPLIT_PER_THREAD = (SPLIT_CHUNKS + 32 * N_SPLIT_WARPS - 1) / (32 * N_SPLIT_WARPS);   // 3
+constexpr int THREADS = 32 * (2 + N_SPLIT_WARPS + N_EPI_WARPS);     // 576
 constexpr int EPI_STG_BYTES = 32 * kD * 4;      // one window row of a warp's 32 pixels: 32 x 21 floats
-constexpr int SMEM_BARRIERS = 128;
+constexpr int SMEM_BARRIERS = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + N_EPI_WARPS * EPI_STG_BYTES + SMEM_BARRIERS + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -66,12 +68,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // bounded wait: a protocol error traps (and surfaces as a launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ long long mbar_wait_b(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try(bar, parity)) return;
+    if (mbar_try(bar, parity)) return 0;
     const long long t0 = clock64();
     while (!mbar_try(bar, parity))
         if (clock64() - t0 > (1ll << 32)) __trap();
+    return clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar)
 {
@@ -129,16 +132,17 @@ struct Params {
     int tilesY, tilesX, n_items;
     int c_dst, c_off;       // channels-last destination: [B, H, W, c_dst], channels [c_off, c_off + 441)
     float slope, nelems, inv_nelems;
+    unsigned long long *trace;   // debugging: per-CTA wait / work cycle counters (8 per CTA), or null
     int flags;              // bit 0: splitters also rewrite the hi tile with its low 13 mantissa bits cleared
                             // bit 1: single TF32 product (layout debugging; not within tolerance)
 };
 
-struct Item { int plane, Y0, X0, h; };
+struct Item { int plane, Y0, X0, h; };          // h: which quarter of the window (rows 9h .. 9h+8)
 __device__ __forceinline__ Item decode_item(int item, const Params &p)
 {
     Item it;
-    it.h = item & 1;
-    int t = item >> 1;
+    it.h = item & 3;
+    int t = item >> 2;
     const int tx = t % p.tilesX; t /= p.tilesX;
     const int ty = t % p.tilesY;
     it.plane = t / p.tilesY;
@@ -154,12 +158,14 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));           // generic-address view of the aligned base
     const uint32_t stg_base = base + STAGES * STAGE_BYTES;
     const uint32_t bar_base = stg_base + N_EPI_WARPS * EPI_STG_BYTES;
-    // barriers: full[s], split[s], empty[s], tmem_full, tmem_empty; then the TMEM base address
+    // barriers: full[s], split[s], empty[s], tmem_full[2], tmem_empty[2]; then the TMEM base address
     auto bar_full = [&](int s) { return bar_base + 8u * s; };
     auto bar_split = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto bar_empty = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    const uint32_t bar_tfull = bar_base + 8u * (3 * STAGES), bar_tempty = bar_tfull + 8u;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + (bar_tempty + 8u - base));
+    auto bar_tfull = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto bar_tempty = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+    const uint32_t slot_addr = bar_base + 8u * (3 * STAGES + 4);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + (slot_addr - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -169,21 +175,23 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(bar_split(s), N_SPLIT_WARPS);
             mbar_init(bar_empty(s), 1);
         }
-        mbar_init(bar_tfull, 1);
-        mbar_init(bar_tempty, N_EPI_WARPS);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull(a), 1);
+            mbar_init(bar_tempty(a), N_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(bar_tempty + 8u), "r"(512) : "memory");
+                     :: "r"(slot_addr), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2 && warp < 2 + N_SPLIT_WARPS) {
-        // the 8 padding rows of every B tile (raw and lo) are read by the second UMMA and never written by TMA: keep
-        // them finite so that the (unused) padding columns of the accumulator cannot hold NaNs
+        // the 4 padding rows of every B tile (raw and lo) are read by the UMMA and never written by TMA: keep them
+        // finite so that the (unused) padding columns of the accumulator cannot hold NaNs
         const int t = threadIdx.x - 64;
-        for (int i = t; i < STAGES * 2 * (B_BYTES - B_TX) / 4; i += 32 * N_SPLIT_WARPS) {
-            const int per = (B_BYTES - B_TX) / 4;                    // floats per padding block
+        constexpr int per = (B_BYTES - B_TX) / 4;                    // floats per padding block
+        for (int i = t; i < STAGES * 2 * per; i += 32 * N_SPLIT_WARPS) {
             const int blk = i / per, o = i - blk * per;
             const int s = blk >> 1, which = blk & 1;
             *reinterpret_cast<float *>(gen + s * STAGE_BYTES + which * RAW_BYTES + A_BYTES + B_TX + o * 4) = 0.f;
@@ -199,109 +207,125 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t it = 0;
+            long long w_empty = 0;
+            const long long t_start = clock64();
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item(item, p);
                 for (int kb = 0; kb < p.CB; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
-                    mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
+                    w_empty += mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
                     mbar_expect_tx(bar_full(s), A_BYTES + B_TX);
                     const uint32_t dst = base + s * STAGE_BYTES;
                     // A: dims (c%8, Y, X, c/8, plane): rows land in shared memory as m = x_local * 16 + y_local
                     tma_load_5d(dst, &tmA, 0, w.Y0, w.X0, kb, w.plane, bar_full(s));
                     // B: dims (c%8, X, Y, c/8, plane): rows n = wy_local * 28 + wx_local; zero fill outside the plane
-                    tma_load_5d(dst + A_BYTES, &tmB, 0, w.X0 - kR, w.Y0 - kR + HALF * w.h, kb, w.plane, bar_full(s));
+                    tma_load_5d(dst + A_BYTES, &tmB, 0, w.X0 - kR, w.Y0 - kR + QROWS * w.h, kb, w.plane, bar_full(s));
                 }
             }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 0] = w_empty; p.trace[blockIdx.x * 8 + 6] = clock64() - t_start; }
         }
     } else if (warp == 1) {
         // ================= UMMA issuer =================
         if (lane == 0) {
             uint32_t it = 0, j = 0;
+            long long w_split = 0, w_tempty = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
-                mbar_wait_b(bar_tempty, (j & 1) ^ 1);                // the epilogue has drained the previous item
+                const int acc = j & 1;                               // accumulator buffer (TMEM columns 256 * acc ...)
+                w_tempty += mbar_wait_b(bar_tempty(acc), ((j >> 1) & 1) ^ 1);    // the epilogue has drained its previous use
                 tc_fence_after();
+                const uint32_t d = tmem + 256u * acc;
                 for (int kb = 0; kb < p.CB; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
-                    mbar_wait_b(bar_split(s), u & 1);
+                    w_split += mbar_wait_b(bar_split(s), u & 1);
                     tc_fence_after();
                     const uint32_t sb = base + s * STAGE_BYTES;
                     const uint64_t a_hi = smem_desc_sw32(sb), b_hi = smem_desc_sw32(sb + A_BYTES);
                     const uint64_t a_lo = smem_desc_sw32(sb + RAW_BYTES), b_lo = smem_desc_sw32(sb + RAW_BYTES + A_BYTES);
-                    const uint64_t b_step = (uint64_t)((256 * KC * 4) >> 4);       // second N = 256 block of the window
                     const uint32_t first = kb == 0 ? 0u : 1u;
                     if (!(p.flags & 2)) {
-                        umma_tf32(tmem, a_lo, b_hi, kIdesc, first);
-                        umma_tf32(tmem + 256, a_lo, b_hi + b_step, kIdesc, first);
-                        umma_tf32(tmem, a_hi, b_lo, kIdesc, 1u);
-                        umma_tf32(tmem + 256, a_hi, b_lo + b_step, kIdesc, 1u);
-                        umma_tf32(tmem, a_hi, b_hi, kIdesc, 1u);
-                        umma_tf32(tmem + 256, a_hi, b_hi + b_step, kIdesc, 1u);
+                        umma_tf32(d, a_lo, b_hi, kIdesc, first);
+                        umma_tf32(d, a_hi, b_lo, kIdesc, 1u);
+                        umma_tf32(d, a_hi, b_hi, kIdesc, 1u);
                     } else {
-                        umma_tf32(tmem, a_hi, b_hi, kIdesc, first);
-                        umma_tf32(tmem + 256, a_hi, b_hi + b_step, kIdesc, first);
+                        umma_tf32(d, a_hi, b_hi, kIdesc, first);
                     }
                     tc_commit(bar_empty(s));                         // stage reusable when these UMMAs have read it
                 }
-                tc_commit(bar_tfull);                                // accumulator complete
+                tc_commit(bar_tfull(acc));                           // accumulator complete
             }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 1] = w_split; p.trace[blockIdx.x * 8 + 2] = w_tempty; }
         }
     } else if (warp < 2 + N_SPLIT_WARPS) {
         // ================= splitters: lo = x - trunc_tf32(x), same position in the lo tile =================
         const int t = threadIdx.x - 64;
         uint32_t it = 0;
+        long long w_full = 0, t_work = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             for (int kb = 0; kb < p.CB; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t u = it / STAGES;
-                mbar_wait_b(bar_full(s), u & 1);
+                w_full += mbar_wait_b(bar_full(s), u & 1);
+                const long long tw0 = clock64();
                 uint8_t *raw = gen + s * STAGE_BYTES;
-#pragma unroll 2
-                for (int i = t; i < SPLIT_CHUNKS; i += 32 * N_SPLIT_WARPS) {
-                    float4 v = *reinterpret_cast<const float4 *>(raw + i * 16);
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    // the residual has at most 13 significant bits; the tensor core keeps 11 of them by truncation:
-                    // round to nearest first (+ half an ulp of TF32 on the bit pattern)
-                    l.x = __uint_as_float(__float_as_uint(__fsub_rn(v.x, h.x)) + 0x1000u);
-                    l.y = __uint_as_float(__float_as_uint(__fsub_rn(v.y, h.y)) + 0x1000u);
-                    l.z = __uint_as_float(__float_as_uint(__fsub_rn(v.z, h.z)) + 0x1000u);
-                    l.w = __uint_as_float(__float_as_uint(__fsub_rn(v.w, h.w)) + 0x1000u);
-                    *reinterpret_cast<float4 *>(raw + RAW_BYTES + i * 16) = l;
-                    if (p.flags & 1) *reinterpret_cast<float4 *>(raw + i * 16) = h;
+                float4 v[SPLIT_PER_THREAD];
+#pragma unroll
+                for (int k = 0; k < SPLIT_PER_THREAD; ++k) {         // all loads first: one shared-memory latency per stage
+                    const int i = t + k * 32 * N_SPLIT_WARPS;
+                    if (i < SPLIT_CHUNKS) v[k] = *reinterpret_cast<const float4 *>(raw + i * 16);
+                }
+#pragma unroll
+                for (int k = 0; k < SPLIT_PER_THREAD; ++k) {
+                    const int i = t + k * 32 * N_SPLIT_WARPS;
+                    if (i < SPLIT_CHUNKS) {
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v[k].x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(v[k].y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(v[k].z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(v[k].w) & 0xffffe000u);
+                        // the residual has at most 13 significant bits; the tensor core keeps 11 of them by truncation:
+                        // round to nearest first (+ half an ulp of TF32 on the bit pattern)
+                        l.x = __uint_as_float(__float_as_uint(__fsub_rn(v[k].x, h.x)) + 0x1000u);
+                        l.y = __uint_as_float(__float_as_uint(__fsub_rn(v[k].y, h.y)) + 0x1000u);
+                        l.z = __uint_as_float(__float_as_uint(__fsub_rn(v[k].z, h.z)) + 0x1000u);
+                        l.w = __uint_as_float(__float_as_uint(__fsub_rn(v[k].w, h.w)) + 0x1000u);
+                        *reinterpret_cast<float4 *>(raw + RAW_BYTES + i * 16) = l;
+                        if (p.flags & 1) *reinterpret_cast<float4 *>(raw + i * 16) = h;
+                    }
                 }
                 fence_proxy_async();                                 // generic-proxy writes -> visible to the UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_split(s));
+                t_work += clock64() - tw0;
             }
         }
+        if (p.trace && t == 0) { p.trace[blockIdx.x * 8 + 3] = w_full; p.trace[blockIdx.x * 8 + 7] = t_work; }
     } else {
         // ================= epilogue =================
         const int ew = warp - (2 + N_SPLIT_WARPS);                   // 0..7
         const int q = warp & 3;                                      // TMEM lane quarter this warp may read
-        const int eh = ew >> 2;                                      // which half of the item's window rows
+        const int eh = ew >> 2;                                      // even / odd window rows of the item
         const int m = 32 * q + lane;                                 // accumulator row = x_local * 16 + y_local
         const int r = m & 15, c = m >> 4, sel = lane >> 4;           // c = 2q + sel
         float *stg = reinterpret_cast<float *>(gen + (stg_base - base) + ew * EPI_STG_BYTES);
         uint32_t j = 0;
+        long long w_tfull = 0, t_epi = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
             const Item w = decode_item(item, p);
+            const int acc = j & 1;
             const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
             const int Y = w.Y0 + r, X = w.X0 + c;
             const bool pix_ok = Y < p.PH && X < p.PW;
             const int pix_ofs = ((n * p.H + 2 * Y + py) * p.W + 2 * X + px) * p.c_dst + p.c_off;
-            mbar_wait_b(bar_tfull, j & 1);
+            w_tfull += mbar_wait_b(bar_tfull(acc), (j >> 1) & 1);
+            const long long te0 = clock64();
             tc_fence_after();
 #pragma unroll 1
-            for (int k = 0; k < HALF / 2; ++k) {
-                const int wl = 2 * k + eh;                           // window row of this item handled now
-                const int tj = HALF * w.h + wl - r;                  // vertical displacement index of that row for my pixel
+            for (int wl = eh; wl < QROWS; wl += 2) {                 // window row of this item handled now
+                const int tj = QROWS * w.h + wl - r;                 // vertical displacement index of that row for my pixel
                 float v[24];
-                const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW + 2 * q);
+                const uint32_t taddr = tmem + 256u * acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW + 2 * q);
                 tmem_ld16(taddr, v);
                 tmem_ld8(taddr + 16, v + 16);
                 tmem_ld_wait();
@@ -325,8 +349,10 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty);
+            if (lane == 0) mbar_arrive(bar_tempty(acc));
+            t_epi += clock64() - te0;
         }
+        if (p.trace && ew == 0 && lane == 0) { p.trace[blockIdx.x * 8 + 4] = w_tfull; p.trace[blockIdx.x * 8 + 5] = t_epi; }
     }
 
     tc_fence_before();
@@ -431,6 +457,7 @@ __global__ void __launch_bounds__(256) nhwc441_to_nchw(const float *__restrict__
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+static unsigned long long *g_tc_trace = nullptr;      // debugging aid, see flowops_corr_tc_trace
 static int g_corr_impl = -1;      // -1: not read yet; bit 0: tensor-core path on; bits 1-2 -> kernel flags (debug)
 
 int corr_impl_flags()
@@ -521,7 +548,7 @@ int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaS
         if (rc) return rc;
         const cuuint64_t dimsB[5] = {8, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)CB, (cuuint64_t)g.B * 4};
         const cuuint64_t strB[4] = {row, line, img, plane};
-        const cuuint32_t boxB[5] = {8, tc::WW, tc::HALF, 1, 1};
+        const cuuint32_t boxB[5] = {8, tc::WW, tc::QROWS, 1, 1};
         rc = encode_map5_sw32(&tmB, P2, dimsB, strB, boxB, "corr_fwd");
         if (rc) return rc;
     }
@@ -529,11 +556,12 @@ int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaS
     p.out = nchw_out ? tmp : out;
     p.CB = CB; p.H = g.H; p.W = g.W; p.PH = PH; p.PW = PW;
     p.tilesY = (PH + tc::TH - 1) / tc::TH; p.tilesX = (PW + tc::TW - 1) / tc::TW;
-    p.n_items = g.B * 4 * p.tilesY * p.tilesX * 2;
+    p.n_items = g.B * 4 * p.tilesY * p.tilesX * 4;
     p.c_dst = nchw_out ? g.oC : c_dst; p.c_off = nchw_out ? 0 : c_off;
     p.slope = nchw_out ? 1.f : slope;
     p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
     p.flags = (corr_impl_flags() >> 1) & 3;
+    p.trace = g_tc_trace;
 
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
@@ -554,6 +582,16 @@ int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaS
 extern "C" int flowops_corr_set_impl(int flags)
 {
     flowops::g_corr_impl = flags;
+    return 0;
+}
+
+// Debugging aid (not part of the operator API): device buffer of 8 x 148 uint64 that the next tensor-core launches fill
+// with per-CTA cycle counters -- [0] TMA producer waiting for a free stage, [1] UMMA thread waiting for split data,
+// [2] UMMA thread waiting for the epilogue to drain TMEM, [3] splitters waiting for TMA data, [4] epilogue waiting for the
+// accumulator, [5] epilogue busy, [6] CTA lifetime, [7] splitters busy.  NULL switches it off.
+extern "C" int flowops_corr_tc_trace(void *device_buffer)
+{
+    flowops::g_tc_trace = static_cast<unsigned long long *>(device_buffer);
     return 0;
 }
 

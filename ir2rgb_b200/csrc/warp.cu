@@ -22,9 +22,24 @@
 // products in fp64, the fourth in fp32, fp32 adds in TL,TR,BL,BR order) and is bit-identical to it.
 // GRIDSAMPLE reproduces ATen's fp32 op chain (GridSampler.cuh: unnormalize -> clip -> floor ->
 // weights as differences -> nw,ne,sw,se FFMA chain).
-#include "warp_rows_bwd.cuh"
+#include <stdlib.h>
+
+#include "warp_win_bwd.cuh"
 
 namespace flowops {
+
+// process-wide switches of the warp kernels (flowops_warp_set_impl): bit 0 = image gradient by owned accumulation in
+// per-warp shared-memory windows (warp_win_bwd.cuh; default on), bit 1 = forward blend with fp32 weights instead of the
+// reference's accidental fp64 weight products (tolerance mode, see flowops.h; default off)
+static int g_warp_impl = -1;
+static int warp_impl_flags()
+{
+    if (g_warp_impl < 0) {
+        const char *e = getenv("FLOWOPS_WARP_IMPL");
+        g_warp_impl = e ? atoi(e) : 1;
+    }
+    return g_warp_impl;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -273,6 +288,17 @@ static int launch_bwd(const float *img, const float *flow, const float *gout, fl
         cudaError_t e = cudaMemsetAsync(gimg, 0, sizeof(float) * (size_t)B * C * H * W, st);
         if (e != cudaSuccess) { set_error("warp_bwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     }
+    if (gimg && C <= 3 && (W % 4) == 0 && aligned16(gimg) && (warp_impl_flags() & 1)) {
+        // owned accumulation in per-warp shared-memory windows (warp_win_bwd.cuh)
+        WarpBwdArgs a{};
+        a.img = img; a.flow = flow; a.gout = gout; a.gimg = gimg; a.gflow = gflow;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.rows = 32;
+        a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+        a.lin_x = lx; a.lin_y = ly; a.invx = invx; a.invy = invy; a.mulx = mulx; a.muly = muly;
+        const int rc = gflow ? launch_warp_win_bwd<MODE, true>(a, st) : launch_warp_win_bwd<MODE, false>(a, st);
+        if (rc) return rc;
+        return check_launch("warp_bwd");
+    }
     if (C <= 3) {
         // row-walking kernel (warp_rows_bwd.cuh)
         WarpBwdArgs a{};
@@ -339,3 +365,11 @@ extern "C" int flowops_warp_bwd(const float *img, const float *flow, const float
     gs_scales(H, W, invx, invy, mulx, muly);
     return launch_bwd<FLOWOPS_WARP_GRIDSAMPLE>(img, flow, gout, gimg, gflow, B, C, H, W, lin_x, lin_y, invx, invy, mulx, muly, st);
 }
+
+extern "C" int flowops_warp_set_impl(int flags)
+{
+    flowops::g_warp_impl = flags;
+    return 0;
+}
+
+extern "C" int flowops_warp_get_impl(void) { return flowops::warp_impl_flags(); }

@@ -80,9 +80,10 @@ int flowops_warp_bwd(const float *img, const float *flow, const float *gout,
 
 /* Process-wide switches of the warp kernels (read at every call; environment variable FLOWOPS_WARP_IMPL sets the
  * initial value):
- *   bit 0 (default 1)  flowops_warp_bwd accumulates the image gradient in per-warp shared-memory windows that each warp
+ *   bit 0 (default 0)  flowops_warp_bwd accumulates the image gradient in per-warp shared-memory windows that each warp
  *                      owns (plain adds, dense vector reductions on flush) instead of one L2 reduction per contribution;
  *                      same values up to the summation order (backward tolerance 1e-4).  Needs C <= 3, W % 4 == 0.
+ *                      Faster on incoherent flows (per-pixel noise), slower on smooth ones -- hence off by default.
  *   bit 1 (default 0)  reserved for the tolerance-mode forward blend.
  * No reference counterpart. */
 int flowops_warp_set_impl(int flags);

@@ -29,14 +29,15 @@
 namespace flowops {
 
 // process-wide switches of the warp kernels (flowops_warp_set_impl): bit 0 = image gradient by owned accumulation in
-// per-warp shared-memory windows (warp_win_bwd.cuh; default on), bit 1 = forward blend with fp32 weights instead of the
+// per-warp shared-memory windows (warp_win_bwd.cuh; default OFF: measured on B200 it cuts the L2 reduction sector
+// operations 4x but only wins on incoherent flows), bit 1 = forward blend with fp32 weights instead of the
 // reference's accidental fp64 weight products (tolerance mode, see flowops.h; default off)
 static int g_warp_impl = -1;
 static int warp_impl_flags()
 {
     if (g_warp_impl < 0) {
         const char *e = getenv("FLOWOPS_WARP_IMPL");
-        g_warp_impl = e ? atoi(e) : 1;
+        g_warp_impl = e ? atoi(e) : 0;
     }
     return g_warp_impl;
 }

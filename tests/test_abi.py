@@ -58,6 +58,22 @@ def test_fast_correlation_kernel_uses_tma(flowops_lib):
     assert "RED.E.ADD.F32" in sass or "REDG" in sass or "RED." in sass, "warp backward uses fire-and-forget reductions"
 
 
+def test_tensor_core_correlation_is_tcgen05(flowops_lib):
+    """The Correlation forward runs on the 5th-generation tensor cores: tcgen05.mma (UTC*MMA), accumulators read back from
+    TMEM with tcgen05.ld (LDTM), 5-D TMA loads, TMEM allocation -- in SASS, where the PTX names never appear."""
+    from ir2rgb_b200 import _lib
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "corr_fwd_tc", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if "corr_fwd_tc" not in sass:      # older cuobjdump: no -fun filter on shared objects
+        sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert re.search(r"\bUTC\w*MMA\b", sass), "tcgen05.mma"
+    assert "LDTM" in sass, "tcgen05.ld"
+    assert "UTMALDG.5D" in sass, "5-D TMA loads of the K-major planes"
+    assert not re.search(r"\bHMMA\b|\bHGMMA\b", sass), "no legacy mma.sync / wgmma path"
+
+
 def test_bad_arguments_are_rejected_without_a_device(flowops_lib):
     lib = flowops_lib
     assert lib.flowops_version() == 1
@@ -81,9 +97,18 @@ def test_shapes_and_workspace(flowops_lib):
     assert (oc.value, oh.value, ow.value) == (441, 48, 64)
     assert lib.flowops_corr_out_shape(10, 10, 4, 1, 4, 2, 2, ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)) == 0
     assert (oc.value, oh.value, ow.value) == (25, 5, 5)
-    # FlowNetC configuration: two parity-plane copies (the role of the reference's rbot1/rbot2, without the
-    # 20-pixel padding); the f2 planes carry 4 extra columns per row for TMA start alignment
-    assert lib.flowops_corr_fwd_workspace_bytes(8, 256, 48, 64, 20, 1, 20, 1, 2) == 8 * 4 * 256 * 24 * (32 + 36) * 4
+    # FlowNetC configuration, FP32-FMA kernel: two parity-plane copies (the role of the reference's rbot1/rbot2, without
+    # the 20-pixel padding); the f2 planes carry 4 extra columns per row for TMA start alignment
+    prev = lib.flowops_corr_get_impl()
+    try:
+        lib.flowops_corr_set_impl(0)
+        assert lib.flowops_corr_fwd_workspace_bytes(8, 256, 48, 64, 20, 1, 20, 1, 2) == 8 * 4 * 256 * 24 * (32 + 36) * 4
+        # tensor-core kernel: two K-major plane copies without any padding + the channels-last cost volume the NCHW
+        # entry point converts from
+        lib.flowops_corr_set_impl(1)
+        assert lib.flowops_corr_fwd_workspace_bytes(8, 256, 48, 64, 20, 1, 20, 1, 2) == (2 * 8 * 256 * 48 * 64 + 8 * 441 * 48 * 64) * 4
+    finally:
+        lib.flowops_corr_set_impl(prev)
     assert lib.flowops_corr_fwd_workspace_bytes(1, 8, 9, 11, 4, 1, 4, 1, 1) == 0               # generic kernel
 
 

@@ -553,3 +553,34 @@ def test_epilogue_into_concat_buffer(ops, c, c_total, c_off):
     with torch.no_grad():
         cat = F.cat_channels(parts, pad_to=8)
     assert cat.shape[1] == -(-(c + 5) // 8) * 8 and torch.equal(cat[:, :c + 5], torch.cat(parts, 1)) and (cat[:, c + 5:] == 0).all()
+
+
+# =============================================================================================
+# warp backward with owned per-warp accumulation windows (flowops_warp_set_impl bit 0)
+# =============================================================================================
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", [(2, 3, 17, 28, 3.0), (1, 1, 40, 64, 10.0), (2, 2, 33, 100, 40.0), (1, 3, 64, 96, 0.0),
+                                  (3, 3, 70, 132, 0.5), (1, 3, 256, 512, 5.0)])
+def test_warp_backward_window_kernel_matches_direct_reductions(flowops_lib, c_oracle, case, mode):
+    """The shared-memory-window image gradient (warp_win_bwd.cuh) against the direct-reduction kernel and, on the small
+    cases, the C oracle: same sums up to the order of the additions."""
+    from ir2rgb_b200 import functional as F
+    B, C, H, W, amp = case
+    torch.manual_seed(21)
+    img = torch.randn(B, C, H, W, device="cuda")
+    flow = (amp * torch.randn(B, 2, H, W, device="cuda")).contiguous()
+    go = torch.randn(B, C, H, W, device="cuda")
+    prev = flowops_lib.flowops_warp_get_impl()
+    try:
+        flowops_lib.flowops_warp_set_impl(0)
+        gi_d, gf_d = F.warp_backward(img, flow, go, True, True, mode)
+        flowops_lib.flowops_warp_set_impl(1)
+        gi_w, gf_w = F.warp_backward(img, flow, go, True, True, mode)
+        gi_w2, _ = F.warp_backward(img, flow, go, True, False, mode)
+    finally:
+        flowops_lib.flowops_warp_set_impl(prev)
+    assert torch.equal(gf_w, gf_d)                       # the flow gradient is the same gather
+    assert maxrel(gi_w, gi_d) <= 1e-5 and maxrel(gi_w2, gi_d) <= 1e-5
+    if mode == 0 and H * W <= 4096:
+        gi_o, _ = c_oracle.resample2d_bwd(img.cpu().numpy(), flow.cpu().numpy(), go.cpu().numpy())
+        assert maxrel(gi_w, gi_o) <= BWD_TOL

@@ -66,5 +66,5 @@ for name, flow in flows.items():
                 rec["us_impl%d_%s" % (impl, "both" if need_flow else "img")] = e0.elapsed_time(e1) / 12 * 1e3
         out["timing"].append(rec)
         print(json.dumps(rec), flush=True)
-lib.flowops_warp_set_impl(1)
+lib.flowops_warp_set_impl(0)
 json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "warp_probe.json"), "w"), indent=1)

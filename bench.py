@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-ops", action="store_true", help="skip the per-operator roofline table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vid2vid", action="store_true", help="skip the BASELINE configs[4] training-iteration timing (`extra`)")
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="layout of the FlowNet2 conv body in the native arm (the reference arm keeps the stock NCHW)")
@@ -57,11 +58,14 @@ def parse():
 
 
 def peaks():
-    p = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    """HBM copy bandwidth and the dense-TF32 tensor peak.  The driver measures a bf16 GEMM; TF32 runs at half the bf16
+    rate on the same pipe, so bf16 / 2 is the TF32 proxy -- the sustained figure for a kernel timed inside a long step."""
+    p = {"hbm_gbs": 6650.0, "tf32_tflops": 1400.0 / 2, "tf32_tflops_burst": 1590.0 / 2, "source": "fallback (B200_PROFILING.md)"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         m = json.load(open(path))
-        p = {"hbm_gbs": float(m["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+        p = {"hbm_gbs": float(m["hbm_gbs"]), "tf32_tflops": float(m.get("bf16_tflops_sustained", m["bf16_tflops"])) / 2,
+             "tf32_tflops_burst": float(m["bf16_tflops"]) / 2, "source": "measured (MEASURED_PEAKS.json; TF32 = bf16 / 2)"}
     return p
 
 
@@ -107,8 +111,10 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# (timed entry point, (B, C, H, W)) -> DRAM bytes per launch measured with `ncu --set full` (profiles/)
-NCU_DRAM_BYTES = {("correlation_planes_forward_into", (16, 256, 64, 128)): 281336576 + 196153088}
+# (timed entry point, (B, C, H, W), tensor-core kernel?) -> DRAM bytes per launch measured with `ncu --set full` (profiles/)
+NCU_DRAM_BYTES = {("correlation_planes_forward_into", (16, 256, 64, 128), False): (281336576 + 196153088, "profiles/ncu_corr_fwd_nhwc_b16_r01.txt"),
+                  ("correlation_planes_forward_into", (16, 256, 64, 128), True): (273361920 + 191170304, "profiles/ncu_corr_fwd_tc_b16_r02.txt")}
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12        # 74.5
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -248,6 +254,9 @@ def ops_table(pk, ffma):
                   "bound": v["bound"], "frac": round(v["frac"], 4),
                   "achieved": round(v.get("achieved_gbs", v.get("achieved_tflops", 0.0)), 2),
                   "unit": "GB/s" if v["bound"] == "hbm" else "TFLOP/s"}
+        for extra in ("frac_executed", "executed_tflops", "x_fp32_pipe_peak"):
+            if extra in v:
+                out[k][extra] = round(v[extra], 4)
         if "cpu_reference_us" in v:
             out[k]["cpu_reference_us"] = round(v["cpu_reference_us"], 1)
             out[k]["cpu_threads"] = v["cpu_threads"]
@@ -306,7 +315,10 @@ def main():
     hconf = torch.empty(B_local, 1, H, W).pin_memory()
 
     launches = Launches()
+    ffma_idle = None
     if args.impl == "native":
+        from ir2rgb_b200 import functional as F0
+        ffma_idle = F0.ffma_peak_tflops()            # FP32-FMA pipe peak on the idle, cool GPU (before any step has run)
         launches.install()
         torch.manual_seed(0)
         net = build_native(device, args.memory_format)
@@ -380,26 +392,40 @@ def main():
                                 "sample": "reference operators are CUDA-only; this arm ran them on the GPU (see DESIGN.md)"}
     else:
         from ir2rgb_b200 import functional as F
-        ffma = F.ffma_peak_tflops()
-        # roofline of the dominant hand-written kernel in the step: Correlation forward (planarize + main)
+        from ir2rgb_b200 import _lib
+        ffma = F.ffma_peak_tflops()                  # the same probe right after the steps (board warm, usually power-capped)
+        tc_on = bool(_lib.load().flowops_corr_get_impl() & 1)
+        # roofline of the operator BASELINE.json's metric names: Correlation forward, timed live inside one eager step
         if corr_events:
             us = [ev[0].elapsed_time(ev[1]) * 1e3 for ev in corr_events]
             shp = corr_events[0][2]
             split = corr_events[0][3].startswith("correlation_planes_forward")
-            flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]
+            flop = 2.0 * shp[0] * shp[2] * shp[3] * 441 * shp[1]          # algorithmic (useful) flops: 2*B*H*W*441*C
             mean_us = sum(us) / len(us)
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this launch shape, from the committed
-            # `ncu --set full` capture (tools/profile_target.py corr_fwd_nhwc_b16); algorithmic bytes are 499.1 MB
-            traffic = NCU_DRAM_BYTES.get((corr_events[0][3], tuple(shp)))
-            line["roofline"] = {"kernel": "corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split
-                                          else "corr_fwd (corr_planarize + corr_fwd_fast)", "bound": "fp32",
-                                "achieved": flop / mean_us / 1e6, "peak": ffma, "unit": "TFLOP/s",
-                                "frac": flop / mean_us / 1e6 / ffma, "traffic": traffic,
-                                "traffic_source": "profiles/ncu_corr_fwd_nhwc_b16_r01.txt (bytes per launch)" if traffic else None,
-                                "peak_source": "flowops_bench_ffma measured on this GPU (nominal 74.4)",
-                                "alg_flop_per_launch": flop, "us_per_launch": mean_us, "launches_timed": len(us),
-                                "share_of_step": sum(us) / (ms_eager * 1e3),
-                                "timed_in": "one eagerly launched step of the same workload (the timed steps replay these kernels from a CUDA graph)"}
+            traffic, traffic_src = NCU_DRAM_BYTES.get((corr_events[0][3], tuple(shp), tc_on), (None, None))
+            common = {"alg_flop_per_launch": flop, "us_per_launch": mean_us, "launches_timed": len(us),
+                      "share_of_step": sum(us) / (ms_eager * 1e3), "traffic": traffic, "traffic_source": traffic_src,
+                      "fp32_peak": {"idle": ffma_idle, "after_steps": ffma, "nominal": FP32_NOMINAL_TFLOPS,
+                                    "source": "flowops_bench_ffma in this process, before the first step and after the timed steps"},
+                      "timed_in": "one eagerly launched step of the same workload (the timed steps replay these kernels from a CUDA graph)"}
+            if tc_on:
+                # tcgen05 kernel (csrc/corr_tc.cu).  `achieved` counts ALGORITHMIC flops; the tensor pipe executes
+                # 3 (3xTF32) x 1024/441 (dense 128 x 256 UMMA tiles around a banded contraction) = 6.97x as many.
+                executed = flop * 3.0 * 1024.0 / 441.0
+                line["roofline"] = dict(common, kernel="corr_fwd_tc (tcgen05 3xTF32; input planes are written by the conv3 epilogue kernel)",
+                                        bound="tensor", achieved=flop / mean_us / 1e6, peak=pk["tf32_tflops"], unit="TFLOP/s",
+                                        frac=flop / mean_us / 1e6 / pk["tf32_tflops"],
+                                        peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                                        executed_tflops=executed / mean_us / 1e6, frac_executed=executed / mean_us / 1e6 / pk["tf32_tflops"],
+                                        executed_over_algorithmic=3.0 * 1024.0 / 441.0,
+                                        x_fp32_pipe_peak=flop / mean_us / 1e6 / max(ffma_idle or ffma, ffma),
+                                        note="algorithmic throughput exceeds what any FP32-FMA kernel can reach when x_fp32_pipe_peak > 1")
+            else:
+                line["roofline"] = dict(common, kernel="corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split
+                                        else "corr_fwd (corr_planarize + corr_fwd_fast)", bound="fp32",
+                                        achieved=flop / mean_us / 1e6, peak=ffma, unit="TFLOP/s", frac=flop / mean_us / 1e6 / ffma,
+                                        peak_idle=ffma_idle, peak_in_step=ffma, frac_vs_nominal=flop / mean_us / 1e6 / FP32_NOMINAL_TFLOPS,
+                                        peak_source="flowops_bench_ffma measured on this GPU after the steps (nominal 74.5)")
         # the largest hand-written kernel family of the step by time (ncu launch list: bias_lrelu_nhwc ~12 % of GPU time):
         # the in-place bias + LeakyReLU epilogue that follows every convolution -- HBM-bound, 8 bytes per element
         if launches.epi_events:
@@ -412,7 +438,7 @@ def main():
                                          "launches_timed": len(us), "share_of_step": sum(us) / (ms_eager * 1e3),
                                          "timed_in": "the same eagerly launched step; launches are back to back with cuDNN kernels, "
                                                      "so part of each tensor is still in L2 when its epilogue runs"}
-        line["peaks"] = dict(pk, ffma_tflops=ffma)
+        line["peaks"] = dict(pk, ffma_tflops=ffma, ffma_tflops_idle=ffma_idle, ffma_tflops_nominal=FP32_NOMINAL_TFLOPS)
         if not args.no_ops:
             try:
                 line["ops"] = ops_table(pk, ffma)
@@ -423,6 +449,19 @@ def main():
                 line["cpu_baseline"] = cpu_port_pairs_per_s()
             except Exception as e:
                 line["cpu_baseline"] = {"error": repr(e)}
+    if args.impl == "native" and world == 1 and not args.no_vid2vid:
+        # BASELINE configs[4]: one vid2vid training iteration (FlowNet2 flow + warp losses through the new operators),
+        # 1 GPU here; the 8-GPU data-parallel run is tools/bench_vid2vid_step.py under torchrun.  Own process: the
+        # 365 M-parameter generator needs the memory this one still holds.
+        try:
+            del net, im1, im2
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_vid2vid_step.py"), "--iters", "5"],
+                               capture_output=True, text=True, timeout=600)
+            rec = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            line["extra"] = {"vid2vid_step": json.loads(rec[-1])} if rec else {"vid2vid_step": {"error": r.stderr[-400:]}}
+        except Exception as e:
+            line["extra"] = {"vid2vid_step": {"error": repr(e)}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -84,7 +84,11 @@ int flowops_warp_bwd(const float *img, const float *flow, const float *gout,
  *                      owns (plain adds, dense vector reductions on flush) instead of one L2 reduction per contribution;
  *                      same values up to the summation order (backward tolerance 1e-4).  Needs C <= 3, W % 4 == 0.
  *                      Faster on incoherent flows (per-pixel noise), slower on smooth ones -- hence off by default.
- *   bit 1 (default 0)  reserved for the tolerance-mode forward blend.
+ *   bit 1 (default 0)  tolerance mode of the RESAMPLE2D forward (flowops_warp_fwd with C <= 3 and the fused glue kernels
+ *                      below): bilinear weights and blend in fp32.  The reference forms three of its four weight products
+ *                      in fp64 by accident of a `1.` literal (resample2d_kernel.cu:55-58); the default path reproduces
+ *                      that bit for bit at the price of 20 fp64 conversions per pixel.  The fp32 blend differs from it
+ *                      by ~1e-7 max-relative (tolerance 1e-5).
  * No reference counterpart. */
 int flowops_warp_set_impl(int flags);
 int flowops_warp_get_impl(void);

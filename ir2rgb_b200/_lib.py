@@ -89,11 +89,18 @@ KERNELS_PER_CALL = {"corr_fwd": 2, "corr_fwd_16": 2, "corr_bwd": 6, "warp_bwd": 
 launch_hook = None          # callable(what, n_kernels) or None
 
 
+def kernels_per_call(what):
+    n = KERNELS_PER_CALL.get(what, 1)
+    if what == "corr_fwd" and _lib is not None and (_lib.flowops_corr_get_impl() & 1):
+        n = 3          # tensor-core path of an eligible shape: layout pass, UMMA kernel, NCHW store pass
+    return n
+
+
 def check(rc, what):
     """Turn a non-zero return into a RuntimeError, like the reference's AT_ERROR
     (correlation_cuda.cc:81-83)."""
     if launch_hook is not None and rc == 0:
-        launch_hook(what, KERNELS_PER_CALL.get(what, 1))
+        launch_hook(what, kernels_per_call(what))
     if rc != 0:
         msg = load().flowops_last_error().decode("utf-8", "replace")
         if rc == -2:

@@ -126,7 +126,10 @@ extern "C" int flowops_warp_diff_norm_fwd(const float *img0, const float *img1, 
         a.out = warped; a.out_bs = warped_batch_stride; a.aux = norm; a.aux_bs = norm_batch_stride;
         a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
         a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
-        if (warped) launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_DIFF_NORM, true>(a, st);
+        if (warp_impl_flags() & 2) {       // tolerance mode: fp32 bilinear weights (flowops_warp_set_impl)
+            if (warped) launch_warp_rows<kWarpResample2dF32, EPI_DIFF_NORM, true>(a, st);
+            else launch_warp_rows<kWarpResample2dF32, EPI_DIFF_NORM, false>(a, st);
+        } else if (warped) launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_DIFF_NORM, true>(a, st);
         else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_DIFF_NORM, false>(a, st);
         return check_launch("warp_diff_norm_fwd");
     }
@@ -169,6 +172,7 @@ extern "C" int flowops_warp_conf_fwd(const float *im1, const float *im2, const f
         a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
         a.lin_x = lin_x; a.lin_y = lin_y; a.invx = invx; a.invy = invy; a.thresh = thresh;
         if (mode == FLOWOPS_WARP_GRIDSAMPLE) launch_warp_rows<FLOWOPS_WARP_GRIDSAMPLE, EPI_CONF, false>(a, st);
+        else if (warp_impl_flags() & 2) launch_warp_rows<kWarpResample2dF32, EPI_CONF, false>(a, st);
         else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONF, false>(a, st);
         return check_launch("warp_conf_fwd");
     }
@@ -194,7 +198,8 @@ extern "C" int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *f
     a.aux = out; a.aux_bs = hw * c_dst; a.c_dst = c_dst; a.inv_div_flow = 1.0f / div_flow;
     a.B = B; a.C = 3; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
     a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
-    launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONCAT, false>(a, (cudaStream_t)stream);
+    if (warp_impl_flags() & 2) launch_warp_rows<kWarpResample2dF32, EPI_CONCAT, false>(a, (cudaStream_t)stream);
+    else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONCAT, false>(a, (cudaStream_t)stream);
     return check_launch("warp_diff_norm_concat_nhwc");
 }
 
@@ -223,6 +228,7 @@ struct FusionInputArgs {
 #ifndef FLOWOPS_TUNE_FUSION_MINBLOCKS       // variant builds: python -m ir2rgb_b200.build --out ... -DFLOWOPS_TUNE_FUSION_MINBLOCKS=4
 #define FLOWOPS_TUNE_FUSION_MINBLOCKS 3     // 80 registers, 3 CTAs per SM (ncu: latency-bound at 34 % occupancy)
 #endif
+template <int MODE>      // FLOWOPS_WARP_RESAMPLE2D (the reference's mixed fp64 / fp32 blend, bit-exact) or kWarpResample2dF32
 __global__ void __launch_bounds__(256, FLOWOPS_TUNE_FUSION_MINBLOCKS) fusion_input_kernel(const __grid_constant__ FusionInputArgs a)
 {
     const WarpArgs &g = a.g;
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(256, FLOWOPS_TUNE_FUSION_MINBLOCKS) fusion_inp
         const float s2x = __fmul_rn(__ldg(ls2 + pl), a.mul_s2), s2y = __fmul_rn(__ldg(ls2 + pl + hwl), a.mul_s2);
         const float sdx = __fmul_rn(__ldg(lsd + pl), a.mul_sd), sdy = __fmul_rn(__ldg(lsd + pl + hwl), a.mul_sd);
         const float yfl = small_int_as_float(y);
-        PixPrep<FLOWOPS_WARP_RESAMPLE2D> qd, q2;
+        PixPrep<MODE> qd, q2;
         pix_prep(qd, g, xfl, yfl, x, y, sdx, sdy);
         pix_prep(q2, g, xfl, yfl, x, y, s2x, s2y);
         PixVals<3> vd, v2;
@@ -294,7 +300,8 @@ extern "C" int flowops_flownet2_fusion_input_nhwc(const float *x, const float *f
         c.lo_s2 = flow2_s2 + (size_t)b0 * 2 * (hw / 16); c.lo_sd = flow2_sd + (size_t)b0 * 2 * (hw / 16);
         dim3 grid, block;
         warp_rows_shape(c.g.B, H, W, c.g.rows, grid, block);
-        fusion_input_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(c);
+        if (warp_impl_flags() & 2) fusion_input_kernel<kWarpResample2dF32><<<grid, block, 0, (cudaStream_t)stream>>>(c);
+        else fusion_input_kernel<FLOWOPS_WARP_RESAMPLE2D><<<grid, block, 0, (cudaStream_t)stream>>>(c);
     }
     return check_launch("flownet2_fusion_input_nhwc");
 }

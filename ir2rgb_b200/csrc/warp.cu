@@ -33,7 +33,7 @@ namespace flowops {
 // operations 4x but only wins on incoherent flows), bit 1 = forward blend with fp32 weights instead of the
 // reference's accidental fp64 weight products (tolerance mode, see flowops.h; default off)
 static int g_warp_impl = -1;
-static int warp_impl_flags()
+int warp_impl_flags()
 {
     if (g_warp_impl < 0) {
         const char *e = getenv("FLOWOPS_WARP_IMPL");
@@ -344,8 +344,11 @@ extern "C" int flowops_warp_fwd(const float *img, const float *flow, float *out,
     if (rc) return rc;
     FLOWOPS_REQUIRE(out, FLOWOPS_EINVAL, "warp_fwd: null output");
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == FLOWOPS_WARP_RESAMPLE2D)
+    if (mode == FLOWOPS_WARP_RESAMPLE2D) {
+        if (C <= 3 && (warp_impl_flags() & 2))         // tolerance mode: fp32 weights (row-walking kernel only)
+            return launch_fwd<kWarpResample2dF32>(img, flow, out, B, C, H, W, nullptr, nullptr, 0.f, 0.f, st);
         return launch_fwd<FLOWOPS_WARP_RESAMPLE2D>(img, flow, out, B, C, H, W, nullptr, nullptr, 0.f, 0.f, st);
+    }
     float invx, invy, mulx, muly;
     gs_scales(H, W, invx, invy, mulx, muly);
     return launch_fwd<FLOWOPS_WARP_GRIDSAMPLE>(img, flow, out, B, C, H, W, lin_x, lin_y, invx, invy, st);

@@ -4,6 +4,9 @@
 
 namespace flowops {
 
+// process-wide switches of the warp kernels (flowops_warp_set_impl; defined in warp.cu)
+int warp_impl_flags();
+
 struct Corners {
     int o_tl, o_tr, o_bl, o_br;   // offsets inside one H*W plane
 };

@@ -63,6 +63,16 @@ template <> struct PixPrep<FLOWOPS_WARP_RESAMPLE2D> {
     bool ex;                // xR == xL + 1 (false when both clamp to the same border column)
     R2dWeights w;
 };
+// Tolerance mode of RESAMPLE2D (internal; flowops_warp_set_impl bit 1): the same coordinates and corners, but the
+// bilinear weights and the blend stay in fp32 -- the reference's three fp64 weight products are an accident of a
+// `1.` literal (resample2d_kernel.cu:55-58), they cost 20 F2F conversions per pixel on the quarter-rate XU pipe, and the
+// contract for floating point is max-relative 1e-5, which an fp32 blend meets by two orders of magnitude.
+constexpr int kWarpResample2dF32 = 2;
+template <> struct PixPrep<kWarpResample2dF32> {
+    unsigned o_t, o_b;
+    bool ex;
+    float w_tl, w_tr, w_bl, w_br;
+};
 template <> struct PixPrep<FLOWOPS_WARP_GRIDSAMPLE> {
     unsigned o_t, o_b;      // iy_nw*W + ix_nw, and the row below (same row when it is out of bounds: never read)
     bool in_e, in_s;
@@ -90,6 +100,23 @@ __device__ __forceinline__ void pix_prep(PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q, co
     const double wa = 1. - (double)alpha, wb = 1. - (double)beta;
     q.w.w_tl = wa * wb; q.w.w_tr = (double)alpha * wb; q.w.w_bl = wa * (double)beta;
     q.w.w_br = __fmul_rn(alpha, beta);
+}
+
+__device__ __forceinline__ void pix_prep(PixPrep<kWarpResample2dF32> &q, const WarpArgs &a, float xfl, float yfl,
+                                         int /*x*/, int /*y*/, float dx, float dy)
+{
+    const float xf = __fadd_rn(xfl, dx), yf = __fadd_rn(yfl, dy);
+    float fx = __fsub_rn(__fadd_rn(xf, kMagic15), kMagic15); fx = fx > xf ? __fsub_rn(fx, 1.f) : fx;
+    float fy = __fsub_rn(__fadd_rn(yf, kMagic15), kMagic15); fy = fy > yf ? __fsub_rn(fy, 1.f) : fy;
+    if (__builtin_expect(!(fmaxf(fabsf(xf), fabsf(yf)) < 4194304.f), 0)) { fx = floorf(xf); fy = floorf(yf); }
+    const unsigned xL = (unsigned)small_float_as_int(fminf(fmaxf(fx, 0.f), a.wm1));
+    const unsigned yT = (unsigned)small_float_as_int(fminf(fmaxf(fy, 0.f), a.hm1));
+    q.ex = fx >= 0.f && fx < a.wm1;
+    q.o_t = yT * (unsigned)a.W + xL;
+    q.o_b = (fy >= 0.f && fy < a.hm1) ? q.o_t + (unsigned)a.W : q.o_t;
+    const float alpha = __fsub_rn(xf, fx), beta = __fsub_rn(yf, fy);
+    const float wa = 1.f - alpha, wb = 1.f - beta;
+    q.w_tl = wa * wb; q.w_tr = alpha * wb; q.w_bl = wa * beta; q.w_br = alpha * beta;
 }
 
 // models/networks.py:97-98 + ATen grid_sampler (align_corners=False, border); see gs_coords / gs_weights.
@@ -139,6 +166,22 @@ __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS
     }
 }
 template <int CT, bool NEED_REF, bool NEED_SELF>
+__device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<kWarpResample2dF32> &q,
+                                           const float *__restrict__ src, const float *__restrict__ ref,
+                                           const float *__restrict__ self, unsigned hw)
+{
+    const float *pt = src + q.o_t, *pb = src + q.o_b;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        g.v[c][0] = __ldg(pt); g.v[c][2] = __ldg(pb);
+        g.v[c][1] = q.ex ? __ldg(pt + 1) : 0.f;
+        g.v[c][3] = q.ex ? __ldg(pb + 1) : 0.f;
+        if (NEED_REF) { g.r[c] = ldg_stream(ref); ref += hw; }
+        if (NEED_SELF) { g.s[c] = __ldg(self); self += hw; }
+        pt += hw; pb += hw;
+    }
+}
+template <int CT, bool NEED_REF, bool NEED_SELF>
 __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q,
                                            const float *__restrict__ src, const float *__restrict__ ref,
                                            const float *__restrict__ /*self*/, unsigned hw)
@@ -158,6 +201,13 @@ __device__ __forceinline__ void pix_gather(PixVals<CT> &g, const PixPrep<FLOWOPS
 __device__ __forceinline__ float pix_blend(const PixPrep<FLOWOPS_WARP_RESAMPLE2D> &q, const float (&v)[4])
 {
     return r2d_blend(q.w, v[0], q.ex ? v[1] : v[0], v[2], q.ex ? v[3] : v[2]);
+}
+__device__ __forceinline__ float pix_blend(const PixPrep<kWarpResample2dF32> &q, const float (&v)[4])
+{
+    float val = q.w_tl * v[0];
+    val = __fmaf_rn(q.w_tr, q.ex ? v[1] : v[0], val);
+    val = __fmaf_rn(q.w_bl, v[2], val);
+    return __fmaf_rn(q.w_br, q.ex ? v[3] : v[2], val);
 }
 // out_acc += val * weight in nw, ne, sw, se order, skipping out-of-bounds corners (ATen grid_sampler_2d_kernel)
 __device__ __forceinline__ float pix_blend(const PixPrep<FLOWOPS_WARP_GRIDSAMPLE> &q, const float (&v)[4])

@@ -121,6 +121,26 @@ def _warp_args(img, flow, mode, dtype=torch.float32):
     return img.contiguous(), flow.contiguous(), B, C, H, W, lx, ly
 
 
+class warp_tolerance_mode:
+    """Context manager: inside it the RESAMPLE2D forward (Resample2d with up to 3 channels and the fused FlowNet2 glue)
+    blends with fp32 weights instead of reproducing the reference's accidental fp64 weight products bit for bit
+    (resample2d_kernel.cu:55-58) -- ~1e-7 max-relative away from the reference kernel (tolerance 1e-5), without the 20
+    fp64 conversions per pixel.  Process-wide switch of the library (flowops_warp_set_impl bit 1), restored on exit."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        lib = _lib.load()
+        self.prev = lib.flowops_warp_get_impl()
+        lib.flowops_warp_set_impl((self.prev | 2) if self.on else (self.prev & ~2))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().flowops_warp_set_impl(self.prev)
+        return False
+
+
 def warp_forward(img, flow, mode=WARP_RESAMPLE2D):
     """fp32 tensors, or image and flow both fp16 / both bf16 (1..3 channels): then one kernel does what the reference's
     fp16 mode spreads over casts -- fp16_resample2d (models.py:22-28) for RESAMPLE2D, Model.resample with opt['fp16']
@@ -294,8 +314,9 @@ class ConcatBuffer:
     read the buffer use weights zero-padded to match (networks/submodules.py), so results are those of the
     unpadded concat."""
 
-    def __init__(self, like, c_total, pad_to=8):
-        B, _, H, W = like.shape
+    def __init__(self, like, c_total, pad_to=8, shape=None):
+        """like: a tensor giving batch, spatial size and device -- or, with shape=(B, H, W), only the device."""
+        B, _, H, W = like.shape if shape is None else (shape[0], 0, shape[1], shape[2])
         self.c_total = c_total
         self.c_pad = -(-c_total // pad_to) * pad_to
         self.n_pixels = B * H * W

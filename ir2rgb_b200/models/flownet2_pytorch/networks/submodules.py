@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .... import cudnn_fused as _cf
 from .... import functional as _F
 
 LEAK = 0.1
@@ -51,6 +52,11 @@ def reset_padded_weights(net):
     """Drop every cached zero-padded weight of `net` (needed after weight updates made through `.data`)."""
     for m in net.modules():
         m.__dict__.pop("_flowops_wpad", None)
+
+
+def _conv_out_hw(conv, x):
+    return tuple((x.shape[2 + i] + 2 * conv.padding[i] - conv.dilation[i] * (conv.kernel_size[i] - 1) - 1) // conv.stride[i] + 1
+                 for i in range(2))
 
 
 def _raw_conv(conv, x, bias):
@@ -100,6 +106,39 @@ class ConvAct(nn.Sequential):
     def forward(self, x, into=None, skip=None):
         conv = self[0]
         if self.fusable(x):
+            sbuf = None
+            if isinstance(conv, nn.Conv2d) and torch.backends.cudnn.allow_tf32 and _F._is_nhwc(x) and _cf.available():
+                # convolution + bias + LeakyReLU as ONE cuDNN runtime-fusion launch (TF32 math, as the unfused cuDNN
+                # convolution under the same setting) where that is faster than the two-kernel path -- decided per layer
+                # by timing both once; with TF32 off the bit-exact two-kernel path below runs
+                slope = self[1].negative_slope
+                out = None
+                if into is not None:
+                    buf, c_off = into
+                    out = buf.tensor[:, c_off:c_off + conv.out_channels] if c_off % 4 == 0 else None
+                if into is None or out is not None:
+                    after = None
+                    if skip is not None:
+                        # also a decoder skip connection: the fused launch writes the dense tensor, a copy puts it into
+                        # the level's concat buffer (the unfused epilogue writes both from one read)
+                        sbuf = _F.ConcatBuffer(x, skip.c_total(conv.out_channels), PAD_CHANNELS,
+                                               shape=(x.shape[0],) + _conv_out_hw(conv, x))
+                        after = lambda t: sbuf.copy_in(t, 0)
+
+                    def unfused():
+                        t = _raw_conv(conv, x, None)
+                        if into is not None:
+                            into[0].bias_lrelu_in(t, conv.bias, slope, into[1])
+                        elif skip is not None:
+                            sbuf.bias_lrelu_in(t, conv.bias, slope, 0, in_place_too=True)
+                        else:
+                            _F.bias_lrelu_(t, conv.bias, slope)
+                    y = _cf.conv_bias_lrelu(conv, x, padded_weight(conv, x.shape[1]), slope, out, unfused, after)
+                    if y is not NotImplemented:
+                        if skip is not None:
+                            after(y)
+                            skip.buf = sbuf
+                        return None if into is not None else y
             y = _raw_conv(conv, x, None)
             if into is not None:
                 buf, c_off = into
@@ -108,7 +147,7 @@ class ConvAct(nn.Sequential):
             if skip is not None and _F._is_nhwc(y):
                 # this output is also a decoder skip connection: allocate that level's concat buffer now and write the
                 # activated features to both places from one read
-                skip.buf = _F.ConcatBuffer(y, skip.c_total(y.shape[1]), PAD_CHANNELS)
+                skip.buf = sbuf if sbuf is not None else _F.ConcatBuffer(y, skip.c_total(y.shape[1]), PAD_CHANNELS)
                 skip.buf.bias_lrelu_in(y, conv.bias, self[1].negative_slope, 0, in_place_too=True)
                 return y
             return _F.bias_lrelu_(y, conv.bias, self[1].negative_slope)

@@ -280,9 +280,20 @@ def test_correlation16_vs_cast_chain(ops, dt, shape):
     corr = ops.Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)
     out = corr(a, b)
     assert out.dtype == dt and out.shape[1] == 441
-    chain32 = corr(a.float(), b.float())
-    # the fp32 arithmetic is the same kernel's: the 16-bit result is the rounded fp32 result, bit for bit
+    # the 16-bit entry point runs the FP32-FMA kernel: its result is that kernel's fp32 result rounded, bit for bit
+    from ir2rgb_b200 import _lib
+    lib = _lib.load()
+    prev = lib.flowops_corr_get_impl()
+    try:
+        lib.flowops_corr_set_impl(0)
+        chain32 = corr(a.float(), b.float())
+    finally:
+        lib.flowops_corr_set_impl(prev)
     assert torch.equal(out, chain32.to(dt))
+    # and agrees with the default fp32 path (the tensor-core kernel where the shape allows it) to 16-bit rounding
+    chain_default = corr(a.float(), b.float())
+    tol = 2.0 ** -10 if dt == torch.float16 else 2.0 ** -7
+    assert (out.float() - chain_default).abs().max().item() <= tol * chain_default.abs().max().item()
 
 
 def test_correlation16_vs_c_oracle_and_reference_ext(ops, c_oracle, ref):

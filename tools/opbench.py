@@ -18,11 +18,14 @@ from ir2rgb_b200 import functional as F  # noqa: E402
 
 
 def peaks():
-    p = {"hbm_gbs": 6650.0, "source": "fallback"}
+    """HBM copy bandwidth and the dense TF32 tensor peak.  MEASURED_PEAKS.json holds a measured bf16 GEMM rate; TF32 runs
+    at half the bf16 rate on the same pipe, so bf16 / 2 is the TF32 proxy (burst figure: kernels here are timed alone)."""
+    p = {"hbm_gbs": 6650.0, "tf32_tflops": 1590.0 / 2, "source": "fallback"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         m = json.load(open(path))
-        p = {"hbm_gbs": float(m["hbm_gbs"]), "source": "measured"}
+        p = {"hbm_gbs": float(m["hbm_gbs"]), "tf32_tflops": float(m["bf16_tflops"]) / 2,
+             "tf32_tflops_sustained": float(m.get("bf16_tflops_sustained", m["bf16_tflops"])) / 2, "source": "measured"}
     return p
 
 
@@ -84,7 +87,7 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
         if ref_ext.available():
             ref = ref_ext
 
-    def add(name, fn, args, ref_fn=None, alg_bytes=None, alg_flop=None, ref_iters=None):
+    def add(name, fn, args, ref_fn=None, alg_bytes=None, alg_flop=None, ref_iters=None, tensor_flop=None):
         """fn(*args) is the new operator, ref_fn(*args) the reference's.  Primary timing: back-to-back
         launches rotating among clones of `args` whose combined footprint exceeds 2x L2 (L2-cold, launch gap
         amortised); also reported: one launch per event pair with an L2 flush in between, and L2-warm."""
@@ -102,9 +105,16 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
         if alg_bytes is not None:
             e.update(bound="hbm", alg_bytes=alg_bytes, achieved_gbs=alg_bytes / mean / 1e3,
                      frac=alg_bytes / mean / 1e3 / pk["hbm_gbs"], frac_of_8TBs=alg_bytes / mean / 1e3 / 8000.0)
-        if alg_flop is not None:
+        if alg_flop is not None and tensor_flop is None:
             e.update(bound="fp32", alg_flop=alg_flop, achieved_tflops=alg_flop / mean / 1e6,
                      frac=alg_flop / mean / 1e6 / ffma)
+        if tensor_flop is not None:
+            # tcgen05 kernel: `achieved` counts the ALGORITHMIC (useful) flops, 2*B*H*W*441*C; the tensor pipe executes
+            # tensor_flop = 3 (3xTF32) x 1024/441 (dense 128 x 256 tiles around a banded contraction) times that
+            e.update(bound="tensor", alg_flop=alg_flop, achieved_tflops=alg_flop / mean / 1e6,
+                     frac=alg_flop / mean / 1e6 / pk["tf32_tflops"], executed_tflops=tensor_flop / mean / 1e6,
+                     frac_executed=tensor_flop / mean / 1e6 / pk["tf32_tflops"],
+                     x_fp32_pipe_peak=alg_flop / mean / 1e6 / ffma)
         if ref is not None and ref_fn is not None:
             rmean, rbest = time_op(lambda: ref_fn(*args), ref_iters or max(3, iters // 4), warmup=1, flush=flush)
             e.update(ref_us=rmean, speedup_vs_ref=rmean / single)
@@ -118,8 +128,25 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
     a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
     go = torch.randn(B, 441, H, W, device="cuda")
     flop = 2.0 * B * H * W * 441 * C
+    from ir2rgb_b200 import _lib
+    lib = _lib.load()
+    tc_on = bool(lib.flowops_corr_get_impl() & 1)
+    tc_x = 3.0 * 1024.0 / 441.0 if tc_on else None       # executed / useful flops of the tensor-core kernel
+
+    def with_impl(flags, f):
+        def g(*x):
+            prev = lib.flowops_corr_get_impl()
+            lib.flowops_corr_set_impl(flags)
+            try:
+                return f(*x)
+            finally:
+                lib.flowops_corr_set_impl(prev)
+        return g
     add("corr_fwd_c2", lambda a, b: F.correlation_forward(a, b, *P), (a, b),
-        (lambda a, b: ref.correlation_forward(a, b, *P)) if ref else None, alg_flop=flop)
+        (lambda a, b: ref.correlation_forward(a, b, *P)) if ref else None, alg_flop=flop,
+        tensor_flop=flop * tc_x if tc_on else None)
+    if tc_on:
+        add("corr_fwd_c2_fp32fma", with_impl(0, lambda a, b: F.correlation_forward(a, b, *P)), (a, b), None, alg_flop=flop)
     add("corr_bwd_c2", lambda a, b, go: F.correlation_backward(a, b, go, *P), (a, b, go),
         (lambda a, b, go: ref.correlation_backward(a, b, go, *P)) if ref else None, alg_flop=2 * flop, ref_iters=2)
     # ---- C4-shaped correlation (FlowNet2 at 512x1024, per-GPU batch 8) ----
@@ -127,7 +154,11 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
         a4, b4 = torch.randn(8, 256, 64, 128, device="cuda"), torch.randn(8, 256, 64, 128, device="cuda")
         add("corr_fwd_c4_b8", lambda a, b: F.correlation_forward(a, b, *P), (a4, b4),
             (lambda a, b: ref.correlation_forward(a, b, *P)) if ref else None,
-            alg_flop=2.0 * 8 * 64 * 128 * 441 * 256, ref_iters=2)
+            alg_flop=2.0 * 8 * 64 * 128 * 441 * 256, ref_iters=2,
+            tensor_flop=2.0 * 8 * 64 * 128 * 441 * 256 * tc_x if tc_on else None)
+        if tc_on:
+            add("corr_fwd_c4_b8_fp32fma", with_impl(0, lambda a, b: F.correlation_forward(a, b, *P)), (a4, b4), None,
+                alg_flop=2.0 * 8 * 64 * 128 * 441 * 256)
         del a4, b4
 
     # ---- C3: Resample2d + ChannelNorm on 16x3x512x1024 ----
@@ -148,6 +179,11 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
     for fl, flow in flows.items():
         add("resample2d_fwd_" + fl, lambda i, f: F.warp_forward(i, f, R2D), (img, flow),
             (lambda i, f: ref.resample2d_forward(i, f)) if ref else None, alg_bytes=8 * plane)
+        def _fast(i, f):
+            with F.warp_tolerance_mode(True):
+                return F.warp_forward(i, f, R2D)
+        # tolerance mode (fp32 bilinear weights; what FlowNet runs): ~1e-7 from the reference kernel instead of bit-exact
+        add("resample2d_fwd_fp32blend_" + fl, _fast, (img, flow), None, alg_bytes=8 * plane)
         add("resample2d_bwd_" + fl, lambda i, f, g: F.warp_backward(i, f, g, True, True, R2D), (img, flow, gout),
             (lambda i, f, g: ref.resample2d_backward(i, f, g)) if ref else None, alg_bytes=13 * plane)
         add("resample2d_bwd_flowonly_" + fl, lambda i, f, g: F.warp_backward(i, f, g, False, True, R2D), (img, flow, gout),

@@ -343,7 +343,10 @@ def main():
         from ir2rgb_b200.runtime import HostPipeline
         pipe = HostPipeline(net, device)
         mb_host = mb if B_local >= 2 * mb else max(1, B_local // 2)     # at least two micro-batches so copies overlap compute
-        e2e_step = lambda: pipe(h1, h2, mb_host, hflow, hconf)
+        # a stream of batches: the next batch's first copy-in and this batch's last copy-out run under computation
+        # (every step still copies all of its frames in and all of its results out inside the timed region; timed()
+        # synchronises the device, and with it both copy streams, before it stops the clock)
+        e2e_step = lambda: pipe(h1, h2, mb_host, hflow, hconf, next_inputs=(h1, h2), wait=False)
     else:
         e2e_step = lambda: run_step(net, h1, h2, mb, host_out=(hflow, hconf))
     ms_e2e = timed(e2e_step, max(1, args.steps), 1, dist, device)

@@ -265,6 +265,19 @@ def test_host_pipeline_matches_direct_calls(nets):
         for s in (0, 2, 4):
             f, c = nets(h1[s:s + 2].cuda(), h2[s:s + 2].cuda())
             assert torch.equal(hflow[s:s + 2], f.cpu()) and torch.equal(hconf[s:s + 2], c.cpu())
+        # a stream of batches: the next batch's first copy-in is issued by the previous call, the last copy-out is not
+        # waited for; a batch that was NOT announced (g1) must still be computed from its own frames
+        g1 = (2 * torch.rand(5, 3, 64, 128) - 1).pin_memory()
+        g2 = (2 * torch.rand(5, 3, 64, 128) - 1).pin_memory()
+        outs = [(torch.empty(5, 2, 64, 128).pin_memory(), torch.empty(5, 1, 64, 128).pin_memory()) for _ in range(3)]
+        pipe = HostPipeline(nets, torch.device("cuda", 0))
+        pipe(h1, h2, 2, *outs[0], next_inputs=(h1, h2), wait=False)
+        pipe(h1, h2, 2, *outs[1], next_inputs=(h1, h2), wait=False)      # prefetched
+        pipe(g1, g2, 2, *outs[2], wait=False)                            # announced h1, got g1: prefetch discarded
+        pipe.synchronize()
+        assert torch.equal(outs[0][0], hflow) and torch.equal(outs[1][0], hflow) and torch.equal(outs[1][1], hconf)
+        f, c = nets(g1[:2].cuda(), g2[:2].cuda())
+        assert torch.equal(outs[2][0][:2], f.cpu()) and torch.equal(outs[2][1][:2], c.cpu())
     finally:
         torch.backends.cudnn.deterministic = prev
 

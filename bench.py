@@ -207,11 +207,13 @@ def timed(fn, steps, warmup, dist, device):
         dist.barrier()
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("bench_timed")       # ncu --nvtx --nvtx-include "bench_timed/" lists exactly these launches
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
     torch.cuda.synchronize(device)
+    torch.cuda.nvtx.range_pop()
     if dist is not None:
         dist.barrier()
     ms = e0.elapsed_time(e1)

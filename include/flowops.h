@@ -191,6 +191,14 @@ int flowops_warp_conf_fwd(const float *im1, const float *im2, const float *flow,
 int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *flow, float div_flow, float *out, int c_dst,
                                        int B, int H, int W, void *stream);
 
+/* flowops_warp_diff_norm_concat_nhwc with the producer of the flow folded in: flow = nn.Upsample(scale_factor=4,
+ * mode='bilinear')(flow_lo * flow_mul) (models.py:106,118 -- the previous sub-network's quarter-resolution flow2 times
+ * div_flow) is formed inside the kernel from flow_lo [B,2,H/4,W/4]; the full-resolution flow is never materialised.
+ * Same values as upsampling with torch first and calling the function above, up to the FMA contraction of the
+ * bilinear blend (<= 1e-6 max-relative on the flow channels; tests/test_flownet_gpu.py).  H, W multiples of 4. */
+int flowops_warp_diff_norm_concat_up4_nhwc(const float *x, const float *flow_lo, float flow_mul, float div_flow,
+                                           float *out, int c_dst, int B, int H, int W, void *stream);
+
 /* The input of the fusion network, models.py:129-152, in one pass, channels-last:
  *   out[b,y,x, 0:11] = (frame 0, flow_sd, flow_s2, ChannelNorm(flow_sd), ChannelNorm(flow_s2),
  *                       ChannelNorm(frame 0 - Resample2d(frame 1, flow_sd)), ChannelNorm(frame 0 - Resample2d(frame 1, flow_s2))),
@@ -280,6 +288,14 @@ int flowops_fill_channels_nhwc(float *dst, size_t n_pixels, int c_dst, int c_off
  * [c_off, c_off + c_src) of dst ([n_pixels][c_dst]).  One call per concatenated tensor (torch.cat of the
  * decoder skip connections, e.g. FlowNetS.py:74). */
 int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels, int c_src, int c_dst, int c_off, void *stream);
+
+/* The decoders' flow upsamplers -- ConvTranspose2d(2, 2, kernel 4, stride 2, padding 1[, bias]) on a dense channels-last
+ * 2-channel flow [B, h, w, 2] (FlowNetS.py:46-49 `upsampled_flow6_to_5` ...; weight [2, 2, 4, 4] contiguous, bias [2] or
+ * NULL) -- written into channels [c_off, c_off + 2) of the channels-last concat buffer dst [B, 2h, 2w, c_dst] (c_off, c_dst
+ * even).  Replaces cuDNN's strided-dgrad launch with its channel-padding kernels, the bias pass and the copy into the
+ * buffer. */
+int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const float *bias, float *dst,
+                                int B, int h, int w, int c_dst, int c_off, void *stream);
 
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 

@@ -191,3 +191,69 @@ extern "C" int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels
         copy_channels_nhwc<float><<<grid_for(total), 256, 0, st>>>(src, dst, total, c_src, c_dst, c_off);
     return check_launch("concat_nhwc");
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// The decoders' flow upsamplers: ConvTranspose2d(2, 2, kernel 4, stride 2, padding 1) on the 2-channel flow
+// (FlowNetS.py:46-49,75-88 `upsampled_flow6_to_5` ...), written straight into its 2-channel slice of the next level's
+// channels-last concat buffer.  16 multiply-adds per output pixel: cuDNN answers this layer with a strided-dgrad GEMM
+// kernel plus channel-padding kernels on both sides, followed here by a bias pass and a copy into the concat buffer --
+// five launches for what is one small gather.
+//   out[b, 2m+py, 2n+px, c_off+co] = bias[co] + sum_ci sum_{t,u in 0..1} in[b, m-1+py+t, n-1+px+u, ci] * w[ci, co, ky(py,t), kx(px,u)]
+//   with ky(0,.) = (3, 1), ky(1,.) = (2, 0)  (see cudnn_fused.py for the derivation); out-of-range input reads as zero.
+// Accumulation order: ci outer, taps inner, fp32 FMAs (cuDNN's order for this layer is unspecified; the operator
+// tolerance applies, tests/test_flownet_gpu.py).
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+__global__ void __launch_bounds__(256) flow_deconv_nhwc_kernel(const float2 *__restrict__ in, const float *__restrict__ wgt,
+                                                               const float *__restrict__ bias, float *__restrict__ dst,
+                                                               int B, int h, int w, unsigned c_dst, unsigned c_off)
+{
+    __shared__ float sw[64];                      // [ci][co][ky][kx]
+    if (threadIdx.x < 64) sw[threadIdx.x] = wgt[threadIdx.x];
+    __syncthreads();
+    const int W2 = 2 * w, H2 = 2 * h;
+    const size_t total = (size_t)B * H2 * W2;
+    const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % W2);
+        const size_t r = i / W2;
+        const int oy = (int)(r % H2), b = (int)(r / H2);
+        const int py = oy & 1, px = ox & 1, m = oy >> 1, n = ox >> 1;
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int iy = m - 1 + py + t, ky = py ? (t ? 0 : 2) : (t ? 1 : 3);
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int ix = n - 1 + px + u, kx = px ? (u ? 0 : 2) : (u ? 1 : 3);
+                if (ix < 0 || ix >= w) continue;
+                const float2 v = __ldg(in + ((size_t)b * h + iy) * w + ix);
+                const int k = ky * 4 + kx;
+                a0 = __fmaf_rn(v.x, sw[k], a0);      a1 = __fmaf_rn(v.x, sw[16 + k], a1);        // ci = 0 -> co = 0, 1
+                a0 = __fmaf_rn(v.y, sw[32 + k], a0); a1 = __fmaf_rn(v.y, sw[48 + k], a1);        // ci = 1
+            }
+        }
+        *reinterpret_cast<float2 *>(dst + i * c_dst + c_off) = make_float2(a0, a1);
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const float *bias, float *dst,
+                                           int B, int h, int w, int c_dst, int c_off, void *stream)
+{
+    FLOWOPS_REQUIRE(flow && weight && dst, FLOWOPS_EINVAL, "flow_deconv_nhwc_to: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && h > 0 && w > 0 && c_off >= 0 && c_off + 2 <= c_dst && ((c_off | c_dst) & 1) == 0, FLOWOPS_EINVAL,
+                    "flow_deconv_nhwc_to: bad shape / channel range (%d, %d x %d, channels %d + 2 of %d; offsets must be even)", B, h, w, c_off, c_dst);
+    FLOWOPS_REQUIRE((((uintptr_t)flow | (uintptr_t)dst) & 7) == 0, FLOWOPS_EINVAL, "flow_deconv_nhwc_to: 8-byte alignment required");
+    const size_t total = (size_t)B * 4 * h * w;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 8;
+    if (blocks > cap) blocks = cap;
+    flow_deconv_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(flow), weight, bias, dst,
+                                                                                  B, h, w, (unsigned)c_dst, (unsigned)c_off);
+    return check_launch("flow_deconv_nhwc_to");
+}

@@ -203,6 +203,31 @@ extern "C" int flowops_warp_diff_norm_concat_nhwc(const float *x, const float *f
     return check_launch("warp_diff_norm_concat_nhwc");
 }
 
+// The same concat with the x4 bilinear upsampling and the scaling of the previous sub-network's flow folded in
+// (models.py:106,118: upsample(flownet(x)[0] * div_flow)): the kernel forms the full-resolution flow from the
+// quarter-resolution field while it walks the rows, so the full-resolution flow tensor is never written or read.
+extern "C" int flowops_warp_diff_norm_concat_up4_nhwc(const float *x, const float *flow_lo, float flow_mul, float div_flow,
+                                                      float *out, int c_dst, int B, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(x && flow_lo && out, FLOWOPS_EINVAL, "warp_diff_norm_concat_up4_nhwc: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 3) == 0 && (W & 3) == 0, FLOWOPS_EINVAL,
+                    "warp_diff_norm_concat_up4_nhwc: bad shape %dx%dx%d (H, W must be multiples of 4)", B, H, W);
+    FLOWOPS_REQUIRE(c_dst >= 12 && (c_dst & 3) == 0 && aligned16(out), FLOWOPS_EINVAL,
+                    "warp_diff_norm_concat_up4_nhwc: c_dst must be a multiple of 4 and at least 12, out 16-byte aligned");
+    FLOWOPS_REQUIRE((size_t)6 * H * W < (1ull << 31) && H <= (1 << 22) && W <= (1 << 22), FLOWOPS_EUNSUPPORTED,
+                    "warp_diff_norm_concat_up4_nhwc: frame too large for int32 indexing");
+    const size_t hw = (size_t)H * W;
+    WarpArgs a{};
+    a.img = x + 3 * hw; a.img_bs = 6 * hw; a.flow = nullptr; a.ref = x; a.ref_bs = 6 * hw;
+    a.flow_lo = flow_lo; a.flow_mul = flow_mul;
+    a.aux = out; a.aux_bs = hw * c_dst; a.c_dst = c_dst; a.inv_div_flow = 1.0f / div_flow;
+    a.B = B; a.C = 3; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
+    a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
+    if (warp_impl_flags() & 2) launch_warp_rows<kWarpResample2dF32, EPI_CONCAT, false, true>(a, (cudaStream_t)stream);
+    else launch_warp_rows<FLOWOPS_WARP_RESAMPLE2D, EPI_CONCAT, false, true>(a, (cudaStream_t)stream);
+    return check_launch("warp_diff_norm_concat_up4_nhwc");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Input of the fusion network (models.py:129-152), one pass, channels-last:
 //   flow_s2 = upsample4(flow2_s2 * div_flow)      flow_sd = upsample3(flow2_sd / div_flow)        (nearest, x4)

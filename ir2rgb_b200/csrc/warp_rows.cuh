@@ -47,7 +47,44 @@ struct WarpArgs {
     int c_dst;                           // CONCAT: channels per pixel of the channels-last destination
     float inv_div_flow;                  // CONCAT: the flow is stored times 1/div_flow (models.py:112; torch divides a CUDA
                                          // tensor by a Python scalar as a multiply by the fp32 reciprocal)
+    const float *flow_lo;                // UP4: [B,2,H/4,W/4] network-unit flow; the kernel forms
+    float flow_mul;                      //      upsample_bilinear_x4(flow_lo * flow_mul) itself (models.py:106,118)
 };
+
+// nn.Upsample(scale_factor=4, mode='bilinear') (align_corners=False) of (lo * mul) at full-resolution pixel (x, y):
+// ATen upsample_bilinear2d -- source index 0.25 * (dst + 0.5) - 0.5 clamped at 0, neighbour +1 unless at the last
+// row / column, value = h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11).  Index and weights are exact in
+// fp32 (multiples of 1/8); the blend differs from ATen's compiled kernel at most in FMA contraction (<= 2 ulp).
+struct Up4Col { unsigned x1; unsigned x1p; float w0, w1; };
+__device__ __forceinline__ Up4Col up4_col(int x, int Wl)
+{
+    Up4Col c;
+    float sx = __fmaf_rn(0.25f, (float)x + 0.5f, -0.5f);
+    sx = sx < 0.f ? 0.f : sx;
+    const int x1 = (int)sx;
+    c.x1 = (unsigned)x1; c.x1p = x1 < Wl - 1 ? 1u : 0u;
+    c.w1 = sx - (float)x1; c.w0 = 1.f - c.w1;
+    return c;
+}
+__device__ __forceinline__ void up4_flow(const float *__restrict__ lo, unsigned hwl, int Wl, int Hl, const Up4Col &c, int y,
+                                         float mul, float &dx, float &dy)
+{
+    float sy = __fmaf_rn(0.25f, (float)y + 0.5f, -0.5f);
+    sy = sy < 0.f ? 0.f : sy;
+    const int y1 = (int)sy;
+    const unsigned y1p = y1 < Hl - 1 ? (unsigned)Wl : 0u;
+    const float h1 = sy - (float)y1, h0 = 1.f - h1;
+    const float *p = lo + (unsigned)y1 * (unsigned)Wl + c.x1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float v00 = __fmul_rn(__ldg(p), mul), v01 = __fmul_rn(__ldg(p + c.x1p), mul);
+        const float v10 = __fmul_rn(__ldg(p + y1p), mul), v11 = __fmul_rn(__ldg(p + y1p + c.x1p), mul);
+        const float top = __fmaf_rn(c.w1, v01, __fmul_rn(c.w0, v00)), bot = __fmaf_rn(c.w1, v11, __fmul_rn(c.w0, v10));
+        const float v = __fmaf_rn(h1, bot, __fmul_rn(h0, top));
+        if (k == 0) dx = v; else dy = v;
+        p += hwl;
+    }
+}
 
 // EPI_CONCAT (C = 3 only): the whole `concat1` / `concat2` tensor of models.py:112-114,124-126 --
 // (frame 0, frame 1, warped frame 1, flow / div_flow, |frame 0 - warped|) -- written channels-last with the pixel
@@ -254,7 +291,7 @@ __device__ __forceinline__ void pix_finish(const WarpArgs &a, const PixPrep<MODE
 
 // grid: (W / blockDim.x, H / (blockDim.y * rows), B)  -- the batch index is block-uniform, so every base
 // pointer below lives in uniform registers and per-thread addressing is 32-bit offsets
-template <int MODE, int CT, int EPI, bool WRITE_WARPED>
+template <int MODE, int CT, int EPI, bool WRITE_WARPED, bool UP4 = false>
 __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant__ WarpArgs a)
 {
     constexpr bool NEED_REF = EPI != EPI_STORE;
@@ -268,7 +305,7 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
     const float *src = a.img + b * a.img_bs;
     asm("" : "+l"(src));     // keep the batch base as one opaque 64-bit value (no b*stride folded into every gather)
     const unsigned p0 = (unsigned)y0 * W + (unsigned)x;
-    const float *fl = a.flow + b * 2 * hw + p0;                       // walks down the column
+    const float *fl = UP4 ? nullptr : a.flow + b * 2 * hw + p0;       // walks down the column
     const float *ref = NEED_REF ? a.ref + b * a.ref_bs + p0 : src;    // unused when !NEED_REF
     float *out = WRITE_WARPED ? a.out + b * a.out_bs + p0 : nullptr;
     const unsigned aux_px = EPI == EPI_CONCAT ? (unsigned)a.c_dst : 1u;      // floats per destination pixel
@@ -276,10 +313,21 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
     const float *self = src + p0;                                            // CONCAT: frame 1 at this pixel
     const float xfl = small_int_as_float(x);
     float yfl = small_int_as_float(y0);
-    float dx = ldg_stream(fl), dy = ldg_stream(fl + hw);
+    // UP4: the flow is formed from the quarter-resolution field (L1 / L2 resident) instead of read at full resolution
+    const int Wl = a.W >> 2, Hl = a.H >> 2;
+    const unsigned hwl = (unsigned)Wl * Hl;
+    const float *lo = UP4 ? a.flow_lo + b * 2 * hwl : nullptr;
+    Up4Col ucol{};
+    if (UP4) ucol = up4_col(x, Wl);
+    float dx, dy;
+    if (UP4) up4_flow(lo, hwl, Wl, Hl, ucol, y0, a.flow_mul, dx, dy);
+    else { dx = ldg_stream(fl); dy = ldg_stream(fl + hw); }
     for (int y = y0; y < y1; ++y) {
         float ndx = 0.f, ndy = 0.f;
-        if (y + 1 < y1) { ndx = ldg_stream(fl + W); ndy = ldg_stream(fl + W + hw); }     // next row's flow
+        if (y + 1 < y1) {                                                                 // next row's flow
+            if (UP4) up4_flow(lo, hwl, Wl, Hl, ucol, y + 1, a.flow_mul, ndx, ndy);
+            else { ndx = ldg_stream(fl + W); ndy = ldg_stream(fl + W + hw); }
+        }
         PixPrep<MODE> cur;
         PixVals<CT> vcur;
         pix_prep(cur, a, xfl, yfl, x, y, dx, dy);
@@ -309,7 +357,7 @@ static inline int warp_rows_pick(int B, int H, int W, int rows = 4)
 }
 
 // C must be 1..3 (compile-time channel counts; the register pipeline is sized by them)
-template <int MODE, int EPI, bool WRITE_WARPED>
+template <int MODE, int EPI, bool WRITE_WARPED, bool UP4 = false>
 static inline void launch_warp_rows(WarpArgs a, cudaStream_t st)
 {
     const int B = a.B;
@@ -317,15 +365,17 @@ static inline void launch_warp_rows(WarpArgs a, cudaStream_t st)
     for (int b0 = 0; b0 < B; b0 += 65535) {            // gridDim.z limit
         WarpArgs c = a;
         c.B = B - b0 < 65535 ? B - b0 : 65535;
-        c.img = a.img + (size_t)b0 * a.img_bs; c.flow = a.flow + (size_t)b0 * 2 * hw;
+        c.img = a.img + (size_t)b0 * a.img_bs;
+        if (a.flow) c.flow = a.flow + (size_t)b0 * 2 * hw;
+        if (a.flow_lo) c.flow_lo = a.flow_lo + (size_t)b0 * 2 * (size_t)(a.H >> 2) * (a.W >> 2);
         if (a.ref) c.ref = a.ref + (size_t)b0 * a.ref_bs;
         if (a.out) c.out = a.out + (size_t)b0 * a.out_bs;
         if (a.aux) c.aux = a.aux + (size_t)b0 * a.aux_bs;
         dim3 grid, block;
         warp_rows_shape(c.B, c.H, c.W, c.rows, grid, block);
-        if (a.C == 3) warp_rows_kernel<MODE, 3, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
-        else if (a.C == 2) warp_rows_kernel<MODE, 2, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
-        else warp_rows_kernel<MODE, 1, EPI, WRITE_WARPED><<<grid, block, 0, st>>>(c);
+        if (a.C == 3) warp_rows_kernel<MODE, 3, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);
+        else if (a.C == 2) warp_rows_kernel<MODE, 2, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);
+        else warp_rows_kernel<MODE, 1, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);
     }
 }
 

@@ -226,6 +226,23 @@ def warp_diff_norm_concat(x, flow, div_flow, c_pad=16):
     return out
 
 
+def warp_diff_norm_concat_up4(x, flow_lo, flow_mul, div_flow, c_pad=16):
+    """warp_diff_norm_concat for flow = nn.Upsample(scale_factor=4, mode='bilinear')(flow_lo * flow_mul) (models.py:106,118)
+    without materialising that flow: flow_lo is the previous sub-network's quarter-resolution flow2 [B,2,H/4,W/4]."""
+    x = _require(x, "x").contiguous()
+    flow_lo = _require(flow_lo, "flow_lo").contiguous()
+    B, C6, H, W = x.shape
+    if C6 != 6 or H % 4 or W % 4 or tuple(flow_lo.shape) != (B, 2, H // 4, W // 4):
+        raise ValueError("expected x [B,6,H,W] with H, W multiples of 4 and flow_lo [B,2,H/4,W/4], got %s and %s"
+                         % (tuple(x.shape), tuple(flow_lo.shape)))
+    with torch.cuda.device_of(x):
+        out = torch.empty((B, c_pad, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if x.numel():
+            check(_lib.load().flowops_warp_diff_norm_concat_up4_nhwc(_p(x), _p(flow_lo), ctypes.c_float(flow_mul), ctypes.c_float(div_flow),
+                                                                     _p(out), c_pad, B, H, W, _stream()), "warp_diff_norm_concat_up4_nhwc")
+    return out
+
+
 def flownet2_fusion_input(x, flow2_s2, flow2_sd, div_flow, c_pad=16):
     """concat3 of models.py:129-152 in one pass: a channels_last [B, c_pad, H, W] tensor whose first 11 channels are
     (frame 0, flow_sd, flow_s2, |flow_sd|, |flow_s2|, warp error under flow_sd, warp error under flow_s2), the rest zero.
@@ -332,6 +349,15 @@ class ConcatBuffer:
             check(_lib.load().flowops_concat_nhwc(_p(t), _p(self.tensor), self.n_pixels, t.shape[1], self.c_pad, c_off, _stream()),
                   "concat_nhwc")
         return c_off + t.shape[1]
+
+    def flow_deconv_in(self, flow, weight, bias, c_off):
+        """dst[:, c_off : c_off + 2] = conv_transpose2d(flow, weight, bias, stride 2, padding 1) for a dense channels_last
+        2-channel flow at half the buffer's resolution and a contiguous [2, 2, 4, 4] weight (the decoders' flow upsamplers)."""
+        B, _, h, w = flow.shape
+        with torch.cuda.device_of(flow):
+            check(_lib.load().flowops_flow_deconv_nhwc_to(_p(flow), _p(weight), _p(bias), _p(self.tensor), B, h, w, self.c_pad, c_off,
+                                                          _stream()), "flow_deconv_nhwc_to")
+        return c_off + 2
 
     def bias_lrelu_in(self, y, bias, slope, c_off, in_place_too=False):
         """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y; with in_place_too

@@ -59,6 +59,7 @@ class FlowNet2(nn.Module):
         self.args = args
         self.fuse_glue = True          # use the fused warp/diff/norm kernel when autograd is off
         self.fuse_fusion_input = True  # channels_last body: concat3 (models.py:129-152) from one kernel
+        self.fuse_upsample = True      # channels_last body: the x4 bilinear upsamplings folded into the concat kernels
 
         self.channelnorm = ChannelNorm()
         self.flownetc = FlowNetC.FlowNetC(args, batchNorm=self.batchNorm)
@@ -94,10 +95,15 @@ class FlowNet2(nn.Module):
         rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1)
         x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max))
 
-        flownetc_flow = self.upsample1(self.flownetc(x, frames=(xa, xb))[0] * self.div_flow)
-        concat1 = _F.warp_diff_norm_concat(x, flownetc_flow, self.div_flow)
-        flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
-        concat2 = _F.warp_diff_norm_concat(x, flownets1_flow, self.div_flow)
+        flow2_c = self.flownetc(x, frames=(xa, xb))[0]
+        if self.fuse_upsample and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
+            # `upsample(flow2 * div_flow)` (models.py:106,118) folded into the concat kernel's flow read
+            concat1 = _F.warp_diff_norm_concat_up4(x, flow2_c, self.div_flow, self.div_flow)
+            concat2 = _F.warp_diff_norm_concat_up4(x, self.flownets_1(concat1)[0], self.div_flow, self.div_flow)
+        else:
+            concat1 = _F.warp_diff_norm_concat(x, self.upsample1(flow2_c * self.div_flow), self.div_flow)
+            flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
+            concat2 = _F.warp_diff_norm_concat(x, flownets1_flow, self.div_flow)
         flow2_s2 = self.flownets_2(concat2)[0]
         flow2_sd = self.flownets_d(x8)[0]
         if self.fuse_fusion_input and _sm.PAD_CHANNELS > 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:

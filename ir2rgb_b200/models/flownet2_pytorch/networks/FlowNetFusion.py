@@ -21,16 +21,20 @@ class FlowNetFusion(nn.Module):
         self.upsampled_flow2_to_1, self.upsampled_flow1_to_0 = flow_upsampler(), flow_upsampler()
         reference_init(self)
 
-    def _concat(self, sk, skip, deconv_lv, feat, up):
+    def _concat(self, sk, skip, deconv_lv, feat, upconv, flow):
         """torch.cat((skip, deconv(feat), up), 1) (FlowNetFusion.py:54,60).  Inference on a channels_last body: the encoder
         layer already wrote `skip` into the level's concat buffer (sk.buf, channels rounded up to a multiple of 8:
         162 -> 168, 82 -> 88), the deconvolution's epilogue writes its slice, only the 2-channel flow is copied."""
-        if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _F._cat_fast((skip, up)):
+        if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _F._cat_fast((skip,)):
             off = skip.shape[1]
             deconv_lv(feat, into=(sk.buf, off))
-            sk.buf.copy_in(up, off + deconv_lv[0].out_channels)
+            c_up = off + deconv_lv[0].out_channels
+            if _sm.FUSE_FLOW_UPSAMPLER and c_up % 2 == 0 and _sm._flow_upsampler_ok(upconv, flow):
+                sk.buf.flow_deconv_in(flow, _sm._dense_weight(upconv), upconv.bias, c_up)     # one kernel, straight into its slice
+            else:
+                sk.buf.copy_in(apply_conv(upconv, flow), c_up)
             return sk.buf.tensor
-        return _F.cat_channels((skip, apply_conv(deconv_lv, feat), up), pad_to=_sm.PAD_CHANNELS)
+        return _F.cat_channels((skip, apply_conv(deconv_lv, feat), apply_conv(upconv, flow)), pad_to=_sm.PAD_CHANNELS)
 
     def forward(self, x):
         sk0, sk1 = Skip(self, 0), Skip(self, 1)
@@ -38,7 +42,7 @@ class FlowNetFusion(nn.Module):
         c1 = self.conv1_1(self.conv1(c0), skip=sk1)
         c2 = self.conv2_1(self.conv2(c1))
         flow2 = apply_conv(self.predict_flow2, c2)
-        cat1 = self._concat(sk1, c1, self.deconv1, c2, apply_conv(self.upsampled_flow2_to_1, flow2))
+        cat1 = self._concat(sk1, c1, self.deconv1, c2, self.upsampled_flow2_to_1, flow2)
         flow1 = apply_conv(self.predict_flow1, apply_conv(self.inter_conv1, cat1))
-        cat0 = self._concat(sk0, c0, self.deconv0, cat1, apply_conv(self.upsampled_flow1_to_0, flow1))
+        cat0 = self._concat(sk0, c0, self.deconv0, cat1, self.upsampled_flow1_to_0, flow1)
         return apply_conv(self.predict_flow0, apply_conv(self.inter_conv0, cat0))

@@ -139,6 +139,18 @@ class ConvAct(nn.Sequential):
                             after(y)
                             skip.buf = sbuf
                         return None if into is not None else y
+            if (isinstance(conv, nn.ConvTranspose2d) and into is not None and into[1] % 4 == 0 and torch.backends.cudnn.allow_tf32
+                    and _F._is_nhwc(x) and _cf.available()):
+                # k4 s2 p1 transposed convolution + bias + LeakyReLU as four fused 2x2 convolutions (one per output
+                # parity) writing stride-2 views of the concat slice -- where that beats strided dgrad + epilogue pass
+                buf, c_off = into
+                slope = self[1].negative_slope
+                dst = buf.tensor[:, c_off:c_off + conv.out_channels]
+
+                def unfused_deconv():
+                    buf.bias_lrelu_in(_raw_conv(conv, x, None), conv.bias, slope, c_off)
+                if _cf.deconv_bias_lrelu(conv, x, padded_weight(conv, x.shape[1]), slope, dst, unfused_deconv) is True:
+                    return None
             y = _raw_conv(conv, x, None)
             if into is not None:
                 buf, c_off = into
@@ -225,6 +237,30 @@ def add_layers(net, batchNorm, table):
         setattr(net, name, conv(batchNorm, cin, cout, kernel_size=k, stride=s))
 
 
+FUSE_FLOW_UPSAMPLER = True
+
+
+def _flow_upsampler_ok(conv, flow):
+    return (isinstance(conv, nn.ConvTranspose2d) and conv.in_channels == 2 and conv.out_channels == 2 and conv.groups == 1
+            and tuple(conv.kernel_size) == (4, 4) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (1, 1)
+            and tuple(conv.output_padding) == (0, 0) and tuple(conv.dilation) == (1, 1)
+            and flow.dtype == torch.float32 and flow.is_cuda and flow.shape[1] == 2
+            and flow.is_contiguous(memory_format=torch.channels_last) and not conv.__dict__.get("_flowops_stock", False))
+
+
+def _dense_weight(conv):
+    """conv.weight as a plain contiguous [Cin, Cout, kh, kw] tensor (a channels_last module keeps a permuted one), cached."""
+    w = conv.weight
+    if w.is_contiguous():
+        return w
+    key = (w.data_ptr(), w._version)
+    cache = conv.__dict__.get("_flowops_wdense")
+    if cache is None or cache[0] != key:
+        cache = (key, w.detach().contiguous())
+        conv.__dict__["_flowops_wdense"] = cache
+    return cache[1]
+
+
 def refine(net, skips, top, levels, inter=False, skip_bufs=None):
     """Shared coarse-to-fine decoder of FlowNetC / FlowNetS / FlowNetSD (e.g. FlowNetS.py:70-90):
     at each level predict a flow, upsample it and the features, concatenate with the skip tensor.
@@ -236,22 +272,30 @@ def refine(net, skips, top, levels, inter=False, skip_bufs=None):
     feat = top
     flows = [apply_conv(getattr(net, "predict_flow%d" % (levels[0] + 1)), top)]
     for lv in levels:
-        up = apply_conv(getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv)), flows[0])
+        upconv = getattr(net, "upsampled_flow%d_to_%d" % (lv + 1, lv))
         deconv_lv = getattr(net, "deconv%d" % lv)
         skip = skips[lv]
-        if deconv_lv.fusable(feat) and _F._cat_fast((skip, up)) and _F._is_nhwc(feat):
+        # the 2-channel flow upsampler as one libflowops kernel writing its slice of the concat buffer (inference,
+        # channels_last, dense 2-channel flow); otherwise the cuDNN transposed convolution + copy
+        direct_up = (FUSE_FLOW_UPSAMPLER and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _flow_upsampler_ok(upconv, flows[0])
+                     and _F._cat_fast((skip,)))
+        up = None if direct_up else apply_conv(upconv, flows[0])
+        if deconv_lv.fusable(feat) and _F._is_nhwc(feat) and (direct_up or _F._cat_fast((skip, up))):
             c_dec = deconv_lv[0].out_channels
             buf = skip_bufs[lv].buf if skip_bufs is not None and skip_bufs.get(lv) is not None else None
             if buf is not None:                 # the encoder already wrote the skip tensor into its slice
                 off = skip.shape[1]
             else:
-                buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + up.shape[1], PAD_CHANNELS)
+                buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + 2, PAD_CHANNELS)
                 off = buf.copy_in(skip, 0)
             deconv_lv(feat, into=(buf, off))
-            buf.copy_in(up, off + c_dec)
+            if direct_up and (off + c_dec) % 2 == 0:
+                buf.flow_deconv_in(flows[0], _dense_weight(upconv), upconv.bias, off + c_dec)
+            else:
+                buf.copy_in(up if up is not None else apply_conv(upconv, flows[0]), off + c_dec)
             feat = buf.tensor
         else:
-            feat = _F.cat_channels((skip, deconv_lv(feat), up))
+            feat = _F.cat_channels((skip, deconv_lv(feat), up if up is not None else apply_conv(upconv, flows[0])))
         head_in = apply_conv(getattr(net, "inter_conv%d" % lv), feat) if inter else feat
         flows.insert(0, apply_conv(getattr(net, "predict_flow%d" % lv), head_in))
     return flows

@@ -336,3 +336,51 @@ def test_channels_last_flownet_with_fused_conv3_epilogue_matches_plain_path(flow
     rel = ((flow_padded - flow_plain).abs().max() / flow_plain.abs().max()).item()
     assert rel <= 1e-4, rel
     assert (conf_padded != conf_plain).float().mean().item() <= 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 128, 192), (2, 512, 1024)])
+def test_concat_with_folded_bilinear_upsampling(flowops_lib, shape):
+    """`upsample_bilinear_x4(flow2 * div_flow)` (models.py:106,118) formed inside the concat kernel: the flow channels
+    agree with nn.Upsample to 1e-6 max-relative (the blend may contract its FMAs differently from ATen's kernel: a few
+    ulp), the channels computed FROM the flow (warped frame, error magnitude) to the operator tolerance 1e-5."""
+    from ir2rgb_b200 import functional as F
+    B, H, W = shape
+    torch.manual_seed(23)
+    x = 2 * torch.rand(B, 6, H, W, device="cuda") - 1
+    lo = torch.randn(B, 2, H // 4, W // 4, device="cuda")
+    up = torch.nn.Upsample(scale_factor=4, mode="bilinear")
+    want = F.warp_diff_norm_concat(x, up(lo * 20.0), 20.0)
+    got = F.warp_diff_norm_concat_up4(x, lo, 20.0, 20.0)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got[:, :6], want[:, :6]) and torch.equal(got[:, 12:], want[:, 12:])     # frames, zero padding
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    assert rel(got[:, 9:11], want[:, 9:11]) <= 1e-6          # flow / div_flow
+    # a flow that moves by an ulp can move a pixel's floor across an integer: compare the warped frame statistically
+    d = (got[:, 6:9] - want[:, 6:9]).abs()
+    assert (d > 1e-4).float().mean().item() <= 1e-4 and rel(got[:, 11:12], want[:, 11:12]) <= 2.0
+    assert d.median().item() <= 1e-6
+
+
+def test_flow_upsampler_kernel_matches_conv_transpose(flowops_lib):
+    """flowops_flow_deconv_nhwc_to (the decoders' 2-channel ConvTranspose2d(k4, s2, p1)) against torch, written into a slice
+    of a padded channels-last concat buffer; with and without bias."""
+    from ir2rgb_b200 import functional as F
+    torch.manual_seed(29)
+    for (B, h, w, bias) in [(2, 5, 7, True), (1, 16, 32, False), (3, 1, 1, True), (2, 64, 128, True)]:
+        conv = torch.nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=bias).cuda()
+        flow = torch.randn(B, 2, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
+        like = torch.empty(B, 1, 2 * h, 2 * w, device="cuda")
+        buf = F.ConcatBuffer(like, 10, 8)
+        buf.tensor.fill_(7.0)
+        with torch.no_grad():
+            want = conv(flow)
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                want = conv(flow)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+            buf.flow_deconv_in(flow, conv.weight.detach().contiguous(), conv.bias, 6)
+        got = buf.tensor[:, 6:8]
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-6
+        assert (buf.tensor[:, :6] == 7.0).all() and (buf.tensor[:, 8:] == 7.0).all()      # neighbours untouched

@@ -35,18 +35,14 @@ def _handle(device):
 
 
 class _Plan:
-    def __init__(self, x, w, bias, y, stride, padding, dilation, slope, handle, unfused=None, after=None, post_padding=None):
+    def __init__(self, x, w, bias, y, stride, padding, dilation, slope, handle, unfused=None, after=None):
         FL = cudnn.data_type.FLOAT
         g = cudnn.pygraph(handle=handle, io_data_type=FL, intermediate_data_type=FL, compute_data_type=FL)
         self.X = g.tensor(name="X", dim=list(x.shape), stride=list(x.stride()), data_type=FL)
         self.W = g.tensor(name="W", dim=list(w.shape), stride=list(w.stride()), data_type=FL)
         n = bias.numel()
         self.B = g.tensor(name="B", dim=[1, n, 1, 1], stride=[n, 1, n, n], data_type=FL)
-        if post_padding is None:
-            c = g.conv_fprop(image=self.X, weight=self.W, padding=list(padding), stride=list(stride), dilation=list(dilation))
-        else:
-            c = g.conv_fprop(image=self.X, weight=self.W, pre_padding=list(padding), post_padding=list(post_padding),
-                             stride=list(stride), dilation=list(dilation))
+        c = g.conv_fprop(image=self.X, weight=self.W, padding=list(padding), stride=list(stride), dilation=list(dilation))
         t = g.bias(input=c, bias=self.B)
         o = g.leaky_relu(input=t, negative_slope=float(slope))
         o.set_output(True).set_dim(list(y.shape)).set_stride(list(y.stride())).set_data_type(FL)
@@ -58,6 +54,14 @@ class _Plan:
         g.build_plans(cudnn.build_plan_policy.ALL)
         self.g = g
         self.index, self.ws, self.ms = self._pick(x, w, bias, y, handle)
+        # trust, but verify: the chosen plan must reproduce the two-kernel result on this very layer (TF32 engines differ
+        # from each other by ~1e-3 of the largest output; a layout or stride misunderstanding shows up as O(1))
+        self.run(x, w, bias, y, handle)
+        want = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, w, bias, tuple(stride), tuple(padding), tuple(dilation)),
+                                              float(slope))
+        err = ((y - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+        if not err <= 1e-2:
+            raise RuntimeError("fused plan disagrees with the unfused convolution (max-relative %.3g)" % err)
         # a fused engine is not always faster than cuDNN's best plain convolution followed by the epilogue pass (the
         # plain convolution has more algorithms to choose from): keep the fused plan only where it wins
         self.ms_unfused = _time3(unfused) if unfused is not None else None
@@ -144,66 +148,3 @@ def conv_bias_lrelu(conv, x, w, slope, out=None, unfused=None, after=None):
 def reset():
     _cache.clear()
 
-
-# ---------------------------------------------------------------------------------------------------------------
-# ConvTranspose2d(k=4, s=2, p=1) + bias + LeakyReLU as four fused 2x2 convolutions
-# ---------------------------------------------------------------------------------------------------------------
-# out[2m + py] = sum over the two kernel rows of the same parity: py = 0 -> in[m-1] * w[3] + in[m] * w[1],
-# py = 1 -> in[m] * w[2] + in[m+1] * w[0] (same along x).  Each output parity is therefore a stride-1 2x2 cross-
-# correlation of the input with a sub-kernel (asymmetric padding), written to a stride-2 view of the output -- an
-# ordinary fprop that cuDNN's runtime-fusion engines take with the bias + LeakyReLU epilogue, instead of the strided
-# dgrad kernel + a separate epilogue pass (15 % + 3 % of the FlowNet2 forward in profiles/launches_r02_flownet2_b16.csv).
-_TAPS = {0: (3, 1), 1: (2, 0)}
-
-
-def deconv_subkernels(conv, w):
-    """The four [Cout, Cin, 2, 2] channels-last sub-kernels of a ConvTranspose2d weight w [Cin, Cout, 4, 4] (possibly
-    zero-padded along Cin), cached on the module next to the padded weight it was derived from."""
-    key = (w.data_ptr(), w._version, tuple(w.shape))
-    cache = conv.__dict__.get("_flowops_wsub")
-    if cache is None or cache[0] != key:
-        subs = {}
-        for py in (0, 1):
-            for px in (0, 1):
-                ws = w.detach()[:, :, list(_TAPS[py]), :][:, :, :, list(_TAPS[px])]            # [Cin, Cout, 2, 2]
-                subs[(py, px)] = ws.permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
-        cache = (key, subs)
-        conv.__dict__["_flowops_wsub"] = cache
-    return cache[1]
-
-
-def deconv_bias_lrelu(conv, x, w, slope, out, unfused=None):
-    """LeakyReLU(conv_transpose2d(x, w) + conv.bias) for the k4 s2 p1 transposed convolutions of the FlowNet2 decoders,
-    written into `out` ([B, Cout, 2H, 2W], may be a channel slice of a channels-last concat buffer).  Returns True, or
-    NotImplemented when the layer is not eligible or the four fused launches do not beat the unfused path."""
-    if (not available() or conv.groups != 1 or tuple(conv.kernel_size) != (4, 4) or tuple(conv.stride) != (2, 2)
-            or tuple(conv.padding) != (1, 1) or tuple(conv.output_padding) != (0, 0) or tuple(conv.dilation) != (1, 1)):
-        return NotImplemented
-    B, _, H, W = x.shape
-    if out.numel() < MIN_OUT_ELEMENTS or out.data_ptr() % 16 or x.data_ptr() % 16:
-        return NotImplemented
-    key = ("deconv", x.device.index, tuple(x.shape), tuple(x.stride()), tuple(w.shape), tuple(out.shape), tuple(out.stride()), float(slope))
-    handle = _handle(x.device)
-    cudnn.set_stream(handle=handle, stream=torch.cuda.current_stream(x.device).cuda_stream)
-    plans = _cache.get(key)
-    subs = deconv_subkernels(conv, w)
-    views = {(py, px): out[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)}
-    if plans is None:
-        if torch.cuda.is_current_stream_capturing():
-            return NotImplemented
-        try:
-            plans = {}
-            for (py, px), y in views.items():
-                pre, post = (1 - py, 1 - px), (py, px)
-                plans[(py, px)] = _Plan(x, subs[(py, px)], conv.bias, y, (1, 1), pre, (1, 1), slope, handle, post_padding=post)
-            run_all = lambda: [plans[k].run(x, subs[k], conv.bias, views[k], handle) for k in plans]
-            if unfused is not None and not (_time3(run_all) < 0.97 * _time3(unfused)):
-                plans = False
-        except Exception:
-            plans = False
-        _cache[key] = plans
-    if plans is False:
-        return NotImplemented
-    for k, plan in plans.items():
-        plan.run(x, subs[k], conv.bias, views[k], handle)
-    return True

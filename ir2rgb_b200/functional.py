@@ -43,6 +43,15 @@ def _is_nhwc(t):
     return (not t.is_contiguous()) and t.is_contiguous(memory_format=torch.channels_last)
 
 
+def _is_nhwc_view(t):
+    """Dense channels_last, or a channel slice of a dense channels_last tensor (pixel stride > C): what the cuDNN
+    graph path (cudnn_fused.py) reads and writes in place of a copy."""
+    if t.dim() != 4 or t.stride(1) != 1 or t.shape[1] == 1:
+        return False
+    ps = t.stride(3)
+    return ps >= t.shape[1] and t.stride(2) == t.shape[3] * ps and t.stride(0) == t.shape[2] * t.stride(2)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -343,6 +352,26 @@ class ConcatBuffer:
             if self.c_pad > c_total:
                 check(_lib.load().flowops_fill_channels_nhwc(_p(self.tensor), self.n_pixels, self.c_pad, c_total,
                                                              self.c_pad - c_total, ctypes.c_float(0.0), _stream()), "fill_channels_nhwc")
+
+    @classmethod
+    def cached(cls, owner, tag, like, c_total, pad_to=8, shape=None):
+        """The concat buffer of one place in the network, allocated (and its zero pad channels filled) once per shape and
+        reused by every later forward: saves the allocation and the fill launch per call, and under CUDA-graph replay the
+        fill is not replayed.  Inference-only, one forward at a time per module (the buffers are internal to a forward:
+        every channel other than the padding is rewritten by the producers of the next one).  `owner` is the nn.Module
+        the buffer belongs to; ConcatBuffer.drop_cached(module) frees them."""
+        B, H, W = (like.shape[0], like.shape[2], like.shape[3]) if shape is None else shape
+        key = (tag, B, H, W, c_total, pad_to, like.device)
+        store = owner.__dict__.setdefault("_flowops_cbuf", {})
+        buf = store.get(key)
+        if buf is None:
+            buf = store[key] = cls(like, c_total, pad_to, shape=shape)
+        return buf
+
+    @staticmethod
+    def drop_cached(module):
+        for m in module.modules():
+            m.__dict__.pop("_flowops_cbuf", None)
 
     def copy_in(self, t, c_off):
         with torch.cuda.device_of(t):

@@ -70,7 +70,7 @@ class FlowNetC(nn.Module):
             # the concat of FlowNetC.py:94 is allocated first (473 -> 480 channels, zero pad); conv_redir's epilogue and
             # the correlation (with corr_activation folded into its store) each write their channel slice
             c2a, c3a, planes = fused
-            buf = _F.ConcatBuffer(c3a, self.conv_redir[0].out_channels + 441, _sm.PAD_CHANNELS)
+            buf = _sm._new_buffer(self.conv_redir, "corr", c3a, self.conv_redir[0].out_channels + 441)
             off = self.conv_redir[0].out_channels
             self.conv_redir(c3a, into=(buf, 0))
             _F.correlation_planes_forward_into(planes, buf, off, self.corr_activation.negative_slope)

@@ -25,7 +25,7 @@ class FlowNetFusion(nn.Module):
         """torch.cat((skip, deconv(feat), up), 1) (FlowNetFusion.py:54,60).  Inference on a channels_last body: the encoder
         layer already wrote `skip` into the level's concat buffer (sk.buf, channels rounded up to a multiple of 8:
         162 -> 168, 82 -> 88), the deconvolution's epilogue writes its slice, only the 2-channel flow is copied."""
-        if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _F._cat_fast((skip,)):
+        if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat):
             off = skip.shape[1]
             deconv_lv(feat, into=(sk.buf, off))
             c_up = off + deconv_lv[0].out_channels

@@ -49,9 +49,20 @@ def padded_weight(conv, cin):
 
 
 def reset_padded_weights(net):
-    """Drop every cached zero-padded weight of `net` (needed after weight updates made through `.data`)."""
+    """Drop every cached tensor derived from the weights of `net` (needed after weight updates made through `.data`)
+    and the cached concat buffers."""
     for m in net.modules():
-        m.__dict__.pop("_flowops_wpad", None)
+        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf"):
+            m.__dict__.pop(k, None)
+
+
+CACHE_CONCAT_BUFFERS = True      # inference: one concat buffer per place and shape, reused across forwards
+
+
+def _new_buffer(owner, tag, like, c_total, shape=None):
+    if CACHE_CONCAT_BUFFERS:
+        return _F.ConcatBuffer.cached(owner, tag, like, c_total, PAD_CHANNELS, shape=shape)
+    return _F.ConcatBuffer(like, c_total, PAD_CHANNELS, shape=shape)
 
 
 def _conv_out_hw(conv, x):
@@ -107,7 +118,7 @@ class ConvAct(nn.Sequential):
         conv = self[0]
         if self.fusable(x):
             sbuf = None
-            if isinstance(conv, nn.Conv2d) and torch.backends.cudnn.allow_tf32 and _F._is_nhwc(x) and _cf.available():
+            if isinstance(conv, nn.Conv2d) and torch.backends.cudnn.allow_tf32 and _F._is_nhwc_view(x) and _cf.available():
                 # convolution + bias + LeakyReLU as ONE cuDNN runtime-fusion launch (TF32 math, as the unfused cuDNN
                 # convolution under the same setting) where that is faster than the two-kernel path -- decided per layer
                 # by timing both once; with TF32 off the bit-exact two-kernel path below runs
@@ -117,13 +128,13 @@ class ConvAct(nn.Sequential):
                     buf, c_off = into
                     out = buf.tensor[:, c_off:c_off + conv.out_channels] if c_off % 4 == 0 else None
                 if into is None or out is not None:
-                    after = None
                     if skip is not None:
-                        # also a decoder skip connection: the fused launch writes the dense tensor, a copy puts it into
-                        # the level's concat buffer (the unfused epilogue writes both from one read)
-                        sbuf = _F.ConcatBuffer(x, skip.c_total(conv.out_channels), PAD_CHANNELS,
-                                               shape=(x.shape[0],) + _conv_out_hw(conv, x))
-                        after = lambda t: sbuf.copy_in(t, 0)
+                        # also a decoder skip connection: the fused launch writes straight into the level's concat
+                        # buffer, and the layers that consume this output read that channel slice in place (the cuDNN
+                        # graph path takes strided tensors; a stock torch convolution makes its own dense copy)
+                        sbuf = _new_buffer(self, "skip", x, skip.c_total(conv.out_channels),
+                                           shape=(x.shape[0],) + _conv_out_hw(conv, x))
+                        out = sbuf.tensor[:, :conv.out_channels]
 
                     def unfused():
                         t = _raw_conv(conv, x, None)
@@ -133,24 +144,11 @@ class ConvAct(nn.Sequential):
                             sbuf.bias_lrelu_in(t, conv.bias, slope, 0, in_place_too=True)
                         else:
                             _F.bias_lrelu_(t, conv.bias, slope)
-                    y = _cf.conv_bias_lrelu(conv, x, padded_weight(conv, x.shape[1]), slope, out, unfused, after)
+                    y = _cf.conv_bias_lrelu(conv, x, padded_weight(conv, x.shape[1]), slope, out, unfused)
                     if y is not NotImplemented:
                         if skip is not None:
-                            after(y)
                             skip.buf = sbuf
                         return None if into is not None else y
-            if (isinstance(conv, nn.ConvTranspose2d) and into is not None and into[1] % 4 == 0 and torch.backends.cudnn.allow_tf32
-                    and _F._is_nhwc(x) and _cf.available()):
-                # k4 s2 p1 transposed convolution + bias + LeakyReLU as four fused 2x2 convolutions (one per output
-                # parity) writing stride-2 views of the concat slice -- where that beats strided dgrad + epilogue pass
-                buf, c_off = into
-                slope = self[1].negative_slope
-                dst = buf.tensor[:, c_off:c_off + conv.out_channels]
-
-                def unfused_deconv():
-                    buf.bias_lrelu_in(_raw_conv(conv, x, None), conv.bias, slope, c_off)
-                if _cf.deconv_bias_lrelu(conv, x, padded_weight(conv, x.shape[1]), slope, dst, unfused_deconv) is True:
-                    return None
             y = _raw_conv(conv, x, None)
             if into is not None:
                 buf, c_off = into
@@ -159,7 +157,7 @@ class ConvAct(nn.Sequential):
             if skip is not None and _F._is_nhwc(y):
                 # this output is also a decoder skip connection: allocate that level's concat buffer now and write the
                 # activated features to both places from one read
-                skip.buf = sbuf if sbuf is not None else _F.ConcatBuffer(y, skip.c_total(y.shape[1]), PAD_CHANNELS)
+                skip.buf = sbuf if sbuf is not None else _new_buffer(self, "skip", y, skip.c_total(y.shape[1]))
                 skip.buf.bias_lrelu_in(y, conv.bias, self[1].negative_slope, 0, in_place_too=True)
                 return y
             return _F.bias_lrelu_(y, conv.bias, self[1].negative_slope)
@@ -277,16 +275,17 @@ def refine(net, skips, top, levels, inter=False, skip_bufs=None):
         skip = skips[lv]
         # the 2-channel flow upsampler as one libflowops kernel writing its slice of the concat buffer (inference,
         # channels_last, dense 2-channel flow); otherwise the cuDNN transposed convolution + copy
+        buf = skip_bufs[lv].buf if skip_bufs is not None and skip_bufs.get(lv) is not None else None
+        skip_ok = buf is not None or _F._cat_fast((skip,))      # already in its slice (possibly returned as a view of it)
         direct_up = (FUSE_FLOW_UPSAMPLER and deconv_lv.fusable(feat) and _F._is_nhwc(feat) and _flow_upsampler_ok(upconv, flows[0])
-                     and _F._cat_fast((skip,)))
+                     and skip_ok)
         up = None if direct_up else apply_conv(upconv, flows[0])
-        if deconv_lv.fusable(feat) and _F._is_nhwc(feat) and (direct_up or _F._cat_fast((skip, up))):
+        if deconv_lv.fusable(feat) and _F._is_nhwc(feat) and skip_ok and (direct_up or _F._cat_fast((up,))):
             c_dec = deconv_lv[0].out_channels
-            buf = skip_bufs[lv].buf if skip_bufs is not None and skip_bufs.get(lv) is not None else None
             if buf is not None:                 # the encoder already wrote the skip tensor into its slice
                 off = skip.shape[1]
             else:
-                buf = _F.ConcatBuffer(skip, skip.shape[1] + c_dec + 2, PAD_CHANNELS)
+                buf = _new_buffer(deconv_lv, "level", skip, skip.shape[1] + c_dec + 2)
                 off = buf.copy_in(skip, 0)
             deconv_lv(feat, into=(buf, off))
             if direct_up and (off + c_dec) % 2 == 0:

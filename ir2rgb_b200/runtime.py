@@ -48,7 +48,8 @@ class GraphedFlowNet(torch.nn.Module):
         """Drop the captured graphs (and the padded-weight caches they point into); the next call captures again."""
         self._graphs.clear()
         for m in self.net.modules():
-            m.__dict__.pop("_flowops_wpad", None)
+            for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf"):
+                m.__dict__.pop(k, None)
 
     @torch.no_grad()
     def forward(self, input_A, input_B):

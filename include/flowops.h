@@ -219,6 +219,16 @@ int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_
                           float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
                           int B, int H, int W, void *stream);
 
+/* flowops_flownet2_prep with frame 0 / frame 1 written "space to depth" for FlowNetC's first layer: xa_s2d, xb_s2d are
+ * channels-last [B, H/2 + 1, W/2 + 1, 16] -- channel (py*2+px)*4 + c holds channel c (c < 3; c = 3 is zero) of pixel
+ * (2(Y-1)+py, 2(X-1)+px); block row 0 and block column 0 are a zero border that the CALLER zeroes once (the kernel never
+ * writes it).  The 7x7 stride-2 convolution of FlowNetC.py:18 on the 3-channel frame equals a 4x4 stride-1 convolution
+ * with padding 1 on this tensor with weights W'[co][(py*2+px)*4+c][t][u] = W[co][c][2t+py-1][2u+px-1] (zero where an index
+ * is -1): 16 input channels instead of 3 (4) put the layer on cuDNN's tensor-op kernels.  H, W even. */
+int flowops_flownet2_prep_s2d(const float *inputs, const float *rgb_mean, float rgb_max,
+                              float *x_planar, float *xa_s2d, float *xb_s2d, float *x_nhwc8,
+                              int B, int H, int W, void *stream);
+
 /* ---- 16-bit storage variants (fp16 / bf16 in HBM, fp32 arithmetic) ----------------------------------------
  * The reference's fp16 mode is "fp16 storage, fp32 math" (flownet2_pytorch/main.py:59).  As run it reaches the
  * operators in three ways, and each entry point below reproduces exactly one of them in a single pass, with half the

@@ -50,6 +50,7 @@ SIGNATURES = {
     "flowops_warp_diff_norm_concat_up4_nhwc": (_int, [_vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _int, _int, _int, _int, _vp]),
     "flowops_flownet2_fusion_input_nhwc": (_int, [_vp, _vp, _vp, ctypes.c_float, _vp, _int, _int, _int, _int, _vp]),
     "flowops_flownet2_prep": (_int, [_vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
+    "flowops_flownet2_prep_s2d": (_int, [_vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "flowops_bias_lrelu": (_int, [_vp, _vp, _int, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_bias_lrelu_nhwc_to": (_int, [_vp, _vp, _vp, _sz, _int, _int, _int, ctypes.c_float, _vp, _vp]),
     "flowops_fill_channels_nhwc": (_int, [_vp, _sz, _int, _int, _int, ctypes.c_float, _vp]),

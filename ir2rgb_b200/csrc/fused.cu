@@ -340,9 +340,15 @@ extern "C" int flowops_flownet2_fusion_input_nhwc(const float *x, const float *f
 // ---------------------------------------------------------------------------------------------
 namespace flowops {
 
+// S2D: xa / xb are written "space to depth" instead of as 4-channel frames -- [B, H/2 + 1, W/2 + 1, 16], the four pixels
+// of a 2 x 2 block side by side (channel (py*2+px)*4 + c), shifted down and right by one block (block row 0 and block
+// column 0 are a zero border the caller provides).  A 7 x 7 stride-2 convolution of the frame is then a 4 x 4 stride-1
+// convolution of this tensor with padding 1 (see FlowNetC.conv1_s2d): 16 input channels instead of 4 puts FlowNetC's
+// first layer on cuDNN's tensor-op kernels.
+template <bool S2D>
 __global__ void __launch_bounds__(256) flownet2_prep_kernel(const float *__restrict__ in, const float *__restrict__ mean, float inv_rgb_max,
                                                             float *__restrict__ xp, float4 *__restrict__ xa, float4 *__restrict__ xb,
-                                                            float4 *__restrict__ x8, unsigned hw, size_t total)
+                                                            float4 *__restrict__ x8, unsigned hw, size_t total, unsigned W)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw;
@@ -359,8 +365,13 @@ __global__ void __launch_bounds__(256) flownet2_prep_kernel(const float *__restr
 #pragma unroll
             for (int k = 0; k < 6; ++k) xp[(b * 6 + k) * hw + p] = v[k];
         }
-        if (xa) xa[i] = make_float4(v[0], v[1], v[2], 0.f);
-        if (xb) xb[i] = make_float4(v[3], v[4], v[5], 0.f);
+        size_t ia = i;
+        if (S2D) {
+            const unsigned y = p / W, x = p - y * W, W2 = (W >> 1) + 1, H2 = (hw / W >> 1) + 1;
+            ia = ((b * H2 + (y >> 1) + 1) * W2 + (x >> 1) + 1) * 4 + (y & 1) * 2 + (x & 1);
+        }
+        if (xa) xa[ia] = make_float4(v[0], v[1], v[2], 0.f);
+        if (xb) xb[ia] = make_float4(v[3], v[4], v[5], 0.f);
         if (x8) { x8[2 * i] = make_float4(v[0], v[1], v[2], v[3]); x8[2 * i + 1] = make_float4(v[4], v[5], 0.f, 0.f); }
     }
 }
@@ -380,8 +391,26 @@ extern "C" int flowops_flownet2_prep(const float *inputs, const float *rgb_mean,
     const size_t cap = (size_t)kNumSMs * 8 * 16;
     if (blocks > cap) blocks = cap;
     // tensor / python-scalar on CUDA is tensor * (1.0f / scalar) in ATen; reproduced so that x matches models.py:98 bit for bit
-    flownet2_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
+    flownet2_prep_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
         reinterpret_cast<float4 *>(xa_nhwc4), reinterpret_cast<float4 *>(xb_nhwc4), reinterpret_cast<float4 *>(x_nhwc8),
-        (unsigned)((size_t)H * W), total);
+        (unsigned)((size_t)H * W), total, (unsigned)W);
     return check_launch("flownet2_prep");
+}
+
+extern "C" int flowops_flownet2_prep_s2d(const float *inputs, const float *rgb_mean, float rgb_max,
+                                         float *x_planar, float *xa_s2d, float *xb_s2d, float *x_nhwc8,
+                                         int B, int H, int W, void *stream)
+{
+    FLOWOPS_REQUIRE(inputs && rgb_mean && xa_s2d && xb_s2d, FLOWOPS_EINVAL, "flownet2_prep_s2d: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0 && (size_t)H * W < (1ull << 31), FLOWOPS_EINVAL,
+                    "flownet2_prep_s2d: bad shape %dx%dx%d (H, W must be even)", B, H, W);
+    FLOWOPS_REQUIRE(aligned16(xa_s2d) && aligned16(xb_s2d) && aligned16(x_nhwc8), FLOWOPS_EINVAL, "flownet2_prep_s2d: outputs must be 16-byte aligned");
+    const size_t total = (size_t)B * H * W;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    flownet2_prep_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
+        reinterpret_cast<float4 *>(xa_s2d), reinterpret_cast<float4 *>(xb_s2d), reinterpret_cast<float4 *>(x_nhwc8),
+        (unsigned)((size_t)H * W), total, (unsigned)W);
+    return check_launch("flownet2_prep_s2d");
 }

@@ -291,6 +291,31 @@ def flownet2_prep(inputs, rgb_mean, rgb_max):
     return x, xa, xb, x8
 
 
+_S2D_CACHE = {}
+
+
+def flownet2_prep_s2d(inputs, rgb_mean, rgb_max):
+    """flownet2_prep with the two frames in the space-to-depth layout FlowNetC's first layer reads on the fast path
+    (include/flowops.h): returns (x planar, xa_s2d, xb_s2d, x8).  The s2d tensors are [B, 16, H/2+1, W/2+1] channels_last
+    with a zero first row / column; they are allocated (and zeroed) once per shape and device and REUSED by later calls."""
+    inputs = _require(inputs, "inputs", ndim=5).contiguous()
+    B, C, F2, H, W = inputs.shape
+    if C != 3 or F2 != 2 or H % 2 or W % 2:
+        raise ValueError("inputs must be [B,3,2,H,W] with even H, W, got %s" % (tuple(inputs.shape),))
+    rgb_mean = rgb_mean.reshape(B, 3).contiguous()
+    with torch.cuda.device_of(inputs):
+        cl = dict(device=inputs.device, dtype=torch.float32, memory_format=torch.channels_last)
+        key = (B, H, W, inputs.device)
+        if key not in _S2D_CACHE:
+            _S2D_CACHE[key] = (torch.zeros((B, 16, H // 2 + 1, W // 2 + 1), **cl), torch.zeros((B, 16, H // 2 + 1, W // 2 + 1), **cl))
+        xa, xb = _S2D_CACHE[key]
+        x = torch.empty((B, 6, H, W), device=inputs.device, dtype=torch.float32)
+        x8 = torch.empty((B, 8, H, W), **cl)
+        check(_lib.load().flowops_flownet2_prep_s2d(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb), _p(x8),
+                                                    B, H, W, _stream()), "flownet2_prep_s2d")
+    return x, xa, xb, x8
+
+
 def warp_conf_forward(im1, im2, flow, thresh=0.02, mode=WARP_GRIDSAMPLE):
     im1 = _require(im1, "im1").contiguous()
     im2 = _require(im2, "im2").contiguous()

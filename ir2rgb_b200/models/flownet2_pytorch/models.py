@@ -60,6 +60,7 @@ class FlowNet2(nn.Module):
         self.fuse_glue = True          # use the fused warp/diff/norm kernel when autograd is off
         self.fuse_fusion_input = True  # channels_last body: concat3 (models.py:129-152) from one kernel
         self.fuse_upsample = True      # channels_last body: the x4 bilinear upsamplings folded into the concat kernels
+        self.s2d_conv1 = True          # channels_last body, TF32 convolutions: FlowNetC.conv1 on space-to-depth frames
 
         self.channelnorm = ChannelNorm()
         self.flownetc = FlowNetC.FlowNetC(args, batchNorm=self.batchNorm)
@@ -93,9 +94,17 @@ class FlowNet2(nn.Module):
         tensors between the sub-networks produced directly in the layout and channel count their consumers read --
         no torch.cat, no slice copies, no NCHW<->NHWC conversions, no cuDNN channel re-padding."""
         rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1)
-        x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max))
+        if self.s2d_conv1 and torch.backends.cudnn.allow_tf32 and inputs.shape[3] % 2 == 0 and inputs.shape[4] % 2 == 0:
+            # FlowNetC's first layer on the space-to-depth frames: a 16-channel 4x4 convolution instead of a 3(4)-channel
+            # 7x7 stride-2 one, which cuDNN runs on a pre-Blackwell kernel without shared-memory staging (4.8 % of the
+            # step).  Same sums in another order: on when TF32 convolutions are (the bit-exact path otherwise).
+            x, xa, xb, x8 = _F.flownet2_prep_s2d(inputs, rgb_mean, float(self.rgb_max))
+            frames = (xa, xb, "s2d")
+        else:
+            x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max))
+            frames = (xa, xb)
 
-        flow2_c = self.flownetc(x, frames=(xa, xb))[0]
+        flow2_c = self.flownetc(x, frames=frames)[0]
         if self.fuse_upsample and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
             # `upsample(flow2 * div_flow)` (models.py:106,118) folded into the concat kernel's flow read
             concat1 = _F.warp_diff_norm_concat_up4(x, flow2_c, self.div_flow, self.div_flow)

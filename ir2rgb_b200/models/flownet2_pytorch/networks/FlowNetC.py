@@ -39,6 +39,28 @@ class FlowNetC(nn.Module):
         reference_init(self)
         self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
 
+    def conv1_s2d(self):
+        """conv1 (3 -> 64, 7x7, stride 2, FlowNetC.py:18) as a 4x4 stride-1 convolution over the space-to-depth frame
+        (functional.flownet2_prep_s2d): W'[co][(py*2+px)*4 + c][t][u] = W[co][c][2t+py-1][2u+px-1].  A ConvAct that shares
+        conv1's bias, kept outside the module tree (the state dict is the reference's), rebuilt when conv1's weight changes."""
+        w = self.conv1[0].weight
+        key = (w.data_ptr(), w._version)
+        cache = self.__dict__.get("_flowops_conv1_s2d")
+        if cache is None or cache[0] != key:
+            w7 = w.detach().contiguous()                                     # [64, 3, 7, 7]
+            w8 = torch.zeros(w7.shape[0], 3, 8, 8, device=w.device, dtype=w.dtype)
+            w8[:, :, 1:, 1:] = w7                                            # index k + 1: the tap "-1" is the zero at 0
+            # w8[co, c, 2t + py, 2u + px] -> [co, py, px, c, t, u]
+            w6 = w8.view(w7.shape[0], 3, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4)
+            ws = torch.zeros(w7.shape[0], 2, 2, 4, 4, 4, device=w.device, dtype=w.dtype)
+            ws[:, :, :, :3] = w6
+            conv = nn.Conv2d(16, w7.shape[0], 4, 1, 1, bias=True).to(w.device)
+            conv.weight = nn.Parameter(ws.view(w7.shape[0], 16, 4, 4).contiguous(memory_format=torch.channels_last), requires_grad=False)
+            conv.bias = self.conv1[0].bias
+            cache = (key, _sm.ConvAct(conv, nn.LeakyReLU(_sm.LEAK, inplace=True)))
+            self.__dict__["_flowops_conv1_s2d"] = cache
+        return cache[1]
+
     def tower(self, frame):
         c2 = self.conv2(self.conv1(frame))
         return c2, self.conv3(c2)
@@ -48,9 +70,10 @@ class FlowNetC(nn.Module):
         correlation's input planes directly (flowops_corr_planes_from_conv), so neither a separate activation
         pass nor the correlation's own layout pre-pass runs.  Same values as the plain path, bit for bit."""
         conv3, act3 = self.conv3[0], self.conv3[1]
-        fa, fb = frames if frames is not None else (x[:, 0:3], x[:, 3:])      # frames: channels-last, zero-padded to 4 channels
-        c2a = self.conv2(self.conv1(fa))
-        c2b = self.conv2(self.conv1(fb))
+        fa, fb = frames[:2] if frames is not None else (x[:, 0:3], x[:, 3:])      # frames: channels-last, zero-padded to 4 channels
+        conv1 = self.conv1_s2d() if frames is not None and len(frames) > 2 and frames[2] == "s2d" else self.conv1
+        c2a = self.conv2(conv1(fa))
+        c2b = self.conv2(conv1(fb))
         y3a = F.conv2d(c2a, conv3.weight, None, conv3.stride, conv3.padding)
         y3b = F.conv2d(c2b, conv3.weight, None, conv3.stride, conv3.padding)
         if not (_F._is_nhwc(y3a) and _F._is_nhwc(y3b)):

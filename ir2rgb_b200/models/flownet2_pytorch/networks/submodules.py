@@ -52,7 +52,7 @@ def reset_padded_weights(net):
     """Drop every cached tensor derived from the weights of `net` (needed after weight updates made through `.data`)
     and the cached concat buffers."""
     for m in net.modules():
-        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf"):
+        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d"):
             m.__dict__.pop(k, None)
 
 

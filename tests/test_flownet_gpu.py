@@ -391,3 +391,33 @@ def test_flow_upsampler_kernel_matches_conv_transpose(flowops_lib):
         got = buf.tensor[:, 6:8]
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-6
         assert (buf.tensor[:, :6] == 7.0).all() and (buf.tensor[:, 8:] == 7.0).all()      # neighbours untouched
+
+
+def test_flownetc_first_layer_on_space_to_depth_frames(flowops_lib):
+    """FlowNetC.conv1 (3 -> 64, 7x7, stride 2) as a 4x4 stride-1 convolution over the space-to-depth frame written by
+    flowops_flownet2_prep_s2d: the same sums in another order (fp32 convolutions: <= 1e-5)."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.models import FlowNet2
+    torch.manual_seed(33)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = False, False
+    try:
+        net = FlowNet2().cuda().eval().to(memory_format=torch.channels_last)
+        inputs = 2 * torch.rand(2, 3, 2, 64, 96, device="cuda") - 1
+        mean = inputs.contiguous().view(2, 3, -1).mean(dim=-1)
+        with torch.no_grad():
+            x, xa, xb, x8 = F.flownet2_prep(inputs, mean, 1.0)
+            x2, sa, sb, x82 = F.flownet2_prep_s2d(inputs, mean, 1.0)
+            assert torch.equal(x, x2) and torch.equal(x8, x82)
+            assert sa.shape == (2, 16, 33, 49) and (sa[:, :, 0] == 0).all() and (sa[:, :, :, 0] == 0).all()
+            for frame, s2d in ((xa, sa), (xb, sb)):
+                want = net.flownetc.conv1(frame)
+                got = net.flownetc.conv1_s2d()(s2d)
+                assert got.shape == want.shape
+                assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+            # a second call reuses the cached s2d tensors (border still zero, interior rewritten)
+            inputs2 = inputs.flip(0).contiguous()
+            _, sa2, _, _ = F.flownet2_prep_s2d(inputs2, inputs2.view(2, 3, -1).mean(dim=-1), 1.0)
+            assert sa2.data_ptr() == sa.data_ptr() and (sa2[:, :, 0] == 0).all()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev

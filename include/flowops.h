@@ -307,6 +307,15 @@ int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels, int c_src
 int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const float *bias, float *dst,
                                 int B, int h, int w, int c_dst, int c_off, void *stream);
 
+/* Epilogue of a ConvTranspose2d(kernel 4, stride 2, padding 1) + LeakyReLU (submodules.py:28-31 `deconv`) whose sums were
+ * formed by a 3x3 convolution with 4*C output channels at the input resolution, one group of C per output parity
+ * (ir2rgb_b200 submodules.deconv_as_conv3): y4 [B, h, w, 4*C] channels-last ->
+ *   dst[b, 2m+py, 2n+px, c_off + co] = LeakyReLU(y4[b, m, n, (py*2+px)*C + co] + bias[co])
+ * i.e. bias, activation and depth-to-space in one pass into the concat buffer dst [B, 2h, 2w, c_dst].  C, c_off, c_dst
+ * multiples of 4. */
+int flowops_bias_lrelu_d2s_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
+                                   int c_dst, int c_off, float slope, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

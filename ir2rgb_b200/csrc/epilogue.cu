@@ -257,3 +257,55 @@ extern "C" int flowops_flow_deconv_nhwc_to(const float *flow, const float *weigh
                                                                                   B, h, w, (unsigned)c_dst, (unsigned)c_off);
     return check_launch("flow_deconv_nhwc_to");
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of a ConvTranspose2d(k4, s2, p1) that was computed as a 3x3 convolution with 4*C output channels at the INPUT
+// resolution (one group of C channels per output parity; submodules.deconv_as_conv3): bias + LeakyReLU + depth-to-space,
+// written into channels [c_off, c_off + C) of the channels-last concat buffer at twice the resolution.
+//   dst[b, 2m+py, 2n+px, c_off + co] = lrelu(y4[b, m, n, (py*2+px)*C + co] + bias[co])
+// A thread moves one float4: reads are fully coalesced, writes are C-float runs per output pixel.
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+__global__ void __launch_bounds__(256) bias_lrelu_d2s_kernel(const float4 *__restrict__ y4, const float *__restrict__ bias,
+                                                             float *__restrict__ dst, size_t total_q, unsigned h, unsigned w,
+                                                             unsigned cq, unsigned c_dst, unsigned c_off, float slope)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_q; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned q = (unsigned)(i % cq);                 // float4 index inside the parity's C channels
+        size_t r = i / cq;
+        const unsigned par = (unsigned)(r & 3); r >>= 2;
+        const unsigned n = (unsigned)(r % w); r /= w;
+        const unsigned m = (unsigned)(r % h);
+        const size_t b = r / h;
+        const float4 v = y4[i];
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias) + q);
+        float4 o;
+        o.x = __fadd_rn(v.x, bb.x); o.x = o.x > 0.f ? o.x : __fmul_rn(o.x, slope);
+        o.y = __fadd_rn(v.y, bb.y); o.y = o.y > 0.f ? o.y : __fmul_rn(o.y, slope);
+        o.z = __fadd_rn(v.z, bb.z); o.z = o.z > 0.f ? o.z : __fmul_rn(o.z, slope);
+        o.w = __fadd_rn(v.w, bb.w); o.w = o.w > 0.f ? o.w : __fmul_rn(o.w, slope);
+        const size_t pix = (b * (2 * h) + 2 * m + (par >> 1)) * (size_t)(2 * w) + 2 * n + (par & 1);
+        *reinterpret_cast<float4 *>(dst + pix * c_dst + c_off + 4 * q) = o;
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_bias_lrelu_d2s_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
+                                              int c_dst, int c_off, float slope, void *stream)
+{
+    FLOWOPS_REQUIRE(y4 && bias && dst, FLOWOPS_EINVAL, "bias_lrelu_d2s_nhwc_to: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && (C & 3) == 0 && c_off >= 0 && c_off + C <= c_dst && ((c_off | c_dst) & 3) == 0,
+                    FLOWOPS_EINVAL, "bias_lrelu_d2s_nhwc_to: bad shape / channel range (C %d, channels %d + C of %d; multiples of 4)", C, c_off, c_dst);
+    FLOWOPS_REQUIRE(aligned16(y4) && aligned16(dst) && aligned16(bias), FLOWOPS_EINVAL, "bias_lrelu_d2s_nhwc_to: 16-byte alignment required");
+    const size_t total_q = (size_t)B * h * w * C;            // = B*h*w*4*C / 4 float4s
+    size_t blocks = (total_q + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    bias_lrelu_d2s_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(y4), bias, dst, total_q,
+                                                                                 (unsigned)h, (unsigned)w, (unsigned)(C / 4), (unsigned)c_dst,
+                                                                                 (unsigned)c_off, slope);
+    return check_launch("bias_lrelu_d2s_nhwc_to");
+}

@@ -307,7 +307,7 @@ def flownet2_prep_s2d(inputs, rgb_mean, rgb_max):
         cl = dict(device=inputs.device, dtype=torch.float32, memory_format=torch.channels_last)
         key = (B, H, W, inputs.device)
         if key not in _S2D_CACHE:
-            _S2D_CACHE[key] = (torch.zeros((B, 16, H // 2 + 1, W // 2 + 1), **cl), torch.zeros((B, 16, H // 2 + 1, W // 2 + 1), **cl))
+            _S2D_CACHE[key] = tuple(torch.empty((B, 16, H // 2 + 1, W // 2 + 1), **cl).zero_() for _ in range(2))
         xa, xb = _S2D_CACHE[key]
         x = torch.empty((B, 6, H, W), device=inputs.device, dtype=torch.float32)
         x8 = torch.empty((B, 8, H, W), **cl)
@@ -412,6 +412,16 @@ class ConcatBuffer:
             check(_lib.load().flowops_flow_deconv_nhwc_to(_p(flow), _p(weight), _p(bias), _p(self.tensor), B, h, w, self.c_pad, c_off,
                                                           _stream()), "flow_deconv_nhwc_to")
         return c_off + 2
+
+    def bias_lrelu_d2s_in(self, y4, bias, slope, c_off):
+        """dst[b, 2m+py, 2n+px, c_off + co] = LeakyReLU(y4[b, m, n, (py*2+px)*C + co] + bias[co]): the epilogue of a k4 s2 p1
+        transposed convolution computed as a 3x3 convolution with 4*C output channels at the input resolution (one group
+        of C per output parity) -- bias, activation and depth-to-space in one pass into the concat slice."""
+        B, C4, h, w = y4.shape
+        with torch.cuda.device_of(y4):
+            check(_lib.load().flowops_bias_lrelu_d2s_nhwc_to(_p(y4), _p(bias), _p(self.tensor), B, h, w, C4 // 4, self.c_pad, c_off,
+                                                             ctypes.c_float(slope), _stream()), "bias_lrelu_d2s_nhwc_to")
+        return c_off + C4 // 4
 
     def bias_lrelu_in(self, y, bias, slope, c_off, in_place_too=False):
         """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y; with in_place_too

@@ -52,7 +52,7 @@ def reset_padded_weights(net):
     """Drop every cached tensor derived from the weights of `net` (needed after weight updates made through `.data`)
     and the cached concat buffers."""
     for m in net.modules():
-        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d"):
+        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
             m.__dict__.pop(k, None)
 
 
@@ -149,6 +149,13 @@ class ConvAct(nn.Sequential):
                         if skip is not None:
                             skip.buf = sbuf
                         return None if into is not None else y
+            if (isinstance(conv, nn.ConvTranspose2d) and into is not None and DECONV_AS_CONV3 and torch.backends.cudnn.allow_tf32
+                    and _F._is_nhwc(x) and _deconv_as_conv3_ok(conv, into[1])):
+                # narrow transposed convolution (<= 16 output channels: cuDNN's strided-dgrad kernel runs it at a fraction
+                # of the tensor-op rate) as a 3x3 convolution with 4 * C output channels + depth-to-space epilogue, where
+                # timing both once says it is faster
+                if _deconv_conv3_run(self, conv, x, into):
+                    return None
             y = _raw_conv(conv, x, None)
             if into is not None:
                 buf, c_off = into
@@ -168,6 +175,63 @@ class ConvAct(nn.Sequential):
                 y = layer(y)
             return y
         return super().forward(x)
+
+
+DECONV_AS_CONV3 = True
+
+
+def _deconv_as_conv3_ok(conv, c_off):
+    return (conv.groups == 1 and tuple(conv.kernel_size) == (4, 4) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (1, 1)
+            and tuple(conv.output_padding) == (0, 0) and tuple(conv.dilation) == (1, 1) and conv.out_channels <= 16
+            and conv.out_channels % 4 == 0 and c_off % 4 == 0 and conv.bias is not None)
+
+
+def deconv_as_conv3_weight(conv, w):
+    """ConvTranspose2d(k4, s2, p1) weight w [Cin, C, 4, 4] (possibly zero-padded along Cin) -> the [4*C, Cin, 3, 3] weight of
+    the 3x3 convolution that forms all four output parities at the input resolution:
+        out[2m+py] = in[m-1] w[3] + in[m] w[1]  (py = 0),   in[m] w[2] + in[m+1] w[0]  (py = 1)        (same along x)
+    so parity (py, px), channel co is output channel (py*2+px)*C + co with taps (dr, ky) in {(-1,3),(0,1)} / {(0,2),(1,0)};
+    the five taps a parity does not use are zero.  Cached on the module (channels_last)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape))
+    cache = conv.__dict__.get("_flowops_wconv3")
+    if cache is None or cache[0] != key:
+        cin, c = w.shape[0], w.shape[1]
+        w3 = w.new_zeros(4 * c, cin, 3, 3)
+        taps = {0: ((0, 3), (1, 1)), 1: ((1, 2), (2, 0))}          # py -> ((dr + 1, ky), ...)
+        wt = w.detach().permute(1, 0, 2, 3)                        # [C, Cin, 4, 4]
+        for py in (0, 1):
+            for px in (0, 1):
+                g = (py * 2 + px) * c
+                for r, ky in taps[py]:
+                    for q, kx in taps[px]:
+                        w3[g:g + c, :, r, q] = wt[:, :, ky, kx]
+        cache = (key, w3.contiguous(memory_format=torch.channels_last))
+        conv.__dict__["_flowops_wconv3"] = cache
+    return cache[1]
+
+
+def _deconv_conv3_run(act, conv, x, into):
+    """Run (and, the first time per shape, time against strided dgrad + epilogue) the 3x3-convolution form; False when the
+    plain path is faster for this layer."""
+    buf, c_off = into
+    slope = act[1].negative_slope
+    w3 = deconv_as_conv3_weight(conv, padded_weight(conv, x.shape[1]))
+
+    def as_conv3():
+        buf.bias_lrelu_d2s_in(F.conv2d(x, w3, None, 1, 1), conv.bias, slope, c_off)
+    key = (tuple(x.shape), buf.c_pad, c_off)
+    choice = conv.__dict__.setdefault("_flowops_conv3_choice", {})
+    if key not in choice:
+        if torch.cuda.is_current_stream_capturing():
+            return False
+
+        def plain():
+            buf.bias_lrelu_in(_raw_conv(conv, x, None), conv.bias, slope, c_off)
+        choice[key] = _cf._time3(as_conv3) < 0.97 * _cf._time3(plain)
+    if not choice[key]:
+        return False
+    as_conv3()
+    return True
 
 
 class Skip:

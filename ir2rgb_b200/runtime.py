@@ -48,7 +48,7 @@ class GraphedFlowNet(torch.nn.Module):
         """Drop the captured graphs (and the padded-weight caches they point into); the next call captures again."""
         self._graphs.clear()
         for m in self.net.modules():
-            for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d"):
+            for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
                 m.__dict__.pop(k, None)
 
     @torch.no_grad()

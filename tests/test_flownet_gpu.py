@@ -421,3 +421,28 @@ def test_flownetc_first_layer_on_space_to_depth_frames(flowops_lib):
             assert sa2.data_ptr() == sa.data_ptr() and (sa2[:, :, 0] == 0).all()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(168, 16, 32, 48), (24, 8, 9, 7), (40, 16, 1, 1)])
+def test_narrow_deconv_as_conv3_with_depth_to_space_epilogue(flowops_lib, cin, cout, h, w):
+    """ConvTranspose2d(k4, s2, p1) + bias + LeakyReLU computed as a 3x3 convolution with 4*C output channels and the
+    depth-to-space epilogue kernel (flowops_bias_lrelu_d2s_nhwc_to), against torch; written into a concat slice."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(37)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        conv = torch.nn.ConvTranspose2d(cin, cout, 4, 2, 1).cuda().to(memory_format=torch.channels_last)
+        x = torch.randn(2, cin, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
+        buf = F.ConcatBuffer(x, cout + 12, 8, shape=(2, 2 * h, 2 * w))
+        buf.tensor.fill_(5.0)
+        with torch.no_grad():
+            want = torch.nn.functional.leaky_relu(conv(x), 0.1)
+            w3 = sm.deconv_as_conv3_weight(conv, conv.weight)
+            buf.bias_lrelu_d2s_in(torch.nn.functional.conv2d(x, w3, None, 1, 1), conv.bias, 0.1, 8)
+        got = buf.tensor[:, 8:8 + cout]
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+        assert (buf.tensor[:, :8] == 5.0).all() and (buf.tensor[:, 8 + cout:] == 5.0).all()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

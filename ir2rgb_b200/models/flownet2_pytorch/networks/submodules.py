@@ -151,7 +151,7 @@ class ConvAct(nn.Sequential):
                         return None if into is not None else y
             if (isinstance(conv, nn.ConvTranspose2d) and into is not None and DECONV_AS_CONV3 and torch.backends.cudnn.allow_tf32
                     and _F._is_nhwc(x) and _deconv_as_conv3_ok(conv, into[1])):
-                # narrow transposed convolution (<= 16 output channels: cuDNN's strided-dgrad kernel runs it at a fraction
+                # narrow transposed convolution (<= 32 output channels: cuDNN's strided-dgrad kernel runs it at a fraction
                 # of the tensor-op rate) as a 3x3 convolution with 4 * C output channels + depth-to-space epilogue, where
                 # timing both once says it is faster
                 if _deconv_conv3_run(self, conv, x, into):
@@ -182,7 +182,7 @@ DECONV_AS_CONV3 = True
 
 def _deconv_as_conv3_ok(conv, c_off):
     return (conv.groups == 1 and tuple(conv.kernel_size) == (4, 4) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (1, 1)
-            and tuple(conv.output_padding) == (0, 0) and tuple(conv.dilation) == (1, 1) and conv.out_channels <= 16
+            and tuple(conv.output_padding) == (0, 0) and tuple(conv.dilation) == (1, 1) and conv.out_channels <= 32
             and conv.out_channels % 4 == 0 and c_off % 4 == 0 and conv.bias is not None)
 
 

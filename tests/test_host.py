@@ -191,3 +191,46 @@ def test_ctypes_shims_have_the_pybind_signatures():
         for n, m in saved.items():
             if m is not None:
                 sys.modules[n] = m
+
+
+def test_deconv_as_conv3_weight_reproduces_conv_transpose():
+    """submodules.deconv_as_conv3_weight: a ConvTranspose2d(k4, s2, p1) equals a 3x3 convolution with 4*C output channels at
+    the input resolution followed by depth-to-space (fp64 on the CPU; the GPU test covers the epilogue kernel)."""
+    import torch
+    import torch.nn.functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks.submodules import deconv_as_conv3_weight
+    torch.manual_seed(0)
+    conv = torch.nn.ConvTranspose2d(10, 8, 4, 2, 1).double()
+    x = torch.randn(2, 10, 5, 7, dtype=torch.float64)
+    want = conv(x)
+    y4 = F.conv2d(x, deconv_as_conv3_weight(conv, conv.weight), None, 1, 1)
+    got = torch.zeros_like(want)
+    for py in (0, 1):
+        for px in (0, 1):
+            g = (py * 2 + px) * 8
+            got[:, :, py::2, px::2] = y4[:, g:g + 8] + conv.bias.view(1, -1, 1, 1)
+    assert (got - want).abs().max().item() <= 1e-12
+
+
+def test_space_to_depth_first_layer_weights():
+    """FlowNetC.conv1_s2d: the 7x7 stride-2 first layer as a 4x4 stride-1 convolution over the space-to-depth frame
+    (layout of flowops_flownet2_prep_s2d restated with torch indexing), fp64 on the CPU."""
+    import torch
+    import torch.nn.functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks import FlowNetC
+    from ir2rgb_b200.models.flownet2_pytorch.models import MyDict
+    torch.manual_seed(1)
+    args = MyDict()
+    args.rgb_max, args.fp16, args.grads = 1, False, {}
+    net = FlowNetC.FlowNetC(args, batchNorm=False).double()
+    B, H, W = 2, 12, 16
+    x = torch.randn(B, 3, H, W, dtype=torch.float64)
+    s2d = torch.zeros(B, 16, H // 2 + 1, W // 2 + 1, dtype=torch.float64)
+    for py in (0, 1):
+        for px in (0, 1):
+            s2d[:, (py * 2 + px) * 4:(py * 2 + px) * 4 + 3, 1:, 1:] = x[:, :, py::2, px::2]
+    with torch.no_grad():
+        want = net.conv1(x)
+        got = net.conv1_s2d()(s2d)
+    assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-12
+    assert "_flowops_conv1_s2d" not in dict(net.named_modules()) and len(net.state_dict()) == len(FlowNetC.FlowNetC(args, batchNorm=False).state_dict())

@@ -23,6 +23,15 @@ namespace flowops {
 
 constexpr float kMagic15 = 12582912.f;   // 1.5 * 2^23: ulp is 1 on [2^23, 2^24)
 
+// Tuning macro (variant builds: python -m ir2rgb_b200.build --out ... -DFLOWOPS_TUNE_WARP2D=4): shape of the patch of
+// pixels one warp of the forward row-walking kernel covers: 0 = 32 x 1 (a row segment), 2 = 16 x 2, 4 = 8 x 4.
+#ifndef FLOWOPS_TUNE_WARP2D
+#define FLOWOPS_TUNE_WARP2D 0
+#endif
+#if FLOWOPS_TUNE_WARP2D
+constexpr int kRowStep = FLOWOPS_TUNE_WARP2D, kWarpCols = 32 / FLOWOPS_TUNE_WARP2D;
+#endif
+
 // v is an integer-valued float in [0, 2^22)
 __device__ __forceinline__ int small_float_as_int(float v)
 {
@@ -296,10 +305,23 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
 {
     constexpr bool NEED_REF = EPI != EPI_STORE;
     constexpr bool NEED_SELF = EPI == EPI_CONCAT;
+#if FLOWOPS_TUNE_WARP2D
+    // a warp covers a 2-D patch (kWarpCols columns x kRowStep rows) instead of 32 x 1: its 32 gather targets then span
+    // fewer image rows (fewer L1 lines per request) at the price of 32 B .. 64 B row segments for the coalesced accesses
+    constexpr int RS = kRowStep;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+    const int x = blockIdx.x * (8 * kWarpCols) + wrp * kWarpCols + (lane % kWarpCols);
+    const int yb = blockIdx.y * (RS * a.rows);
+    const int y0 = yb + lane / kWarpCols;
+    if (x >= a.W || y0 >= a.H) return;
+    const int y1 = min(yb + RS * a.rows, a.H);
+#else
+    constexpr int RS = 1;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
     if (x >= a.W || y0 >= a.H) return;
     const int y1 = min(y0 + a.rows, a.H);
+#endif
     const unsigned hw = (unsigned)a.H * a.W, W = (unsigned)a.W;
     const size_t b = blockIdx.z;
     const float *src = a.img + b * a.img_bs;
@@ -322,11 +344,11 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
     float dx, dy;
     if (UP4) up4_flow(lo, hwl, Wl, Hl, ucol, y0, a.flow_mul, dx, dy);
     else { dx = ldg_stream(fl); dy = ldg_stream(fl + hw); }
-    for (int y = y0; y < y1; ++y) {
+    for (int y = y0; y < y1; y += RS) {
         float ndx = 0.f, ndy = 0.f;
-        if (y + 1 < y1) {                                                                 // next row's flow
-            if (UP4) up4_flow(lo, hwl, Wl, Hl, ucol, y + 1, a.flow_mul, ndx, ndy);
-            else { ndx = ldg_stream(fl + W); ndy = ldg_stream(fl + W + hw); }
+        if (y + RS < y1) {                                                                // next row's flow
+            if (UP4) up4_flow(lo, hwl, Wl, Hl, ucol, y + RS, a.flow_mul, ndx, ndy);
+            else { ndx = ldg_stream(fl + RS * W); ndy = ldg_stream(fl + RS * W + hw); }
         }
         PixPrep<MODE> cur;
         PixVals<CT> vcur;
@@ -334,7 +356,7 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
         pix_gather<CT, NEED_REF, NEED_SELF>(vcur, cur, src, ref, self, hw);
         pix_finish<MODE, CT, EPI, WRITE_WARPED>(a, cur, vcur, out, aux, hw, dx, dy);
         dx = ndx; dy = ndy;
-        fl += W; ref += W; self += W; out += W; aux += (size_t)W * aux_px; yfl = __fadd_rn(yfl, 1.f);
+        fl += RS * W; ref += RS * W; self += RS * W; out += RS * W; aux += (size_t)(RS * W) * aux_px; yfl = __fadd_rn(yfl, (float)RS);
     }
 }
 
@@ -373,6 +395,10 @@ static inline void launch_warp_rows(WarpArgs a, cudaStream_t st)
         if (a.aux) c.aux = a.aux + (size_t)b0 * a.aux_bs;
         dim3 grid, block;
         warp_rows_shape(c.B, c.H, c.W, c.rows, grid, block);
+#if FLOWOPS_TUNE_WARP2D
+        block = dim3(256, 1, 1);
+        grid = dim3((c.W + 8 * kWarpCols - 1) / (8 * kWarpCols), (c.H + kRowStep * c.rows - 1) / (kRowStep * c.rows), c.B);
+#endif
         if (a.C == 3) warp_rows_kernel<MODE, 3, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);
         else if (a.C == 2) warp_rows_kernel<MODE, 2, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);
         else warp_rows_kernel<MODE, 1, EPI, WRITE_WARPED, UP4><<<grid, block, 0, st>>>(c);

@@ -420,11 +420,14 @@ def main():
                 line["roofline"] = dict(common, kernel="corr_fwd_tc (tcgen05 3xTF32; input planes are written by the conv3 epilogue kernel)",
                                         bound="tensor", achieved=flop / mean_us / 1e6, peak=pk["tf32_tflops"], unit="TFLOP/s",
                                         frac=flop / mean_us / 1e6 / pk["tf32_tflops"],
+                                        frac_3xtf32=flop / mean_us / 1e6 / (pk["tf32_tflops"] / 3.0),
                                         peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                                         executed_tflops=executed / mean_us / 1e6, frac_executed=executed / mean_us / 1e6 / pk["tf32_tflops"],
                                         executed_over_algorithmic=3.0 * 1024.0 / 441.0,
                                         x_fp32_pipe_peak=flop / mean_us / 1e6 / max(ffma_idle or ffma, ffma),
-                                        note="algorithmic throughput exceeds what any FP32-FMA kernel can reach when x_fp32_pipe_peak > 1")
+                                        note="frac = algorithmic / TF32 peak; frac_3xtf32 = against TF32 peak / 3, the ceiling of ANY "
+                                             "fp32-accurate (3xTF32) tensor-core kernel; frac_executed = flops the tensor pipe executes / "
+                                             "TF32 peak; x_fp32_pipe_peak > 1 means faster than any FP32-FMA kernel can be")
             else:
                 line["roofline"] = dict(common, kernel="corr_fwd_fast (input planes are written by the conv3 epilogue kernel)" if split
                                         else "corr_fwd (corr_planarize + corr_fwd_fast)", bound="fp32",

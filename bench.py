@@ -302,6 +302,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # whatever NCCL does print goes to stderr
         dist.init_process_group("nccl", device_id=device)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark     # True: as the reference does (models/models.py:26)
 
@@ -344,7 +345,7 @@ def main():
         # public runtime helper: H2D of micro-batch i+1 and D2H of i-1 overlap the computation of micro-batch i
         from ir2rgb_b200.runtime import HostPipeline
         pipe = HostPipeline(net, device)
-        mb_host = mb if B_local >= 2 * mb else max(1, B_local // 2)     # at least two micro-batches so copies overlap compute
+        mb_host = mb      # copies overlap computation ACROSS steps (next_inputs / wait=False below), so one micro-batch per step is fine
         # a stream of batches: the next batch's first copy-in and this batch's last copy-out run under computation
         # (every step still copies all of its frames in and all of its results out inside the timed region; timed()
         # synchronises the device, and with it both copy streams, before it stops the clock)

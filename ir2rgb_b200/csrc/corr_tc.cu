@@ -37,11 +37,8 @@ namespace flowops {
 namespace tc {
 
 constexpr int kD = 21, kR = 10;
-constexpr int TH = 16, TW = 8;                  // pixel tile (plane rows x plane columns)
-constexpr int M = TH * TW;                      // 128 = UMMA M
-constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;   // 36 x 28 window
-constexpr int QROWS = WH / 4;                   // 9 window rows per work item
-constexpr int NUSED = QROWS * WW;               // 252 accumulator columns in use
+constexpr int M = 128;                          // pixels per tile = UMMA M
+constexpr int NUSED = 252;                      // accumulator columns in use: a quarter of the window (both tile shapes)
 constexpr int NPAD = 256;                       // one UMMA N = 256
 constexpr int KC = 8;                           // channels per pipeline stage = K of one tf32 UMMA (32 bytes)
 constexpr int STAGES = 6;
@@ -58,6 +55,16 @@ constexpr int EPI_STG_BYTES = 32 * kD * 4;      // one window row of a warp's 32
 constexpr int SMEM_BARRIERS = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + N_EPI_WARPS * EPI_STG_BYTES + SMEM_BARRIERS + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// Pixel tile (plane rows x plane columns, TH * TW = 128) and its window: (TH + 20) x (TW + 20) f2 positions, processed in
+// four quarters of QROWS window rows.  16 x 8: window 36 x 28, quarters of 9 rows; 8 x 16: window 28 x 36, quarters of 7
+// rows -- 252 accumulator columns either way.  The host picks the shape that wastes fewer partial tiles.
+template <int TH_, int TW_> struct Tile {
+    static constexpr int TH = TH_, TW = TW_;
+    static constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;
+    static constexpr int QROWS = WH / 4;
+    static_assert(TH * TW == M && WH % 4 == 0 && QROWS * WW == NUSED, "tile shape");
+};
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
@@ -138,6 +145,7 @@ struct Params {
 };
 
 struct Item { int plane, Y0, X0, h; };          // h: which quarter of the window (rows 9h .. 9h+8)
+template <class T>
 __device__ __forceinline__ Item decode_item(int item, const Params &p)
 {
     Item it;
@@ -146,13 +154,18 @@ __device__ __forceinline__ Item decode_item(int item, const Params &p)
     const int tx = t % p.tilesX; t /= p.tilesX;
     const int ty = t % p.tilesY;
     it.plane = t / p.tilesY;
-    it.Y0 = ty * TH; it.X0 = tx * TW;
+    it.Y0 = ty * T::TH; it.X0 = tx * T::TW;
     return it;
 }
 
+// T: tile shape.  NCHW = false: channels-last store (LeakyReLU folded in) through a shared-memory transpose, A rows arrive
+// as m = x*TH + y.  NCHW = true: the reference's [B, 441, H, W] layout stored straight from registers, A rows arrive as
+// m = y*TW + x so that a warp holds whole tile rows (8 or 16 pixels of one output row per store segment).
+template <class T, bool NCHW>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p)
 {
+    constexpr int QROWS = T::QROWS, WW = T::WW, TW = T::TW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));           // generic-address view of the aligned base
@@ -210,15 +223,16 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             long long w_empty = 0;
             const long long t_start = clock64();
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item w = decode_item(item, p);
+                const Item w = decode_item<T>(item, p);
                 for (int kb = 0; kb < p.CB; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
                     w_empty += mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
                     mbar_expect_tx(bar_full(s), A_BYTES + B_TX);
                     const uint32_t dst = base + s * STAGE_BYTES;
-                    // A: dims (c%8, Y, X, c/8, plane): rows land in shared memory as m = x_local * 16 + y_local
-                    tma_load_5d(dst, &tmA, 0, w.Y0, w.X0, kb, w.plane, bar_full(s));
+                    // A: map dims (c%8, Y, X, ...) -> rows m = x_local * TH + y_local; NCHW: (c%8, X, Y, ...) -> m = y_local * TW + x_local
+                    if (NCHW) tma_load_5d(dst, &tmA, 0, w.X0, w.Y0, kb, w.plane, bar_full(s));
+                    else      tma_load_5d(dst, &tmA, 0, w.Y0, w.X0, kb, w.plane, bar_full(s));
                     // B: dims (c%8, X, Y, c/8, plane): rows n = wy_local * 28 + wx_local; zero fill outside the plane
                     tma_load_5d(dst + A_BYTES, &tmB, 0, w.X0 - kR, w.Y0 - kR + QROWS * w.h, kb, w.plane, bar_full(s));
                 }
@@ -306,51 +320,106 @@ corr_fwd_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ew = warp - (2 + N_SPLIT_WARPS);                   // 0..7
         const int q = warp & 3;                                      // TMEM lane quarter this warp may read
         const int eh = ew >> 2;                                      // even / odd window rows of the item
-        const int m = 32 * q + lane;                                 // accumulator row = x_local * 16 + y_local
-        const int r = m & 15, c = m >> 4, sel = lane >> 4;           // c = 2q + sel
-        float *stg = reinterpret_cast<float *>(gen + (stg_base - base) + ew * EPI_STG_BYTES);
+        const int m = 32 * q + lane;                                 // accumulator row
         uint32_t j = 0;
         long long w_tfull = 0, t_epi = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
-            const Item w = decode_item(item, p);
-            const int acc = j & 1;
-            const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
-            const int Y = w.Y0 + r, X = w.X0 + c;
-            const bool pix_ok = Y < p.PH && X < p.PW;
-            const int pix_ofs = ((n * p.H + 2 * Y + py) * p.W + 2 * X + px) * p.c_dst + p.c_off;
-            w_tfull += mbar_wait_b(bar_tfull(acc), (j >> 1) & 1);
-            const long long te0 = clock64();
-            tc_fence_after();
+        if constexpr (!NCHW) {
+            const int r = m % T::TH, c = m / T::TH;                  // m = x_local * TH + y_local
+            constexpr int LPC = T::TH;                               // lanes per tile column inside a warp
+            const int sel = lane / LPC;                              // column of this lane relative to the warp's first one
+            constexpr int NSEL = 32 / LPC;                           // 2 (16 x 8 tile) or 4 (8 x 16)
+            constexpr int NLOAD = kD + NSEL - 1 <= 24 ? 24 : 32;
+            float *stg = reinterpret_cast<float *>(gen + (stg_base - base) + ew * EPI_STG_BYTES);
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+                const Item w = decode_item<T>(item, p);
+                const int acc = j & 1;
+                const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
+                const int Y = w.Y0 + r, X = w.X0 + c;
+                const bool pix_ok = Y < p.PH && X < p.PW;
+                const int pix_ofs = ((n * p.H + 2 * Y + py) * p.W + 2 * X + px) * p.c_dst + p.c_off;
+                w_tfull += mbar_wait_b(bar_tfull(acc), (j >> 1) & 1);
+                const long long te0 = clock64();
+                tc_fence_after();
 #pragma unroll 1
-            for (int wl = eh; wl < QROWS; wl += 2) {                 // window row of this item handled now
-                const int tj = QROWS * w.h + wl - r;                 // vertical displacement index of that row for my pixel
-                float v[24];
-                const uint32_t taddr = tmem + 256u * acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW + 2 * q);
-                tmem_ld16(taddr, v);
-                tmem_ld8(taddr + 16, v + 16);
-                tmem_ld_wait();
-                __syncwarp();                                        // previous row's staging fully read
+                for (int wl = eh; wl < QROWS; wl += 2) {             // window row of this item handled now
+                    const int tj = QROWS * w.h + wl - r;             // vertical displacement index of that row for my pixel
+                    float v[NLOAD];
+                    const uint32_t taddr = tmem + 256u * acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW + NSEL * q);
+                    tmem_ld16(taddr, v);
+                    if (NLOAD == 24) tmem_ld8(taddr + 16, v + 16); else tmem_ld16(taddr + 16, v + 16);
+                    tmem_ld_wait();
+                    __syncwarp();                                    // previous row's staging fully read
 #pragma unroll
-                for (int i = 0; i < kD; ++i) {
-                    float t = sel ? v[i + 1] : v[i];
-                    t = div_nelems(t, p.nelems, p.inv_nelems);
-                    t = t > 0.f ? t : __fmul_rn(t, p.slope);
-                    stg[lane * kD + i] = t;
+                    for (int i = 0; i < kD; ++i) {
+                        float t = v[i];
+                        if (NSEL == 2) t = sel ? v[i + 1] : v[i];
+                        else t = sel == 0 ? v[i] : (sel == 1 ? v[i + 1] : (sel == 2 ? v[i + 2] : v[i + 3]));
+                        t = div_nelems(t, p.nelems, p.inv_nelems);
+                        t = t > 0.f ? t : __fmul_rn(t, p.slope);
+                        stg[lane * kD + i] = t;
+                    }
+                    const int my_ofs = (pix_ok && tj >= 0 && tj < kD) ? pix_ofs + tj * kD : -1;
+                    __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < kD; ++e) {                   // 32 x 21 values, 32 per trip, pixel-major
+                        const int f = e * 32 + lane;
+                        const int pl = f / kD, i = f - pl * kD;
+                        const int ofs = __shfl_sync(0xffffffffu, my_ofs, pl);
+                        if (ofs >= 0) p.out[ofs + i] = stg[f];
+                    }
                 }
-                const int my_ofs = (pix_ok && tj >= 0 && tj < kD) ? pix_ofs + tj * kD : -1;
+                tc_fence_before();
                 __syncwarp();
-#pragma unroll
-                for (int e = 0; e < kD; ++e) {                       // 32 x 21 values, 32 per trip, pixel-major
-                    const int f = e * 32 + lane;
-                    const int pl = f / kD, i = f - pl * kD;
-                    const int ofs = __shfl_sync(0xffffffffu, my_ofs, pl);
-                    if (ofs >= 0) p.out[ofs + i] = stg[f];
-                }
+                if (lane == 0) mbar_arrive(bar_tempty(acc));
+                t_epi += clock64() - te0;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty(acc));
-            t_epi += clock64() - te0;
+        } else {
+            // NCHW: m = y_local * TW + x_local, so this warp holds 32 / TW whole tile rows; for a fixed channel a store
+            // instruction writes 32 / TW row segments of TW pixels (stride 2 in the image: the other column parity's tile
+            // fills the gaps).  The per-lane column offset c is taken out with a select tree (no shared-memory staging).
+            const int r = m / TW, c = m % TW;
+            constexpr int NLOAD = (kD + TW - 1 + 3) / 4 * 4;         // 28 (TW = 8) or 36 (TW = 16) columns of the window row
+            const size_t hw = (size_t)p.H * p.W;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+                const Item w = decode_item<T>(item, p);
+                const int acc = j & 1;
+                const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
+                const int Y = w.Y0 + r, X = w.X0 + c;
+                const bool pix_ok = Y < p.PH && X < p.PW;
+                float *pix = p.out + (size_t)n * (kD * kD) * hw + (size_t)(2 * Y + py) * p.W + (2 * X + px);
+                w_tfull += mbar_wait_b(bar_tfull(acc), (j >> 1) & 1);
+                const long long te0 = clock64();
+                tc_fence_after();
+#pragma unroll 1
+                for (int wl = eh; wl < QROWS; wl += 2) {
+                    const int tj = QROWS * w.h + wl - r;
+                    float v[40];
+                    const uint32_t taddr = tmem + 256u * acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(wl * WW);
+                    tmem_ld16(taddr, v);
+                    if (NLOAD == 28) { tmem_ld8(taddr + 16, v + 16); tmem_ld8(taddr + 20, v + 20); }      // columns 0..27 (20..23 twice)
+                    else { tmem_ld16(taddr + 16, v + 16); tmem_ld8(taddr + 28, v + 28); }                // columns 0..35
+                    tmem_ld_wait();
+                    // v[i] <- v[i + c]: one select level per bit of c
+#pragma unroll
+                    for (int bit = 1; bit < TW; bit <<= 1) {
+                        const bool on = (c & bit) != 0;
+#pragma unroll
+                        for (int i = 0; i < NLOAD - bit; ++i) v[i] = on ? v[i + bit] : v[i];
+                    }
+                    if (pix_ok && tj >= 0 && tj < kD) {
+                        float *dst = pix + (size_t)(tj * kD) * hw;
+#pragma unroll
+                        for (int i = 0; i < kD; ++i) {
+                            stg_stream(dst, div_nelems(v[i], p.nelems, p.inv_nelems));
+                            dst += hw;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty(acc));
+                t_epi += clock64() - te0;
+            }
         }
         if (p.trace && ew == 0 && lane == 0) { p.trace[blockIdx.x * 8 + 4] = w_tfull; p.trace[blockIdx.x * 8 + 5] = t_epi; }
     }

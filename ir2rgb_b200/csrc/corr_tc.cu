@@ -28,7 +28,8 @@
 //
 // Roles (one persistent CTA per SM, 576 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + UMMA issue (one
 // thread), warps 2-9 = splitters, warps 10-17 = epilogue (tcgen05.ld -> scale / LeakyReLU -> shared-memory transpose ->
-// channels-last store: each pixel's run of channels is contiguous).  mbarrier pipelines: full (TMA -> splitters),
+// channels-last store: each pixel's run of channels is contiguous; for the reference's NCHW layout the accumulator rows are
+// ordered tile-row-major instead and stored straight from registers, 8- or 16-pixel row segments per channel).  mbarrier pipelines: full (TMA -> splitters),
 // split (splitters -> UMMA), empty (tcgen05.commit -> TMA), tmem_full[2] / tmem_empty[2] (UMMA <-> epilogue).
 #include "corr.cuh"
 #include "tma.cuh"
@@ -500,27 +501,6 @@ __global__ void __launch_bounds__(256) planes8_from_nhwc(const float *in, float 
     }
 }
 
-// channels-last cost volume [B, HW, 441] -> the reference's NCHW layout [B, 441, HW] (only the NCHW entry points need it)
-__global__ void __launch_bounds__(256) nhwc441_to_nchw(const float *__restrict__ in, float *__restrict__ out, int HW)
-{
-    __shared__ float t[32][33];
-    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const float *src = in + (size_t)n * HW * (kD * kD);
-    float *dst = out + (size_t)n * HW * (kD * kD);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int pix = p0 + ly + 8 * i, ch = c0 + lx;
-        t[ly + 8 * i][lx] = (pix < HW && ch < kD * kD) ? ldg_stream(src + (size_t)pix * (kD * kD) + ch) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ch = c0 + ly + 8 * i, pix = p0 + lx;
-        if (pix < HW && ch < kD * kD) stg_stream(dst + (size_t)ch * HW + pix, t[lx][ly + 8 * i]);
-    }
-}
-
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -546,9 +526,9 @@ bool corr_tc_supported(const CorrGeom &g)
 
 static size_t tc_plane_bytes(const CorrGeom &g) { return sizeof(float) * (size_t)g.B * g.C * g.H * g.W; }
 
-size_t corr_tc_fwd_workspace(const CorrGeom &g, bool nchw_out)
+size_t corr_tc_fwd_workspace(const CorrGeom &g, bool /*nchw_out*/)
 {
-    return 2 * tc_plane_bytes(g) + (nchw_out ? sizeof(float) * (size_t)g.B * g.H * g.W * g.oC : 0);
+    return 2 * tc_plane_bytes(g);          // the two P8 plane sets; both output layouts are stored by the kernel itself
 }
 
 static int encode_map5_sw32(CUtensorMap *tm, const void *base, const cuuint64_t dims[5], const cuuint64_t strides[4],
@@ -598,52 +578,60 @@ int corr_tc_planes_nhwc(const float *in, int which, const CorrGeom &g, const flo
     return check_launch("planes8_from_nhwc");
 }
 
-// the correlation proper on P8 planes in the workspace; out is channels-last [B, H, W, c_dst] (channels c_off..c_off+440)
-// or, with nchw_out, the reference's [B, 441, H, W] (through a channels-last temporary in the workspace)
+namespace tc {
+
+// the correlation proper on P8 planes in the workspace; out is channels-last [B, H, W, c_dst] (channels c_off..c_off+440,
+// LeakyReLU(slope) folded in) or, with NCHW, the reference's [B, 441, H, W]
+template <class T, bool NCHW>
+static int tc_launch(float *out, const CorrGeom &g, float *P1, float *P2, cudaStream_t st, int c_dst, int c_off, float slope)
+{
+    const int PH = g.H / 2, PW = g.W / 2, CB = g.C / 8;
+    CUtensorMap tmA, tmB;
+    const cuuint64_t row = 32, line = (cuuint64_t)PW * row, img = line * PH, plane = img * CB;
+    const cuuint64_t dimsYX[5] = {8, (cuuint64_t)PH, (cuuint64_t)PW, (cuuint64_t)CB, (cuuint64_t)g.B * 4};      // Y before X: rows m = x*TH + y
+    const cuuint64_t strYX[4] = {line, row, img, plane};
+    const cuuint64_t dimsXY[5] = {8, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)CB, (cuuint64_t)g.B * 4};      // natural order: rows m = y*W_box + x
+    const cuuint64_t strXY[4] = {row, line, img, plane};
+    const cuuint32_t boxA_yx[5] = {8, T::TH, T::TW, 1, 1}, boxA_xy[5] = {8, T::TW, T::TH, 1, 1};
+    const cuuint32_t boxB[5] = {8, T::WW, T::QROWS, 1, 1};
+    int rc = NCHW ? encode_map5_sw32(&tmA, P1, dimsXY, strXY, boxA_xy, "corr_fwd") : encode_map5_sw32(&tmA, P1, dimsYX, strYX, boxA_yx, "corr_fwd");
+    if (rc) return rc;
+    rc = encode_map5_sw32(&tmB, P2, dimsXY, strXY, boxB, "corr_fwd");
+    if (rc) return rc;
+    Params p;
+    p.out = out;
+    p.CB = CB; p.H = g.H; p.W = g.W; p.PH = PH; p.PW = PW;
+    p.tilesY = (PH + T::TH - 1) / T::TH; p.tilesX = (PW + T::TW - 1) / T::TW;
+    p.n_items = g.B * 4 * p.tilesY * p.tilesX * 4;
+    p.c_dst = c_dst; p.c_off = c_off; p.slope = slope;
+    p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
+    p.flags = (corr_impl_flags() >> 1) & 3;
+    p.trace = g_tc_trace;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // per-device attribute, set before every launch (see corr_fast.cu)
+    const cudaError_t e = cudaFuncSetAttribute(corr_fwd_tc<T, NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+    const int grid = p.n_items < sms ? p.n_items : sms;
+    corr_fwd_tc<T, NCHW><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+    return check_launch("corr_fwd_tc");
+}
+
+}  // namespace tc
+
 int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
                  bool nchw_out, int c_dst, int c_off, float slope)
 {
     float *P1, *P2, *tmp;
-    int rc = tc_ws(g, ws, ws_bytes, nchw_out, P1, P2, tmp, "corr_fwd");
+    int rc = tc_ws(g, ws, ws_bytes, false, P1, P2, tmp, "corr_fwd");
     if (rc) return rc;
-    const int PH = g.H / 2, PW = g.W / 2, CB = g.C / 8;
-    CUtensorMap tmA, tmB;
-    {
-        const cuuint64_t row = 32, line = (cuuint64_t)PW * row, img = line * PH, plane = img * CB;
-        const cuuint64_t dimsA[5] = {8, (cuuint64_t)PH, (cuuint64_t)PW, (cuuint64_t)CB, (cuuint64_t)g.B * 4};
-        const cuuint64_t strA[4] = {line, row, img, plane};
-        const cuuint32_t boxA[5] = {8, tc::TH, tc::TW, 1, 1};
-        rc = encode_map5_sw32(&tmA, P1, dimsA, strA, boxA, "corr_fwd");
-        if (rc) return rc;
-        const cuuint64_t dimsB[5] = {8, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)CB, (cuuint64_t)g.B * 4};
-        const cuuint64_t strB[4] = {row, line, img, plane};
-        const cuuint32_t boxB[5] = {8, tc::WW, tc::QROWS, 1, 1};
-        rc = encode_map5_sw32(&tmB, P2, dimsB, strB, boxB, "corr_fwd");
-        if (rc) return rc;
-    }
-    tc::Params p;
-    p.out = nchw_out ? tmp : out;
-    p.CB = CB; p.H = g.H; p.W = g.W; p.PH = PH; p.PW = PW;
-    p.tilesY = (PH + tc::TH - 1) / tc::TH; p.tilesX = (PW + tc::TW - 1) / tc::TW;
-    p.n_items = g.B * 4 * p.tilesY * p.tilesX * 4;
-    p.c_dst = nchw_out ? g.oC : c_dst; p.c_off = nchw_out ? 0 : c_off;
-    p.slope = nchw_out ? 1.f : slope;
-    p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
-    p.flags = (corr_impl_flags() >> 1) & 3;
-    p.trace = g_tc_trace;
-
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(tc::corr_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("corr_fwd: cannot reserve %d bytes of shared memory: %s", tc::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
-    const int grid = p.n_items < sms ? p.n_items : sms;
-    tc::corr_fwd_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmA, tmB, p);
-    rc = check_launch("corr_fwd_tc");
-    if (rc || !nchw_out) return rc;
-    const int HW = g.H * g.W;
-    tc::nhwc441_to_nchw<<<dim3((HW + 31) / 32, (g.oC + 31) / 32, g.B), 256, 0, st>>>(tmp, out, HW);
-    return check_launch("nhwc441_to_nchw");
+    if (!nchw_out) return tc::tc_launch<tc::Tile<16, 8>, false>(out, g, P1, P2, st, c_dst, c_off, slope);
+    // NCHW: the tile shape that wastes fewer partial tiles (16 x 8 on a tie)
+    const int PH = g.H / 2, PW = g.W / 2;
+    const long long t168 = (long long)((PH + 15) / 16) * ((PW + 7) / 8), t816 = (long long)((PH + 7) / 8) * ((PW + 15) / 16);
+    if (t816 < t168) return tc::tc_launch<tc::Tile<8, 16>, true>(out, g, P1, P2, st, 0, 0, 1.f);
+    return tc::tc_launch<tc::Tile<16, 8>, true>(out, g, P1, P2, st, 0, 0, 1.f);
 }
 
 }  // namespace flowops

@@ -56,7 +56,10 @@ extern "C" size_t flowops_corr_bwd_workspace_bytes(int B, int C, int H, int W, i
 {
     CorrGeom g;
     if (corr_geometry(g, B, C, H, W, pad, k, md, s1, s2)) return 0;
-    return corr_fast_supported(g) ? corr_fast_bwd_workspace(g) : 0;
+    if (!corr_fast_supported(g)) return 0;
+    size_t n = corr_fast_bwd_workspace(g);
+    if (corr_tc_bwd_supported(g)) { const size_t t = corr_tc_bwd_workspace(g); if (t > n) n = t; }
+    return n;
 }
 
 extern "C" int flowops_corr_fwd(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
@@ -143,6 +146,7 @@ extern "C" int flowops_corr_bwd(const float *in1, const float *in2, const float 
     // stride1 > 1 (correlation_cuda_kernel.cu:164-165,238); it is never used that way.
     FLOWOPS_REQUIRE(s1 == 1, FLOWOPS_EUNSUPPORTED, "corr_bwd: stride1 != 1 is not defined by the reference backward");
     cudaStream_t st = (cudaStream_t)stream;
+    if (corr_tc_bwd_supported(g)) return corr_tc_bwd_launch(in1, in2, gout, gin1, gin2, g, workspace, workspace_bytes, st);
     if (corr_fast_supported(g)) return corr_fast_bwd_launch(in1, in2, gout, gin1, gin2, g, workspace, workspace_bytes, st);
     return corr_bwd_generic_launch(in1, in2, gout, gin1, gin2, g, st);
 }

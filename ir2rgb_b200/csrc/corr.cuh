@@ -44,4 +44,10 @@ int corr_tc_planes_nhwc(const float *in, int which, const CorrGeom &g, const flo
 int corr_tc_main(float *out, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st,
                  bool nchw_out, int c_dst, int c_off, float slope);
 
+// Tensor-core backward (csrc/corr_tc_bwd.cu): both gradients in one persistent launch after two layout passes.
+bool corr_tc_bwd_supported(const CorrGeom &g);
+size_t corr_tc_bwd_workspace(const CorrGeom &g);
+int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
+                       const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace flowops

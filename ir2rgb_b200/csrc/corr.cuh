@@ -36,6 +36,7 @@ int corr_fast_bwd_launch(const float *in1, const float *in2, const float *gout, 
 // Tensor-core (tcgen05, 3xTF32) forward for the FlowNetC configuration: csrc/corr_tc.cu.  Selected when supported
 // unless FLOWOPS_CORR_IMPL=ffma (or flowops_corr_set_impl(0)); the FP32-FMA kernel above stays the general path.
 int corr_impl_flags();
+unsigned long long *corr_tc_trace_buffer();     // debugging: see flowops_corr_tc_trace
 bool corr_tc_supported(const CorrGeom &g);
 size_t corr_tc_fwd_workspace(const CorrGeom &g, bool nchw_out);
 int corr_tc_planes_nchw(const float *in1, const float *in2, const CorrGeom &g, void *ws, size_t ws_bytes, cudaStream_t st);

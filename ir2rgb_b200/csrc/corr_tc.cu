@@ -444,6 +444,8 @@ __global__ void __launch_bounds__(256) planes8_from_nhwc(const float *in, float 
 static unsigned long long *g_tc_trace = nullptr;      // debugging aid, see flowops_corr_tc_trace
 static int g_corr_impl = -1;      // -1: not read yet; bit 0: tensor-core path on; bits 1-2 -> kernel flags (debug)
 
+unsigned long long *corr_tc_trace_buffer() { return g_tc_trace; }
+
 int corr_impl_flags()
 {
     if (g_corr_impl < 0) {

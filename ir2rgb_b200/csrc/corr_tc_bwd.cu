@@ -38,17 +38,12 @@ constexpr int TH = 16, TW = 8, M = TH * TW;                 // pixel tile = UMMA
 constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;           // window: 36 x 28 positions
 constexpr int KB_Y = 2, KB_X = 4;                           // a K block: 2 window rows x 4 window columns = K of one tf32 UMMA
 constexpr int NA = WH / KB_Y, NB = WW / KB_X;               // 18 x 7 = 126 K blocks per tile
-constexpr int REC = kD * WW;                                // 588 floats per pixel record of G'
 constexpr int A_BYTES = M * 8 * 4;                          // 4096
 constexpr int B_MAX = 256 * 8 * 4;                          // 8192 (N = 256 channels)
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_MAX;        // A hi, A lo, B raw (= hi), B lo
-constexpr int STAGES = 8;
-constexpr int N_WORK_WARPS = 8, N_EPI_WARPS = 4;
-constexpr int THREADS = 32 * (2 + N_WORK_WARPS + N_EPI_WARPS);      // 448
-constexpr int SMEM_BARRIERS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIERS + 1024;
+constexpr int N_SPLIT_WARPS = 4, N_SKEW_WARPS = 8, N_EPI_WARPS = 4;
+constexpr int THREADS = 32 * (2 + N_SPLIT_WARPS + N_SKEW_WARPS + N_EPI_WARPS);      // 576
+constexpr int SMEM_BARRIERS = 512;
 static_assert(WH % KB_Y == 0 && WW % KB_X == 0 && KB_Y * KB_X == 8, "K blocks tile the window");
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 using tc::mbar_wait_b;
 
@@ -63,7 +58,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t saddr)
 }
 
 struct Params {
-    const float *G[2];      // skewed gradient records: [0] for gI1, [1] for gI2 (mirrored)
+    const float *gout;      // gO [B, 441, H, W]
     float *out[2];          // gI1, gI2 (NCHW); a null entry is never selected (which0 / n_which)
     int which0, n_which;
     int C, NC, n_chunks;    // channels, channels per pass (UMMA N), passes
@@ -71,6 +66,7 @@ struct Params {
     int tilesY, tilesX, planes, n_items;
     float nelems, inv_nelems;
     int flags;              // bit 1 (as in the forward): single TF32 product (layout debugging)
+    unsigned long long *trace;   // debugging: per-CTA wait counters (8 per CTA), or null
 };
 
 struct Item { int which, plane, Y0, X0, chunk; };
@@ -86,9 +82,52 @@ __device__ __forceinline__ Item decode_item(int item, const Params &p)
     return it;
 }
 
+// TMEM loads / stores and the A-from-TMEM UMMA used only here
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes x 8 columns of tf32 words
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float4 tf32_residual(float4 v)
+{
+    // lo = x - trunc_tf32(x) (exact), rounded to TF32 by adding half an ulp to the bit pattern (the tensor core truncates)
+    float4 l;
+    l.x = __uint_as_float(__float_as_uint(__fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xffffe000u))) + 0x1000u);
+    l.y = __uint_as_float(__float_as_uint(__fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xffffe000u))) + 0x1000u);
+    l.z = __uint_as_float(__float_as_uint(__fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xffffe000u))) + 0x1000u);
+    l.w = __uint_as_float(__float_as_uint(__fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xffffe000u))) + 0x1000u);
+    return l;
+}
+
+// ATM = true: the A operand (skewed gradient tile, hi and lo) lives in TMEM (tcgen05.st by the skew warps, 16 columns per
+// stage next to ONE 256-column accumulator) and shared memory carries only Bw; ATM = false: A tiles in shared memory
+// (K-major SWIZZLE_32B) and two accumulators.
+template <bool ATM> struct Cfg {
+    static constexpr int STAGES = ATM ? 12 : 8;
+    static constexpr int B_OFS = ATM ? 0 : 2 * A_BYTES;
+    static constexpr int STAGE_BYTES = B_OFS + 2 * B_MAX;       // [A hi, A lo,] B raw (= hi), B lo
+    static constexpr int NACC = ATM ? 1 : 2;
+    static constexpr int A_COL0 = 256;                          // first TMEM column of the A ring (ATM)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIERS + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(!ATM || A_COL0 + 16 * STAGES <= 512, "TMEM budget");
+};
+
+template <bool ATM>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const Params p)
 {
+    using K = Cfg<ATM>;
+    constexpr int STAGES = K::STAGES, STAGE_BYTES = K::STAGE_BYTES, B_OFS = K::B_OFS, NACC = K::NACC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -107,7 +146,7 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_ready(s), N_WORK_WARPS);
+            mbar_init(bar_ready(s), 1 + N_SKEW_WARPS);                // one split warp per K block (round robin) + the skew warps
             mbar_init(bar_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -129,6 +168,8 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
         // ================= TMA producer: one K block of the window's features per stage =================
         if (lane == 0) {
             uint32_t it = 0;
+            long long w_empty = 0;
+            const long long t_start = clock64();
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item(item, p);
                 const CUtensorMap *tm = w.which == 0 ? &tmB0 : &tmB1;
@@ -136,13 +177,14 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
                     for (int b = 0; b < NB; ++b, ++it) {
                         const int s = it % STAGES;
                         const uint32_t u = it / STAGES;
-                        mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
+                        w_empty += mbar_wait_b(bar_empty(s), (u & 1) ^ 1);
                         mbar_expect_tx(bar_full(s), b_bytes);
                         // dims (c%32, X, Y, c/32, plane): lands as [c/32][wy_local][wx_local][32 channels]; zero fill outside the plane
-                        tc::tma_load_5d(base + s * STAGE_BYTES + 2 * A_BYTES, tm, 0, w.X0 - kR + KB_X * b, w.Y0 - kR + KB_Y * a,
+                        tc::tma_load_5d(base + s * STAGE_BYTES + B_OFS, tm, 0, w.X0 - kR + KB_X * b, w.Y0 - kR + KB_Y * a,
                                         w.chunk * (p.NC >> 5), w.plane, bar_full(s));
                     }
             }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 0] = w_empty; p.trace[blockIdx.x * 8 + 6] = clock64() - t_start; }
         }
     } else if (warp == 1) {
         // ================= UMMA issuer =================
@@ -150,93 +192,149 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
             // D = fp32, A and B = TF32, A K-major, B MN-major (bit 16), N >> 3 in bits 17-22, M >> 4 in bits 24-28
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(p.NC >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t it = 0, j = 0;
+            long long w_ready = 0, w_tempty = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
-                const int acc = j & 1;
-                mbar_wait_b(bar_tempty(acc), ((j >> 1) & 1) ^ 1);
+                const int acc = j % NACC;
+                w_tempty += mbar_wait_b(bar_tempty(acc), ((j / NACC) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d = tmem + 256u * acc;
                 for (int kb = 0; kb < NA * NB; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
-                    mbar_wait_b(bar_ready(s), u & 1);
+                    w_ready += mbar_wait_b(bar_ready(s), u & 1);
                     tc::tc_fence_after();
                     const uint32_t sb = base + s * STAGE_BYTES;
-                    const uint64_t a_hi = tc::smem_desc_sw32(sb), a_lo = tc::smem_desc_sw32(sb + A_BYTES);
-                    const uint64_t b_hi = smem_desc_mn_sw128_32b(sb + 2 * A_BYTES), b_lo = smem_desc_mn_sw128_32b(sb + 2 * A_BYTES + B_MAX);
+                    const uint64_t b_hi = smem_desc_mn_sw128_32b(sb + B_OFS), b_lo = smem_desc_mn_sw128_32b(sb + B_OFS + B_MAX);
                     const uint32_t first = kb == 0 ? 0u : 1u;
-                    if (!(p.flags & 2)) {
+                    if (ATM) {
+                        const uint32_t a_hi = tmem + K::A_COL0 + 16u * s, a_lo = a_hi + 8u;
+                        umma_tf32_ts(d, a_lo, b_hi, idesc, first);
+                        umma_tf32_ts(d, a_hi, b_lo, idesc, 1u);
+                        umma_tf32_ts(d, a_hi, b_hi, idesc, 1u);
+                    } else {
+                        const uint64_t a_hi = tc::smem_desc_sw32(sb), a_lo = tc::smem_desc_sw32(sb + A_BYTES);
                         tc::umma_tf32(d, a_lo, b_hi, idesc, first);
                         tc::umma_tf32(d, a_hi, b_lo, idesc, 1u);
                         tc::umma_tf32(d, a_hi, b_hi, idesc, 1u);
-                    } else {
-                        tc::umma_tf32(d, a_hi, b_hi, idesc, first);
                     }
                     tc::tc_commit(bar_empty(s));
                 }
                 tc::tc_commit(bar_tfull(acc));
             }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 1] = w_ready; p.trace[blockIdx.x * 8 + 2] = w_tempty; }
         }
-    } else if (warp < 2 + N_WORK_WARPS) {
-        // ================= skew + split =================
-        const int t = threadIdx.x - 64;                              // 0..255
-        const int m = t & (M - 1), yy = t >> 7;                      // accumulator row, window row parity inside the K block
+    } else if (warp < 2 + N_SPLIT_WARPS) {
+        // ================= split: lo tile of Bw, same position as the raw tile; split warp k takes K blocks k, k + 4, ... =================
+        const int sw = warp - 2;
+        const int n_chunks16 = 2 * p.NC;                             // 16-byte chunks of one Bw K block
+        const uint32_t n_kb = (uint32_t)((p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (NA * NB);
+        long long w_full = 0, t_split = 0;
+        for (uint32_t it = sw; it < n_kb; it += N_SPLIT_WARPS) {
+            const int s = it % STAGES;
+            const uint32_t u = it / STAGES;
+            uint8_t *braw = gen + s * STAGE_BYTES + B_OFS;
+            w_full += mbar_wait_b(bar_full(s), u & 1);               // Bw has landed (and the stage's previous readers are done)
+            const long long ts0 = clock64();
+#pragma unroll 1
+            for (int i0 = 0; i0 < n_chunks16; i0 += 128) {
+                float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4 *>(braw + (i0 + lane + 32 * k) * 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<float4 *>(braw + B_MAX + (i0 + lane + 32 * k) * 16) = tf32_residual(v[k]);
+            }
+            tc::fence_proxy_async();                                 // generic-proxy writes -> visible to the UMMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(s));
+            t_split += clock64() - ts0;
+        }
+        if (p.trace && sw == 0 && lane == 0) { p.trace[blockIdx.x * 8 + 3] = w_full; p.trace[blockIdx.x * 8 + 5] = t_split; }
+    } else if (warp < 2 + N_SPLIT_WARPS + N_SKEW_WARPS) {
+        // ================= skew: the banded gradient tile A (hi and lo) from gO =================
+        const int m = 32 * (warp & 3) + lane;                        // accumulator row = TMEM lane (a warp reaches its own lane quarter)
+        const int yy = (warp - (2 + N_SPLIT_WARPS)) >> 2;            // window row parity inside the K block
         const int r = m >> 3, cx = m & 7;                            // m = r * 8 + cx
         const uint32_t a_ofs = (uint32_t)m * 32u + 16u * (uint32_t)(yy ^ ((m >> 2) & 1));     // 32-byte swizzle: chunk ^= address bit 7
-        const int n_chunks16 = 2 * p.NC;                             // 16-byte chunks of one Bw K block
+        const uint32_t a_lane = (uint32_t)(32 * (warp & 3)) << 16;
+        const size_t hw = (size_t)p.H * p.W;
         uint32_t it = 0;
+        long long w_sk_empty = 0, t_sk = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const Item w = decode_item(item, p);
             const int Y = w.Y0 + r, X = w.X0 + cx;
             const bool pix_ok = Y < p.PH && X < p.PW;
-            const float *rec = p.G[w.which] + (((size_t)w.plane * p.PH + (pix_ok ? Y : 0)) * p.PW + (pix_ok ? X : 0)) * REC;
+            const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
+            const float *go_n = p.gout + (size_t)n * (kD * kD) * hw;
+            // A[m][(wy, wx)] = G[(tj = wy - r, ti = wx - cx)][my pixel]: per window row 21 gradient values, one per horizontal
+            // displacement, placed at window columns cx .. cx + 20 of the row's 28.  The loads are issued per displacement (all
+            // lanes read the same channel plane: 8 pixels of a tile row share two sectors) and the lane-dependent shift by cx
+            // is applied in registers when the row is consumed (one select level per bit of cx).
+            auto load_row = [&](int a, float (&v)[kD]) {
+                const int tj = KB_Y * a + yy - r;
+#pragma unroll
+                for (int ti = 0; ti < kD; ++ti) v[ti] = 0.f;
+                if (!(pix_ok && tj >= 0 && tj < kD)) return;
+                if (w.which == 0) {
+                    // gI1: G = gO: channel tj*21 + ti at my pixel; consecutive ti are one channel plane apart
+                    const float *src = go_n + (size_t)(tj * kD) * hw + (size_t)(2 * Y + py) * p.W + (2 * X + px);
+#pragma unroll
+                    for (int ti = 0; ti < kD; ++ti) v[ti] = ldg_stream(src + (size_t)ti * hw);
+                } else {
+                    // gI2: G[(tj, ti)][q] = gO[(20 - tj, 20 - ti)][q + (tj - 10, ti - 10)], zero outside the plane
+                    const int Ys = Y + tj - kR;
+                    if (Ys < 0 || Ys >= p.PH) return;
+                    const float *src = go_n + (size_t)((kD - 1 - tj) * kD + kD - 1) * hw + (size_t)(2 * Ys + py) * p.W + px + 2 * (X - kR);
+                    const ptrdiff_t step = 2 - (ptrdiff_t)hw;            // ti + 1: one channel down, one plane column right
+#pragma unroll
+                    for (int ti = 0; ti < kD; ++ti) {
+                        const int Xs = X + ti - kR;
+                        if (Xs >= 0 && Xs < p.PW) v[ti] = ldg_stream(src + (ptrdiff_t)ti * step);
+                    }
+                }
+            };
+            float vcur[kD], vnext[kD];
+            load_row(0, vcur);
 #pragma unroll 1
             for (int a = 0; a < NA; ++a) {
-                const int tj = KB_Y * a + yy - r;                    // vertical displacement index of this window row for my pixel
-                float4 q[NB];
-                if (pix_ok && tj >= 0 && tj < kD) {
+                if (a + 1 < NA) load_row(a + 1, vnext);              // the next window row's values are in flight while this one is consumed
+                float wv[WW];                                        // the row in window coordinates: wv[j] = v[j - cx]
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) q[b] = ldg_stream4(rec + tj * WW + 4 * b);
-                } else {
+                for (int j = 0; j < WW; ++j) wv[j] = j < kD ? vcur[j] : 0.f;
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) q[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int bit = 1; bit < TW; bit <<= 1) {
+                    const bool on = (cx & bit) != 0;
+#pragma unroll
+                    for (int j = WW - 1; j >= 0; --j) wv[j] = on ? (j >= bit ? wv[j - bit] : 0.f) : wv[j];
                 }
 #pragma unroll
                 for (int b = 0; b < NB; ++b, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
-                    uint8_t *stage = gen + s * STAGE_BYTES;
-                    mbar_wait_b(bar_empty(s), (u & 1) ^ 1);          // the UMMAs that read this stage's A tiles are done
-                    {
-                        const float4 v = q[b];
-                        float4 l;
-                        l.x = __uint_as_float(__float_as_uint(__fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xffffe000u))) + 0x1000u);
-                        l.y = __uint_as_float(__float_as_uint(__fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xffffe000u))) + 0x1000u);
-                        l.z = __uint_as_float(__float_as_uint(__fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xffffe000u))) + 0x1000u);
-                        l.w = __uint_as_float(__float_as_uint(__fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xffffe000u))) + 0x1000u);
+                    w_sk_empty += mbar_wait_b(bar_empty(s), (u & 1) ^ 1);          // the UMMAs that read this stage's A tiles are done
+                    const long long ts0 = clock64();
+                    const float4 v = make_float4(wv[4 * b], wv[4 * b + 1], wv[4 * b + 2], wv[4 * b + 3]), l = tf32_residual(v);
+                    if (ATM) {
+                        tc::tc_fence_after();
+                        const uint32_t col = tmem + a_lane + K::A_COL0 + 16u * s + 4u * yy;
+                        tmem_st4(col, v);
+                        tmem_st4(col + 8u, l);
+                        tmem_st_wait();
+                        tc::tc_fence_before();
+                    } else {
+                        uint8_t *stage = gen + s * STAGE_BYTES;
                         *reinterpret_cast<float4 *>(stage + a_ofs) = v;
                         *reinterpret_cast<float4 *>(stage + A_BYTES + a_ofs) = l;
+                        tc::fence_proxy_async();
                     }
-                    mbar_wait_b(bar_full(s), u & 1);                 // Bw has landed
-                    uint8_t *braw = stage + 2 * A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int i = t + k * 32 * N_WORK_WARPS;
-                        if (i < n_chunks16) {
-                            const float4 v = *reinterpret_cast<const float4 *>(braw + i * 16);
-                            float4 l;
-                            l.x = __uint_as_float(__float_as_uint(__fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xffffe000u))) + 0x1000u);
-                            l.y = __uint_as_float(__float_as_uint(__fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xffffe000u))) + 0x1000u);
-                            l.z = __uint_as_float(__float_as_uint(__fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xffffe000u))) + 0x1000u);
-                            l.w = __uint_as_float(__float_as_uint(__fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xffffe000u))) + 0x1000u);
-                            *reinterpret_cast<float4 *>(braw + B_MAX + i * 16) = l;
-                        }
-                    }
-                    tc::fence_proxy_async();                         // generic-proxy writes -> visible to the UMMA (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_ready(s));
+                    t_sk += clock64() - ts0;
                 }
+#pragma unroll
+                for (int ti = 0; ti < kD; ++ti) vcur[ti] = vnext[ti];
             }
         }
+        if (p.trace && warp == 2 + N_SPLIT_WARPS && lane == 0) { p.trace[blockIdx.x * 8 + 4] = w_sk_empty; p.trace[blockIdx.x * 8 + 7] = t_sk; }
     } else {
         // ================= epilogue: TMEM -> 1/C -> NCHW =================
         const int q = warp & 3;                                      // TMEM lane quarter this warp may read
@@ -244,14 +342,16 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
         const int r = m >> 3, cx = m & 7;
         const size_t hw = (size_t)p.H * p.W;
         uint32_t j = 0;
+        long long t_epi = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
             const Item w = decode_item(item, p);
-            const int acc = j & 1;
+            const int acc = j % NACC;
             const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
             const int Y = w.Y0 + r, X = w.X0 + cx;
             const bool pix_ok = Y < p.PH && X < p.PW;
             float *dst = p.out[w.which] + ((size_t)n * p.C + (size_t)w.chunk * p.NC) * hw + (size_t)(2 * Y + py) * p.W + (2 * X + px);
-            mbar_wait_b(bar_tfull(acc), (j >> 1) & 1);
+            mbar_wait_b(bar_tfull(acc), (j / NACC) & 1);
+            const long long te0 = clock64();
             tc::tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < p.NC; c0 += 16) {
@@ -266,7 +366,9 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty(acc));
+            t_epi += clock64() - te0;
         }
+        (void)t_epi;
     }
 
     tc::tc_fence_before();
@@ -278,54 +380,8 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pre-pass: gO [n][441][H][W] -> G'[n*4 + parity][Y][X][tj][wxl], wxl = ti + (X % 8), zeros outside 0 <= ti <= 20.
-//   MIRRORED = false (gI1): G'[..][tj][wxl] = gO[(tj, ti)][pixel]
-//   MIRRORED = true  (gI2): G'[..][tj][wxl] = gO[(20 - tj, 20 - ti)][pixel + (tj - 10, ti - 10) in plane coordinates], zero outside
-// A CTA owns 16 consecutive image columns of one image row (= 8 plane columns of both column parities, one period of the
-// skew); per group of 3 vertical displacements it stages the 21 channel rows it needs in shared memory with coalesced
-// reads and writes 28-float rows with 128-bit stores.
+// layout pass
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TJB = 3;
-template <bool MIRRORED>
-__global__ void __launch_bounds__(256) gskew_from_nchw(const float *__restrict__ gout, float *__restrict__ G, int H, int W)
-{
-    constexpr int NCOL = MIRRORED ? 16 + 4 * kR : 16;
-    __shared__ float s[TJB][kD][NCOL];
-    const int x0 = blockIdx.x * 16, y = blockIdx.y, n = blockIdx.z;
-    const int PH = H >> 1, PW = W >> 1;
-    const size_t hw = (size_t)H * W;
-    const float *src_n = gout + (size_t)n * (kD * kD) * hw;
-    for (int g = 0; g < kD / TJB; ++g) {
-        for (int idx = threadIdx.x; idx < TJB * kD * NCOL; idx += 256) {
-            const int j = idx % NCOL, ti = (idx / NCOL) % kD, t3 = idx / (NCOL * kD);
-            const int tj = TJB * g + t3;
-            int ch, ys, xs;
-            if (MIRRORED) { ch = (kD - 1 - tj) * kD + (kD - 1 - ti); ys = y + 2 * (tj - kR); xs = x0 - 2 * kR + j; }
-            else          { ch = tj * kD + ti; ys = y; xs = x0 + j; }
-            float v = 0.f;
-            if (ys >= 0 && ys < H && xs >= 0 && xs < W) v = ldg_stream(src_n + (size_t)ch * hw + (size_t)ys * W + xs);
-            s[t3][ti][j] = v;
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < TJB * 16 * (WW / 4); idx += 256) {
-            const int quad = idx % (WW / 4), col = (idx / (WW / 4)) & 15, t3 = idx / (16 * (WW / 4));
-            const int x = x0 + col;
-            if (x >= W) continue;
-            const int cx = col >> 1;                                 // (x >> 1) % 8 since x0 is a multiple of 16
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int ti = 4 * quad + e - cx;
-                v[e] = (ti >= 0 && ti < kD) ? (MIRRORED ? s[t3][ti][col + 2 * ti] : s[t3][ti][col]) : 0.f;
-            }
-            const int plane = n * 4 + (y & 1) * 2 + (col & 1);
-            float *dst = G + (((size_t)plane * PH + (y >> 1)) * PW + (x >> 1)) * REC + (TJB * g + t3) * WW + 4 * quad;
-            stg_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
-        }
-        __syncthreads();
-    }
-}
-
 // NCHW -> "P32" planes P[n*4 + parity][c/32][Y][X][c%32]: 128-byte rows of 32 channels per plane position, the row format of
 // the MN-major tf32 operand (a 128-byte inner TMA dimension is what CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B takes; with the
 // forward's 32-byte P8 rows that swizzle mode faults -- measured, tools/tma_sw_probe.cu).  A thread owns one pixel and one
@@ -357,7 +413,6 @@ __global__ void __launch_bounds__(256) planes32_from_nchw(const float *__restric
 // ---------------------------------------------------------------------------------------------------------------
 static inline size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 static size_t tcb_plane_bytes(const CorrGeom &g) { return up256(sizeof(float) * (size_t)g.B * g.C * g.H * g.W); }
-static size_t tcb_rec_bytes(const CorrGeom &g) { return up256(sizeof(float) * (size_t)g.B * g.H * g.W * tcb::REC); }
 
 bool corr_tc_bwd_supported(const CorrGeom &g)
 {
@@ -366,7 +421,7 @@ bool corr_tc_bwd_supported(const CorrGeom &g)
 
 size_t corr_tc_bwd_workspace(const CorrGeom &g)
 {
-    return 2 * tcb_plane_bytes(g) + 2 * tcb_rec_bytes(g);        // P8 planes of both inputs, skewed gradient records of both gradients
+    return 2 * tcb_plane_bytes(g);        // P32 planes of both inputs
 }
 
 int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, float *gin1, float *gin2,
@@ -385,20 +440,6 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
         if (rc0) return rc0;
     }
     int rc = 0;
-    float *G1 = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(ws) + 2 * tcb_plane_bytes(g));
-    float *G2 = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(G1) + tcb_rec_bytes(g));
-
-    const dim3 pgrid((g.W + 15) / 16, g.H, g.B);
-    if (gin1) {
-        tcb::gskew_from_nchw<false><<<pgrid, 256, 0, st>>>(gout, G1, g.H, g.W);
-        rc = check_launch("gskew_from_nchw");
-        if (rc) return rc;
-    }
-    if (gin2) {
-        tcb::gskew_from_nchw<true><<<pgrid, 256, 0, st>>>(gout, G2, g.H, g.W);
-        rc = check_launch("gskew_from_nchw(mirrored)");
-        if (rc) return rc;
-    }
 
     const int PH = g.H / 2, PW = g.W / 2;
     const int NC = g.C <= 256 ? g.C : 256;
@@ -413,7 +454,7 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
     if (rc) return rc;
 
     tcb::Params p;
-    p.G[0] = G1; p.G[1] = G2;
+    p.gout = gout;
     p.out[0] = gin1; p.out[1] = gin2;
     p.which0 = gin1 ? 0 : 1;
     p.n_which = (gin1 ? 1 : 0) + (gin2 ? 1 : 0);
@@ -424,14 +465,21 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
     p.n_items = p.n_which * p.planes * p.tilesY * p.tilesX * p.n_chunks;
     p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
     p.flags = (corr_impl_flags() >> 1) & 3;
+    p.trace = corr_tc_trace_buffer();
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // per-device attribute, set before every launch (see corr_fast.cu)
-    const cudaError_t e = cudaFuncSetAttribute(tcb::corr_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", tcb::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
     const int grid = p.n_items < sms ? p.n_items : sms;
-    tcb::corr_bwd_tc<<<grid, tcb::THREADS, tcb::SMEM_BYTES, st>>>(tmB0, tmB1, p);
+    // per-device attribute, set before every launch (see corr_fast.cu)
+    if (p.flags & 1) {              // flowops_corr_set_impl(3): A tiles in shared memory (the first version; kept for A/B timing)
+        const cudaError_t e = cudaFuncSetAttribute(tcb::corr_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<false>::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", tcb::Cfg<false>::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+        tcb::corr_bwd_tc<false><<<grid, tcb::THREADS, tcb::Cfg<false>::SMEM_BYTES, st>>>(tmB0, tmB1, p);
+    } else {
+        const cudaError_t e = cudaFuncSetAttribute(tcb::corr_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<true>::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", tcb::Cfg<true>::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
+        tcb::corr_bwd_tc<true><<<grid, tcb::THREADS, tcb::Cfg<true>::SMEM_BYTES, st>>>(tmB0, tmB1, p);
+    }
     return check_launch("corr_bwd_tc");
 }
 

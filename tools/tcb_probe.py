@@ -43,13 +43,17 @@ def main():
             h1, _ = F.correlation_backward(a, b, go, *P, need1=True, need2=False)
             _, h2 = F.correlation_backward(a, b, go, *P, need1=False, need2=True)
             e["single_output_calls_equal"] = bool(torch.equal(h1, g1) and torch.equal(h2, g2))
+            lib.flowops_corr_set_impl(3)
+            k1, k2 = F.correlation_backward(a, b, go, *P)
+            e["smemA_g1"], e["smemA_g2"] = maxrel(k1, r1), maxrel(k2, r2)
+            lib.flowops_corr_set_impl(args.flags)
         except Exception as ex:                      # noqa: BLE001
             e = {"shape": shape, "error": repr(ex)}
             print(json.dumps(e), flush=True)
             out.append(e)
             break
         if shape[0] == 8:
-            for name, flags in (("tc", args.flags), ("ffma", 0)):
+            for name, flags in (("tc", args.flags), ("tc_smemA", 3), ("ffma", 0)):
                 lib.flowops_corr_set_impl(flags)
                 for _ in range(3):
                     F.correlation_backward(a, b, go, *P)

@@ -27,6 +27,8 @@
 // thread), warps 2-9 = skew + split (A hi / lo tiles from G', lo tile of Bw), warps 10-13 = epilogue (tcgen05.ld -> 1/C ->
 // NCHW store).  mbarriers: full (TMA -> split), ready (skew / split -> UMMA), empty (tcgen05.commit -> TMA and skew),
 // tmem_full[2] / tmem_empty[2] (UMMA <-> epilogue); every wait is bounded.
+#include <stdlib.h>
+
 #include "corr.cuh"
 #include "tc.cuh"
 
@@ -34,16 +36,21 @@ namespace flowops {
 namespace tcb {
 
 constexpr int kD = 21, kR = 10;
-constexpr int TH = 16, TW = 8, M = TH * TW;                 // pixel tile = UMMA M
-constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;           // window: 36 x 28 positions
+constexpr int M = 128;                                      // pixels per tile = UMMA M
 constexpr int KB_Y = 2, KB_X = 4;                           // a K block: 2 window rows x 4 window columns = K of one tf32 UMMA
-constexpr int NA = WH / KB_Y, NB = WW / KB_X;               // 18 x 7 = 126 K blocks per tile
+// Pixel tile (plane rows x plane columns) and its window of (TH + 20) x (TW + 20) positions = 126 K blocks either way:
+// 16 x 8 -> 36 x 28 (18 x 7 K blocks), 8 x 16 -> 28 x 36 (14 x 9).  The host picks the shape with fewer (partial) tiles.
+template <int TH_, int TW_> struct Tile {
+    static constexpr int TH = TH_, TW = TW_;
+    static constexpr int WH = TH + 2 * kR, WW = TW + 2 * kR;
+    static constexpr int NA = WH / KB_Y, NB = WW / KB_X;
+    static_assert(TH * TW == M && WH % KB_Y == 0 && WW % KB_X == 0 && KB_Y * KB_X == 8, "K blocks tile the window");
+};
 constexpr int A_BYTES = M * 8 * 4;                          // 4096
 constexpr int B_MAX = 256 * 8 * 4;                          // 8192 (N = 256 channels)
 constexpr int N_SPLIT_WARPS = 4, N_SKEW_WARPS = 8, N_EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + N_SPLIT_WARPS + N_SKEW_WARPS + N_EPI_WARPS);      // 576
 constexpr int SMEM_BARRIERS = 512;
-static_assert(WH % KB_Y == 0 && WW % KB_X == 0 && KB_Y * KB_X == 8, "K blocks tile the window");
 
 using tc::mbar_wait_b;
 
@@ -62,6 +69,7 @@ struct Params {
     float *out[2];          // gI1, gI2 (NCHW); a null entry is never selected (which0 / n_which)
     int which0, n_which;
     int C, NC, n_chunks;    // channels, channels per pass (UMMA N), passes
+    int nacc, acc_stride;   // accumulators in TMEM (2 when two fit next to the A ring) and their column stride
     int H, W, PH, PW;
     int tilesY, tilesX, planes, n_items;
     float nelems, inv_nelems;
@@ -70,6 +78,7 @@ struct Params {
 };
 
 struct Item { int which, plane, Y0, X0, chunk; };
+template <class T>
 __device__ __forceinline__ Item decode_item(int item, const Params &p)
 {
     Item it;
@@ -78,7 +87,7 @@ __device__ __forceinline__ Item decode_item(int item, const Params &p)
     const int ty = item % p.tilesY; item /= p.tilesY;
     it.plane = item % p.planes;
     it.which = p.which0 + item / p.planes;
-    it.Y0 = ty * TH; it.X0 = tx * TW;
+    it.Y0 = ty * T::TH; it.X0 = tx * T::TW;
     return it;
 }
 
@@ -115,19 +124,20 @@ template <bool ATM> struct Cfg {
     static constexpr int STAGES = ATM ? 12 : 8;
     static constexpr int B_OFS = ATM ? 0 : 2 * A_BYTES;
     static constexpr int STAGE_BYTES = B_OFS + 2 * B_MAX;       // [A hi, A lo,] B raw (= hi), B lo
-    static constexpr int NACC = ATM ? 1 : 2;
     static constexpr int A_COL0 = 256;                          // first TMEM column of the A ring (ATM)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIERS + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(!ATM || A_COL0 + 16 * STAGES <= 512, "TMEM budget");
 };
 
-template <bool ATM>
+template <bool ATM, class T>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const Params p)
 {
     using K = Cfg<ATM>;
-    constexpr int STAGES = K::STAGES, STAGE_BYTES = K::STAGE_BYTES, B_OFS = K::B_OFS, NACC = K::NACC;
+    constexpr int TW = T::TW, WW = T::WW, NA = T::NA, NB = T::NB;
+    constexpr int STAGES = K::STAGES, STAGE_BYTES = K::STAGE_BYTES, B_OFS = K::B_OFS;
+    const int NACC = p.nacc;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -171,7 +181,7 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
             long long w_empty = 0;
             const long long t_start = clock64();
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item w = decode_item(item, p);
+                const Item w = decode_item<T>(item, p);
                 const CUtensorMap *tm = w.which == 0 ? &tmB0 : &tmB1;
                 for (int a = 0; a < NA; ++a)
                     for (int b = 0; b < NB; ++b, ++it) {
@@ -197,7 +207,7 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
                 const int acc = j % NACC;
                 w_tempty += mbar_wait_b(bar_tempty(acc), ((j / NACC) & 1) ^ 1);
                 tc::tc_fence_after();
-                const uint32_t d = tmem + 256u * acc;
+                const uint32_t d = tmem + (uint32_t)(p.acc_stride * acc);
                 for (int kb = 0; kb < NA * NB; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t u = it / STAGES;
@@ -253,14 +263,14 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
         // ================= skew: the banded gradient tile A (hi and lo) from gO =================
         const int m = 32 * (warp & 3) + lane;                        // accumulator row = TMEM lane (a warp reaches its own lane quarter)
         const int yy = (warp - (2 + N_SPLIT_WARPS)) >> 2;            // window row parity inside the K block
-        const int r = m >> 3, cx = m & 7;                            // m = r * 8 + cx
+        const int r = m / TW, cx = m % TW;                           // m = r * TW + cx
         const uint32_t a_ofs = (uint32_t)m * 32u + 16u * (uint32_t)(yy ^ ((m >> 2) & 1));     // 32-byte swizzle: chunk ^= address bit 7
         const uint32_t a_lane = (uint32_t)(32 * (warp & 3)) << 16;
         const size_t hw = (size_t)p.H * p.W;
         uint32_t it = 0;
         long long w_sk_empty = 0, t_sk = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item w = decode_item(item, p);
+            const Item w = decode_item<T>(item, p);
             const int Y = w.Y0 + r, X = w.X0 + cx;
             const bool pix_ok = Y < p.PH && X < p.PW;
             const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
@@ -339,12 +349,12 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
         // ================= epilogue: TMEM -> 1/C -> NCHW =================
         const int q = warp & 3;                                      // TMEM lane quarter this warp may read
         const int m = 32 * q + lane;
-        const int r = m >> 3, cx = m & 7;
+        const int r = m / TW, cx = m % TW;
         const size_t hw = (size_t)p.H * p.W;
         uint32_t j = 0;
         long long t_epi = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
-            const Item w = decode_item(item, p);
+            const Item w = decode_item<T>(item, p);
             const int acc = j % NACC;
             const int n = w.plane >> 2, py = (w.plane >> 1) & 1, px = w.plane & 1;
             const int Y = w.Y0 + r, X = w.X0 + cx;
@@ -356,7 +366,7 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
 #pragma unroll 1
             for (int c0 = 0; c0 < p.NC; c0 += 16) {
                 float v[16];
-                tc::tmem_ld16(tmem + 256u * acc + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+                tc::tmem_ld16(tmem + (uint32_t)(p.acc_stride * acc) + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
                 if (pix_ok) {
 #pragma unroll
@@ -442,7 +452,11 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
     int rc = 0;
 
     const int PH = g.H / 2, PW = g.W / 2;
-    const int NC = g.C <= 256 ? g.C : 256;
+    // Channels per pass (UMMA N).  Passes of 128 channels would halve the work items (a finer tail) and let two accumulators
+    // sit next to the A ring in TMEM, but a tf32 UMMA of N = 128 takes as long as one of N = 256 (measured: 178 vs 190 clocks),
+    // so the full width is the default; FLOWOPS_TCB_NC overrides it for A/B timing.
+    int NC = g.C <= 256 ? g.C : 256;
+    if (const char *e = getenv("FLOWOPS_TCB_NC")) { const int v = atoi(e); if (v > 0 && v <= 256 && v % 32 == 0 && g.C % v == 0) NC = v; }   // A/B timing
     CUtensorMap tmB0, tmB1;
     const cuuint64_t row = 128, line = (cuuint64_t)PW * row, img = line * PH, plane = img * (g.C / 32);
     const cuuint64_t dims[5] = {32, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)(g.C / 32), (cuuint64_t)g.B * 4};
@@ -459,8 +473,15 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
     p.which0 = gin1 ? 0 : 1;
     p.n_which = (gin1 ? 1 : 0) + (gin2 ? 1 : 0);
     p.C = g.C; p.NC = NC; p.n_chunks = g.C / NC;
+    const bool atm = !(((corr_impl_flags() >> 1) & 3) & 1);
+    p.nacc = (!atm || NC <= 128) ? 2 : 1;
+    p.acc_stride = (atm && NC <= 128) ? 128 : 256;
     p.H = g.H; p.W = g.W; p.PH = PH; p.PW = PW;
-    p.tilesY = (PH + tcb::TH - 1) / tcb::TH; p.tilesX = (PW + tcb::TW - 1) / tcb::TW;
+    // tile shape: the one that needs fewer (partial) tiles, 16 x 8 on a tie (e.g. 24 x 32 planes: 6 tiles of 8 x 16, not 8 of 16 x 8)
+    const long long t168 = (long long)((PH + 15) / 16) * ((PW + 7) / 8), t816 = (long long)((PH + 7) / 8) * ((PW + 15) / 16);
+    const bool wide = t816 < t168;
+    p.tilesY = wide ? (PH + 7) / 8 : (PH + 15) / 16;
+    p.tilesX = wide ? (PW + 15) / 16 : (PW + 7) / 8;
     p.planes = g.B * 4;
     p.n_items = p.n_which * p.planes * p.tilesY * p.tilesX * p.n_chunks;
     p.nelems = (float)g.C; p.inv_nelems = 1.f / (float)g.C;
@@ -470,16 +491,17 @@ int corr_tc_bwd_launch(const float *in1, const float *in2, const float *gout, fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.n_items < sms ? p.n_items : sms;
+    // p.flags & 1 (flowops_corr_set_impl(3)): A tiles in shared memory (the first version; kept for A/B timing)
+    using T168 = tcb::Tile<16, 8>;
+    using T816 = tcb::Tile<8, 16>;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const tcb::Params) =
+        atm ? (wide ? tcb::corr_bwd_tc<true, T816> : tcb::corr_bwd_tc<true, T168>)
+            : (wide ? tcb::corr_bwd_tc<false, T816> : tcb::corr_bwd_tc<false, T168>);
+    const int smem = atm ? tcb::Cfg<true>::SMEM_BYTES : tcb::Cfg<false>::SMEM_BYTES;
     // per-device attribute, set before every launch (see corr_fast.cu)
-    if (p.flags & 1) {              // flowops_corr_set_impl(3): A tiles in shared memory (the first version; kept for A/B timing)
-        const cudaError_t e = cudaFuncSetAttribute(tcb::corr_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<false>::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", tcb::Cfg<false>::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
-        tcb::corr_bwd_tc<false><<<grid, tcb::THREADS, tcb::Cfg<false>::SMEM_BYTES, st>>>(tmB0, tmB1, p);
-    } else {
-        const cudaError_t e = cudaFuncSetAttribute(tcb::corr_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<true>::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", tcb::Cfg<true>::SMEM_BYTES, cudaGetErrorString(e)); return (int)e; }
-        tcb::corr_bwd_tc<true><<<grid, tcb::THREADS, tcb::Cfg<true>::SMEM_BYTES, st>>>(tmB0, tmB1, p);
-    }
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("corr_bwd: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    kern<<<grid, tcb::THREADS, smem, st>>>(tmB0, tmB1, p);
     return check_launch("corr_bwd_tc");
 }
 

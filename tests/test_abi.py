@@ -74,6 +74,20 @@ def test_tensor_core_correlation_is_tcgen05(flowops_lib):
     assert not re.search(r"\bHMMA\b|\bHGMMA\b", sass), "no legacy mma.sync / wgmma path"
 
 
+def test_tensor_core_correlation_backward_is_tcgen05_with_the_a_operand_in_tmem(flowops_lib):
+    """The Correlation backward: tcgen05.mma, the skewed-gradient operand written into TMEM with tcgen05.st (STTM),
+    accumulators read back with tcgen05.ld (LDTM), 5-D TMA loads of the feature planes."""
+    from ir2rgb_b200 import _lib
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = [f for f in sass.split("Function : ")[1:] if f.startswith("_ZN7flowops3tcb11corr_bwd_tcILb1E")]
+    assert funcs, "corr_bwd_tc<true, ...> is in the library"
+    for f in funcs:
+        assert re.search(r"\bUTC\w*MMA\b", f) and "STTM" in f and "LDTM" in f and "UTMALDG.5D" in f
+
+
 def test_bad_arguments_are_rejected_without_a_device(flowops_lib):
     lib = flowops_lib
     assert lib.flowops_version() == 1

@@ -147,8 +147,14 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
         tensor_flop=flop * tc_x if tc_on else None)
     if tc_on:
         add("corr_fwd_c2_fp32fma", with_impl(0, lambda a, b: F.correlation_forward(a, b, *P)), (a, b), None, alg_flop=flop)
+    # backward on the tensor cores (csrc/corr_tc_bwd.cu): K = the 36 x 28 window (1008 positions, 441 of them inside the band)
+    tcb_x = 3.0 * 1008.0 / 441.0 if tc_on else None
     add("corr_bwd_c2", lambda a, b, go: F.correlation_backward(a, b, go, *P), (a, b, go),
-        (lambda a, b, go: ref.correlation_backward(a, b, go, *P)) if ref else None, alg_flop=2 * flop, ref_iters=2)
+        (lambda a, b, go: ref.correlation_backward(a, b, go, *P)) if ref else None, alg_flop=2 * flop, ref_iters=2,
+        tensor_flop=2 * flop * tcb_x if tc_on else None)
+    if tc_on:
+        add("corr_bwd_c2_fp32fma", with_impl(0, lambda a, b, go: F.correlation_backward(a, b, go, *P)), (a, b, go), None,
+            alg_flop=2 * flop)
     # ---- C4-shaped correlation (FlowNet2 at 512x1024, per-GPU batch 8) ----
     if not small:
         a4, b4 = torch.randn(8, 256, 64, 128, device="cuda"), torch.randn(8, 256, 64, 128, device="cuda")
@@ -159,7 +165,13 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
         if tc_on:
             add("corr_fwd_c4_b8_fp32fma", with_impl(0, lambda a, b: F.correlation_forward(a, b, *P)), (a4, b4), None,
                 alg_flop=2.0 * 8 * 64 * 128 * 441 * 256)
-        del a4, b4
+        go4 = torch.randn(8, 441, 64, 128, device="cuda")
+        add("corr_bwd_c4_b8", lambda a, b, go: F.correlation_backward(a, b, go, *P), (a4, b4, go4), None,
+            alg_flop=4.0 * 8 * 64 * 128 * 441 * 256, tensor_flop=4.0 * 8 * 64 * 128 * 441 * 256 * tcb_x if tc_on else None)
+        if tc_on:
+            add("corr_bwd_c4_b8_fp32fma", with_impl(0, lambda a, b, go: F.correlation_backward(a, b, go, *P)), (a4, b4, go4), None,
+                alg_flop=4.0 * 8 * 64 * 128 * 441 * 256)
+        del a4, b4, go4
 
     # ---- C3: Resample2d + ChannelNorm on 16x3x512x1024 ----
     B, H, W = (2, 128, 256) if small else (16, 512, 1024)

@@ -218,9 +218,13 @@ corr_bwd_tc(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CU
                     const uint32_t first = kb == 0 ? 0u : 1u;
                     if (ATM) {
                         const uint32_t a_hi = tmem + K::A_COL0 + 16u * s, a_lo = a_hi + 8u;
-                        umma_tf32_ts(d, a_lo, b_hi, idesc, first);
-                        umma_tf32_ts(d, a_hi, b_lo, idesc, 1u);
-                        umma_tf32_ts(d, a_hi, b_hi, idesc, 1u);
+                        if (!(p.flags & 2)) {
+                            umma_tf32_ts(d, a_lo, b_hi, idesc, first);
+                            umma_tf32_ts(d, a_hi, b_lo, idesc, 1u);
+                            umma_tf32_ts(d, a_hi, b_hi, idesc, 1u);
+                        } else {
+                            umma_tf32_ts(d, a_hi, b_hi, idesc, first);       // single TF32 product: timing / layout debugging only
+                        }
                     } else {
                         const uint64_t a_hi = tc::smem_desc_sw32(sb), a_lo = tc::smem_desc_sw32(sb + A_BYTES);
                         tc::umma_tf32(d, a_lo, b_hi, idesc, first);

@@ -17,9 +17,10 @@ if op in ("corr_fwd", "corr_bwd"):
     a, b = torch.randn(8, 256, 48, 64, device="cuda"), torch.randn(8, 256, 48, 64, device="cuda")
     go = torch.randn(8, 441, 48, 64, device="cuda")
     fn = (lambda: F.correlation_forward(a, b, *P)) if op == "corr_fwd" else (lambda: F.correlation_backward(a, b, go, *P))
-elif op == "corr_fwd_nhwc_b16":    # what the FlowNet2 step launches: planes from the conv3 epilogue, channels-last store + LeakyReLU
-    a = torch.randn(16, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
-    b = torch.randn(16, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
+elif op in ("corr_fwd_nhwc_b16", "corr_fwd_nhwc_b32"):    # what the FlowNet2 step launches: planes from the conv3 epilogue, channels-last store + LeakyReLU
+    nb = int(op[-2:])
+    a = torch.randn(nb, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
+    b = torch.randn(nb, 256, 64, 128, device="cuda").contiguous(memory_format=torch.channels_last)
     planes = F.CorrelationPlanes(a.shape, a.device)
     zb = torch.zeros(256, device="cuda")
     planes.fill_from_conv_(a, zb, 1.0, 0, write_act=False)

@@ -316,6 +316,15 @@ int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const fl
 int flowops_bias_lrelu_d2s_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
                                    int c_dst, int c_off, float slope, void *stream);
 
+/* The same epilogue with the decoder level's flow upsampler folded in (FlowNetFusion.py:52-60,
+ * torch.cat((skip, deconv(x), upsampled_flow(flow)), 1)): channels [c_off, c_off + C) as above and channels
+ * [c_off + C, c_off + C + 2) = ConvTranspose2d(2, 2, 4, 2, 1)(flow) + flow_bias for the dense channels-last flow
+ * [B, h, w, 2] at the input resolution, flow_weight [2, 2, 4, 4] contiguous, flow_bias [2] or NULL -- the arithmetic of
+ * flowops_flow_deconv_nhwc_to, bit for bit. */
+int flowops_bias_lrelu_d2s_flowup_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
+                                          int c_dst, int c_off, float slope, const float *flow, const float *flow_weight,
+                                          const float *flow_bias, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

@@ -206,6 +206,29 @@ extern "C" int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels
 // ---------------------------------------------------------------------------------------------
 namespace flowops {
 
+// one output pixel of ConvTranspose2d(2, 2, k4, s2, p1): sw = [ci][co][ky][kx] weights in shared memory
+__device__ __forceinline__ float2 flow_deconv_pixel(const float2 *__restrict__ in, const float *sw, float b0, float b1,
+                                                    int b, int oy, int ox, int h, int w)
+{
+    const int py = oy & 1, px = ox & 1, m = oy >> 1, n = ox >> 1;
+    float a0 = b0, a1 = b1;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int iy = m - 1 + py + t, ky = py ? (t ? 0 : 2) : (t ? 1 : 3);
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int ix = n - 1 + px + u, kx = px ? (u ? 0 : 2) : (u ? 1 : 3);
+            if (ix < 0 || ix >= w) continue;
+            const float2 v = __ldg(in + ((size_t)b * h + iy) * w + ix);
+            const int k = ky * 4 + kx;
+            a0 = __fmaf_rn(v.x, sw[k], a0);      a1 = __fmaf_rn(v.x, sw[16 + k], a1);        // ci = 0 -> co = 0, 1
+            a0 = __fmaf_rn(v.y, sw[32 + k], a0); a1 = __fmaf_rn(v.y, sw[48 + k], a1);        // ci = 1
+        }
+    }
+    return make_float2(a0, a1);
+}
+
 __global__ void __launch_bounds__(256) flow_deconv_nhwc_kernel(const float2 *__restrict__ in, const float *__restrict__ wgt,
                                                                const float *__restrict__ bias, float *__restrict__ dst,
                                                                int B, int h, int w, unsigned c_dst, unsigned c_off)
@@ -220,23 +243,7 @@ __global__ void __launch_bounds__(256) flow_deconv_nhwc_kernel(const float2 *__r
         const int ox = (int)(i % W2);
         const size_t r = i / W2;
         const int oy = (int)(r % H2), b = (int)(r / H2);
-        const int py = oy & 1, px = ox & 1, m = oy >> 1, n = ox >> 1;
-        float a0 = b0, a1 = b1;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int iy = m - 1 + py + t, ky = py ? (t ? 0 : 2) : (t ? 1 : 3);
-            if (iy < 0 || iy >= h) continue;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int ix = n - 1 + px + u, kx = px ? (u ? 0 : 2) : (u ? 1 : 3);
-                if (ix < 0 || ix >= w) continue;
-                const float2 v = __ldg(in + ((size_t)b * h + iy) * w + ix);
-                const int k = ky * 4 + kx;
-                a0 = __fmaf_rn(v.x, sw[k], a0);      a1 = __fmaf_rn(v.x, sw[16 + k], a1);        // ci = 0 -> co = 0, 1
-                a0 = __fmaf_rn(v.y, sw[32 + k], a0); a1 = __fmaf_rn(v.y, sw[48 + k], a1);        // ci = 1
-            }
-        }
-        *reinterpret_cast<float2 *>(dst + i * c_dst + c_off) = make_float2(a0, a1);
+        *reinterpret_cast<float2 *>(dst + i * c_dst + c_off) = flow_deconv_pixel(in, sw, b0, b1, b, oy, ox, h, w);
     }
 }
 
@@ -308,4 +315,70 @@ extern "C" int flowops_bias_lrelu_d2s_nhwc_to(const float *y4, const float *bias
                                                                                  (unsigned)h, (unsigned)w, (unsigned)(C / 4), (unsigned)c_dst,
                                                                                  (unsigned)c_off, slope);
     return check_launch("bias_lrelu_d2s_nhwc_to");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The same epilogue with the decoder level's 2-channel flow upsampler folded in: channels [c_off, c_off + C) as above and
+// channels [c_off + C, c_off + C + 2) = ConvTranspose2d(2, 2, k4, s2, p1)(flow) + its bias, for the flow at the INPUT
+// resolution [B, h, w, 2] (FlowNetFusion.py:52-60: torch.cat((skip, deconv(x), upsampled_flow(flow)), 1)).  One more "quad"
+// per output pixel writes the two flow channels right behind the pixel's run of deconvolution channels, instead of a second
+// kernel writing 8 bytes per pixel at the concat buffer's channel pitch (309 us per 16 pairs at 512 x 1024).
+// ---------------------------------------------------------------------------------------------
+namespace flowops {
+
+__global__ void __launch_bounds__(256) bias_lrelu_d2s_flowup_kernel(const float4 *__restrict__ y4, const float *__restrict__ bias,
+                                                                    float *__restrict__ dst, size_t total_q, unsigned h, unsigned w,
+                                                                    unsigned cq, unsigned c_dst, unsigned c_off, float slope,
+                                                                    const float2 *__restrict__ flow, const float *__restrict__ fwgt,
+                                                                    const float *__restrict__ fbias)
+{
+    __shared__ float sw[64];
+    if (threadIdx.x < 64) sw[threadIdx.x] = fwgt[threadIdx.x];
+    __syncthreads();
+    const float fb0 = fbias ? __ldg(fbias) : 0.f, fb1 = fbias ? __ldg(fbias + 1) : 0.f;
+    const unsigned cq1 = cq + 1;                               // quads per output pixel: C / 4 of the deconvolution + 1 for the flow
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_q; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned q = (unsigned)(i % cq1);
+        size_t r = i / cq1;
+        const unsigned par = (unsigned)(r & 3); r >>= 2;
+        const unsigned n = (unsigned)(r % w); r /= w;
+        const unsigned m = (unsigned)(r % h);
+        const size_t b = r / h;
+        const unsigned oy = 2 * m + (par >> 1), ox = 2 * n + (par & 1);
+        const size_t pix = (b * (2 * h) + oy) * (size_t)(2 * w) + ox;
+        if (q < cq) {
+            const float4 v = y4[(((b * h + m) * w + n) * 4 + par) * cq + q];
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias) + q);
+            float4 o;
+            o.x = __fadd_rn(v.x, bb.x); o.x = o.x > 0.f ? o.x : __fmul_rn(o.x, slope);
+            o.y = __fadd_rn(v.y, bb.y); o.y = o.y > 0.f ? o.y : __fmul_rn(o.y, slope);
+            o.z = __fadd_rn(v.z, bb.z); o.z = o.z > 0.f ? o.z : __fmul_rn(o.z, slope);
+            o.w = __fadd_rn(v.w, bb.w); o.w = o.w > 0.f ? o.w : __fmul_rn(o.w, slope);
+            *reinterpret_cast<float4 *>(dst + pix * c_dst + c_off + 4 * q) = o;
+        } else {
+            *reinterpret_cast<float2 *>(dst + pix * c_dst + c_off + 4 * cq) = flow_deconv_pixel(flow, sw, fb0, fb1, (int)b, (int)oy, (int)ox, (int)h, (int)w);
+        }
+    }
+}
+
+}  // namespace flowops
+
+extern "C" int flowops_bias_lrelu_d2s_flowup_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
+                                                     int c_dst, int c_off, float slope, const float *flow, const float *flow_weight,
+                                                     const float *flow_bias, void *stream)
+{
+    FLOWOPS_REQUIRE(y4 && bias && dst && flow && flow_weight, FLOWOPS_EINVAL, "bias_lrelu_d2s_flowup_nhwc_to: null pointer");
+    FLOWOPS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && (C & 3) == 0 && c_off >= 0 && c_off + C + 2 <= c_dst && ((c_off | c_dst) & 3) == 0,
+                    FLOWOPS_EINVAL, "bias_lrelu_d2s_flowup_nhwc_to: bad shape / channel range (C %d + 2, channels from %d of %d; multiples of 4)", C, c_off, c_dst);
+    FLOWOPS_REQUIRE(aligned16(y4) && aligned16(dst) && aligned16(bias) && (((uintptr_t)flow) & 7) == 0, FLOWOPS_EINVAL,
+                    "bias_lrelu_d2s_flowup_nhwc_to: 16-byte alignment required (8 for the flow)");
+    const size_t total_q = (size_t)B * h * w * 4 * (C / 4 + 1);
+    size_t blocks = (total_q + 255) / 256;
+    const size_t cap = (size_t)kNumSMs * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    bias_lrelu_d2s_flowup_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(y4), bias, dst, total_q, (unsigned)h, (unsigned)w, (unsigned)(C / 4), (unsigned)c_dst, (unsigned)c_off,
+        slope, reinterpret_cast<const float2 *>(flow), flow_weight, flow_bias);
+    return check_launch("bias_lrelu_d2s_flowup_nhwc_to");
 }

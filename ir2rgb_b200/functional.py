@@ -413,15 +413,25 @@ class ConcatBuffer:
                                                           _stream()), "flow_deconv_nhwc_to")
         return c_off + 2
 
-    def bias_lrelu_d2s_in(self, y4, bias, slope, c_off):
+    def bias_lrelu_d2s_in(self, y4, bias, slope, c_off, flow_up=None):
         """dst[b, 2m+py, 2n+px, c_off + co] = LeakyReLU(y4[b, m, n, (py*2+px)*C + co] + bias[co]): the epilogue of a k4 s2 p1
         transposed convolution computed as a 3x3 convolution with 4*C output channels at the input resolution (one group
-        of C per output parity) -- bias, activation and depth-to-space in one pass into the concat slice."""
+        of C per output parity) -- bias, activation and depth-to-space in one pass into the concat slice.  With
+        flow_up = (flow, weight, bias) the level's 2-channel flow upsampler (see flow_deconv_in) is written by the same
+        kernel into the two channels behind the slice."""
         B, C4, h, w = y4.shape
         with torch.cuda.device_of(y4):
-            check(_lib.load().flowops_bias_lrelu_d2s_nhwc_to(_p(y4), _p(bias), _p(self.tensor), B, h, w, C4 // 4, self.c_pad, c_off,
-                                                             ctypes.c_float(slope), _stream()), "bias_lrelu_d2s_nhwc_to")
-        return c_off + C4 // 4
+            if flow_up is None:
+                check(_lib.load().flowops_bias_lrelu_d2s_nhwc_to(_p(y4), _p(bias), _p(self.tensor), B, h, w, C4 // 4, self.c_pad, c_off,
+                                                                 ctypes.c_float(slope), _stream()), "bias_lrelu_d2s_nhwc_to")
+                return c_off + C4 // 4
+            flow, fw, fb = flow_up
+            if tuple(flow.shape) != (B, 2, h, w):
+                raise ValueError("bias_lrelu_d2s_in: the flow must be [B, 2, h, w] at the deconvolution's input resolution")
+            check(_lib.load().flowops_bias_lrelu_d2s_flowup_nhwc_to(_p(y4), _p(bias), _p(self.tensor), B, h, w, C4 // 4, self.c_pad, c_off,
+                                                                    ctypes.c_float(slope), _p(flow), _p(fw), _p(fb), _stream()),
+                  "bias_lrelu_d2s_flowup_nhwc_to")
+        return c_off + C4 // 4 + 2
 
     def bias_lrelu_in(self, y, bias, slope, c_off, in_place_too=False):
         """dst[:, c_off : c_off + C] = LeakyReLU(y + bias) for a dense channels_last conv output y; with in_place_too

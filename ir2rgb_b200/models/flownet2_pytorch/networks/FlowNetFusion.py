@@ -27,9 +27,13 @@ class FlowNetFusion(nn.Module):
         162 -> 168, 82 -> 88), the deconvolution's epilogue writes its slice, only the 2-channel flow is copied."""
         if sk.buf is not None and deconv_lv.fusable(feat) and _F._is_nhwc(feat):
             off = skip.shape[1]
-            deconv_lv(feat, into=(sk.buf, off))
             c_up = off + deconv_lv[0].out_channels
-            if _sm.FUSE_FLOW_UPSAMPLER and c_up % 2 == 0 and _sm._flow_upsampler_ok(upconv, flow):
+            fuse_up = _sm.FUSE_FLOW_UPSAMPLER and c_up % 2 == 0 and _sm._flow_upsampler_ok(upconv, flow)
+            fu = {"flow": flow, "weight": _sm._dense_weight(upconv), "bias": upconv.bias, "done": False} if fuse_up else None
+            deconv_lv(feat, into=(sk.buf, off), flow_up=fu)     # the depth-to-space epilogue takes the flow upsampler along
+            if fuse_up and fu["done"]:
+                pass
+            elif fuse_up:
                 sk.buf.flow_deconv_in(flow, _sm._dense_weight(upconv), upconv.bias, c_up)     # one kernel, straight into its slice
             else:
                 sk.buf.copy_in(apply_conv(upconv, flow), c_up)

@@ -114,7 +114,7 @@ class ConvAct(nn.Sequential):
         return (FUSE_EPILOGUE and len(self) == 2 and self[0].bias is not None and not torch.is_grad_enabled()
                 and x.is_cuda and x.dtype == torch.float32)
 
-    def forward(self, x, into=None, skip=None):
+    def forward(self, x, into=None, skip=None, flow_up=None):
         conv = self[0]
         if self.fusable(x):
             sbuf = None
@@ -154,7 +154,7 @@ class ConvAct(nn.Sequential):
                 # narrow transposed convolution (<= 32 output channels: cuDNN's strided-dgrad kernel runs it at a fraction
                 # of the tensor-op rate) as a 3x3 convolution with 4 * C output channels + depth-to-space epilogue, where
                 # timing both once says it is faster
-                if _deconv_conv3_run(self, conv, x, into):
+                if _deconv_conv3_run(self, conv, x, into, flow_up):
                     return None
             y = _raw_conv(conv, x, None)
             if into is not None:
@@ -210,15 +210,19 @@ def deconv_as_conv3_weight(conv, w):
     return cache[1]
 
 
-def _deconv_conv3_run(act, conv, x, into):
+def _deconv_conv3_run(act, conv, x, into, flow_up=None):
     """Run (and, the first time per shape, time against strided dgrad + epilogue) the 3x3-convolution form; False when the
-    plain path is faster for this layer."""
+    plain path is faster for this layer.  flow_up: {"flow", "weight", "bias", "done"} of the level's flow upsampler -- the
+    depth-to-space epilogue then writes the two upsampled flow channels behind the slice too and sets "done"."""
     buf, c_off = into
     slope = act[1].negative_slope
     w3 = deconv_as_conv3_weight(conv, padded_weight(conv, x.shape[1]))
+    fu = None
+    if flow_up is not None and tuple(flow_up["flow"].shape[2:]) == tuple(x.shape[2:]) and (c_off + conv.out_channels) % 2 == 0:
+        fu = (flow_up["flow"], flow_up["weight"], flow_up["bias"])
 
     def as_conv3():
-        buf.bias_lrelu_d2s_in(F.conv2d(x, w3, None, 1, 1), conv.bias, slope, c_off)
+        buf.bias_lrelu_d2s_in(F.conv2d(x, w3, None, 1, 1), conv.bias, slope, c_off, fu)
     key = (tuple(x.shape), buf.c_pad, c_off)
     choice = conv.__dict__.setdefault("_flowops_conv3_choice", {})
     if key not in choice:
@@ -231,6 +235,8 @@ def _deconv_conv3_run(act, conv, x, into):
     if not choice[key]:
         return False
     as_conv3()
+    if fu is not None:
+        flow_up["done"] = True
     return True
 
 

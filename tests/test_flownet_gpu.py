@@ -446,3 +446,30 @@ def test_narrow_deconv_as_conv3_with_depth_to_space_epilogue(flowops_lib, cin, c
         assert (buf.tensor[:, :8] == 5.0).all() and (buf.tensor[:, 8 + cout:] == 5.0).all()
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(168, 16, 32, 48), (24, 8, 9, 7), (40, 32, 1, 1)])
+def test_depth_to_space_epilogue_with_the_flow_upsampler_folded_in(flowops_lib, cin, cout, h, w):
+    """flowops_bias_lrelu_d2s_flowup_nhwc_to: the deconvolution slice equals the plain depth-to-space epilogue and the two flow
+    channels behind it equal flowops_flow_deconv_nhwc_to, bit for bit; the rest of the concat buffer is untouched."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(41)
+    conv = torch.nn.ConvTranspose2d(cin, cout, 4, 2, 1).cuda().to(memory_format=torch.channels_last)
+    up = torch.nn.ConvTranspose2d(2, 2, 4, 2, 1).cuda()
+    x = torch.randn(2, cin, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
+    flow = (3 * torch.randn(2, 2, h, w, device="cuda")).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y4 = torch.nn.functional.conv2d(x, sm.deconv_as_conv3_weight(conv, conv.weight), None, 1, 1)
+        fw = up.weight.detach().contiguous()
+        sep = F.ConcatBuffer(x, cout + 14, 8, shape=(2, 2 * h, 2 * w))
+        sep.tensor.fill_(5.0)
+        sep.bias_lrelu_d2s_in(y4, conv.bias, 0.1, 8)
+        sep.flow_deconv_in(flow, fw, up.bias, 8 + cout)
+        one = F.ConcatBuffer(x, cout + 14, 8, shape=(2, 2 * h, 2 * w))
+        one.tensor.fill_(5.0)
+        assert one.bias_lrelu_d2s_in(y4, conv.bias, 0.1, 8, (flow, fw, up.bias)) == 8 + cout + 2
+        want_up = up(flow)
+    assert torch.equal(one.tensor, sep.tensor)
+    assert ((one.tensor[:, 8 + cout:10 + cout] - want_up).abs().max() / want_up.abs().max()).item() <= 1e-6
+    assert (one.tensor[:, :8] == 5.0).all() and (one.tensor[:, 10 + cout:] == 5.0).all()

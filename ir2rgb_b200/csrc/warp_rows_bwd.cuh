@@ -15,6 +15,8 @@
 //   * the flow gradient is the forward's gather, with the same prefetch of the next row's flow and the same
 //     32-bit corner addressing (warp_rows.cuh).
 #pragma once
+#include <stdlib.h>
+
 #include "warp_rows.cuh"
 
 namespace flowops {
@@ -33,19 +35,73 @@ __device__ __forceinline__ void red_add_nz(float *p, float v)
     if (!(v == 0.f)) red_add(p, v);
 }
 
+// Per-pixel state of the backward: corner offsets (top-left and the row below; the right-hand column is +1 when `ex`),
+// image-gradient weights, and what the flow gradient of either coordinate convention needs.
+struct BwdPix {
+    unsigned o_t, o_b, xL, yT;
+    bool ex, ey;
+    float w_tl, w_tr, w_bl, w_br;                    // image-gradient weights
+    float gam_x, gam_y;                              // RESAMPLE2D flow-gradient weights
+    float ax, ay, bx, by;                            // GRIDSAMPLE: (ix_se-ix),(iy_se-iy),(ix-ix_nw),(iy-iy_nw)
+    float gmx, gmy;
+};
+
+template <int MODE>
+__device__ __forceinline__ void bwd_pix_setup(BwdPix &q, const WarpBwdArgs &a, float xfl, float yfl, float lin_xv, int y, float dx, float dy)
+{
+    const unsigned W = (unsigned)a.W;
+    q.gam_x = q.gam_y = q.ax = q.ay = q.bx = q.by = q.gmx = q.gmy = 0.f;
+    if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
+        const float xf = __fadd_rn(xfl, dx), yf = __fadd_rn(yfl, dy);
+        float fx = __fsub_rn(__fadd_rn(xf, kMagic15), kMagic15); fx = fx > xf ? __fsub_rn(fx, 1.f) : fx;
+        float fy = __fsub_rn(__fadd_rn(yf, kMagic15), kMagic15); fy = fy > yf ? __fsub_rn(fy, 1.f) : fy;
+        float tx = (xf < 0.f && fx != xf) ? __fadd_rn(fx, 1.f) : fx;      // (float)(int)xf: truncation
+        float ty = (yf < 0.f && fy != yf) ? __fadd_rn(fy, 1.f) : fy;
+        if (__builtin_expect(!(fmaxf(fabsf(xf), fabsf(yf)) < 4194304.f), 0)) {
+            fx = floorf(xf); fy = floorf(yf); tx = (float)(int)xf; ty = (float)(int)yf;
+        }
+        const unsigned xL = q.xL = (unsigned)small_float_as_int(fminf(fmaxf(fx, 0.f), a.wm1));
+        const unsigned yT = q.yT = (unsigned)small_float_as_int(fminf(fmaxf(fy, 0.f), a.hm1));
+        q.ex = fx >= 0.f && fx < a.wm1;
+        q.ey = fy >= 0.f && fy < a.hm1;
+        q.o_t = yT * W + xL;
+        // resample2d_kernel.cu:97-98: truncation, not floor, in the image-gradient kernel
+        const float alpha = __fsub_rn(xf, tx), beta = __fsub_rn(yf, ty);
+        q.w_tl = (1 - alpha) * (1 - beta); q.w_tr = alpha * (1 - beta);
+        q.w_bl = (1 - alpha) * beta;       q.w_br = alpha * beta;
+        q.gam_x = 1 - __fsub_rn(xf, fx);     // :160 (used for d/d dy)
+        q.gam_y = 1 - __fsub_rn(yf, fy);     // :172 (used for d/d dx)
+    } else {
+        const float gx = __fadd_rn(lin_xv, __fmul_rn(dx, a.invx));
+        const float gy = __fadd_rn(__ldg(a.lin_y + y), __fmul_rn(dy, a.invy));
+        float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), a.wm1 + 1.f, -1.f), 0.5f);
+        float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), a.hm1 + 1.f, -1.f), 0.5f);
+        // clip_coordinates_set_grad: gradient is zero at and beyond both borders
+        q.gmx = (ix <= 0.f || ix >= a.wm1) ? 0.f : 1.f;
+        q.gmy = (iy <= 0.f || iy >= a.hm1) ? 0.f : 1.f;
+        ix = fminf(a.wm1, fmaxf(ix, 0.f));
+        iy = fminf(a.hm1, fmaxf(iy, 0.f));
+        float fx = __fsub_rn(__fadd_rn(ix, kMagic15), kMagic15); fx = fx > ix ? __fsub_rn(fx, 1.f) : fx;
+        float fy = __fsub_rn(__fadd_rn(iy, kMagic15), kMagic15); fy = fy > iy ? __fsub_rn(fy, 1.f) : fy;
+        q.ex = __fadd_rn(fx, 1.f) <= a.wm1;           // weight of a clamped neighbour is 0
+        q.ey = __fadd_rn(fy, 1.f) <= a.hm1;
+        q.xL = (unsigned)small_float_as_int(fx); q.yT = (unsigned)small_float_as_int(fy);
+        q.o_t = q.yT * W + q.xL;
+        q.ax = __fadd_rn(fx, 1.f) - ix; q.ay = __fadd_rn(fy, 1.f) - iy;
+        q.bx = ix - fx;                 q.by = iy - fy;
+        q.w_tl = q.ax * q.ay; q.w_tr = q.bx * q.ay; q.w_bl = q.ax * q.by; q.w_br = q.bx * q.by;
+    }
+    q.o_b = q.ey ? q.o_t + W : q.o_t;
+}
+
+// rows y0 .. y1-1 of column xr of batch item b, for one whole warp (lane = position inside a 32-pixel row segment)
 template <int MODE, int CT, bool NEED_IMG, bool NEED_FLOW>
-__global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_constant__ WarpBwdArgs a)
+__device__ __forceinline__ void warp_rows_bwd_body(const WarpBwdArgs &a, int xr, int y0, int y1, int lane, size_t b)
 {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int xr = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid_x = xr < a.W;                    // out-of-image lanes stay alive for the shuffles
     const int x = valid_x ? xr : a.W - 1;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
-    if (y0 >= a.H) return;                            // uniform per warp (a warp never spans two rows)
-    const int y1 = min(y0 + a.rows, a.H);
     const unsigned hw = (unsigned)a.H * a.W, W = (unsigned)a.W;
-    const size_t b = blockIdx.z;
     const float *src = a.img + b * CT * hw;
     asm("" : "+l"(src));
     float *gi = NEED_IMG ? a.gimg + b * CT * hw : nullptr;
@@ -72,52 +128,12 @@ __global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < CT; ++c) g[c] = valid_x ? ldg_stream(go + (size_t)c * hw) : 0.f;
 
-        unsigned o_t, o_b;
-        bool ex, ey;
-        float w_tl, w_tr, w_bl, w_br;                    // image-gradient weights
-        float gam_x = 0.f, gam_y = 0.f;                  // RESAMPLE2D flow-gradient weights
-        float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;    // GRIDSAMPLE: (ix_se-ix),(iy_se-iy),(ix-ix_nw),(iy-iy_nw)
-        float gmx = 0.f, gmy = 0.f;
-        if (MODE == FLOWOPS_WARP_RESAMPLE2D) {
-            const float xf = __fadd_rn(xfl, dx), yf = __fadd_rn(yfl, dy);
-            float fx = __fsub_rn(__fadd_rn(xf, kMagic15), kMagic15); fx = fx > xf ? __fsub_rn(fx, 1.f) : fx;
-            float fy = __fsub_rn(__fadd_rn(yf, kMagic15), kMagic15); fy = fy > yf ? __fsub_rn(fy, 1.f) : fy;
-            float tx = (xf < 0.f && fx != xf) ? __fadd_rn(fx, 1.f) : fx;      // (float)(int)xf: truncation
-            float ty = (yf < 0.f && fy != yf) ? __fadd_rn(fy, 1.f) : fy;
-            if (__builtin_expect(!(fmaxf(fabsf(xf), fabsf(yf)) < 4194304.f), 0)) {
-                fx = floorf(xf); fy = floorf(yf); tx = (float)(int)xf; ty = (float)(int)yf;
-            }
-            const unsigned xL = (unsigned)small_float_as_int(fminf(fmaxf(fx, 0.f), a.wm1));
-            const unsigned yT = (unsigned)small_float_as_int(fminf(fmaxf(fy, 0.f), a.hm1));
-            ex = fx >= 0.f && fx < a.wm1;
-            ey = fy >= 0.f && fy < a.hm1;
-            o_t = yT * W + xL;
-            // resample2d_kernel.cu:97-98: truncation, not floor, in the image-gradient kernel
-            const float alpha = __fsub_rn(xf, tx), beta = __fsub_rn(yf, ty);
-            w_tl = (1 - alpha) * (1 - beta); w_tr = alpha * (1 - beta);
-            w_bl = (1 - alpha) * beta;       w_br = alpha * beta;
-            gam_x = 1 - __fsub_rn(xf, fx);     // :160 (used for d/d dy)
-            gam_y = 1 - __fsub_rn(yf, fy);     // :172 (used for d/d dx)
-        } else {
-            const float gx = __fadd_rn(lin_xv, __fmul_rn(dx, a.invx));
-            const float gy = __fadd_rn(__ldg(a.lin_y + y), __fmul_rn(dy, a.invy));
-            float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), a.wm1 + 1.f, -1.f), 0.5f);
-            float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), a.hm1 + 1.f, -1.f), 0.5f);
-            // clip_coordinates_set_grad: gradient is zero at and beyond both borders
-            gmx = (ix <= 0.f || ix >= a.wm1) ? 0.f : 1.f;
-            gmy = (iy <= 0.f || iy >= a.hm1) ? 0.f : 1.f;
-            ix = fminf(a.wm1, fmaxf(ix, 0.f));
-            iy = fminf(a.hm1, fmaxf(iy, 0.f));
-            float fx = __fsub_rn(__fadd_rn(ix, kMagic15), kMagic15); fx = fx > ix ? __fsub_rn(fx, 1.f) : fx;
-            float fy = __fsub_rn(__fadd_rn(iy, kMagic15), kMagic15); fy = fy > iy ? __fsub_rn(fy, 1.f) : fy;
-            ex = __fadd_rn(fx, 1.f) <= a.wm1;           // weight of a clamped neighbour is 0
-            ey = __fadd_rn(fy, 1.f) <= a.hm1;
-            o_t = (unsigned)small_float_as_int(fy) * W + (unsigned)small_float_as_int(fx);
-            ax = __fadd_rn(fx, 1.f) - ix; ay = __fadd_rn(fy, 1.f) - iy;
-            bx = ix - fx;                 by = iy - fy;
-            w_tl = ax * ay; w_tr = bx * ay; w_bl = ax * by; w_br = bx * by;
-        }
-        o_b = ey ? o_t + W : o_t;
+        BwdPix q;
+        bwd_pix_setup<MODE>(q, a, xfl, yfl, lin_xv, y, dx, dy);
+        const unsigned o_t = q.o_t, o_b = q.o_b;
+        const bool ex = q.ex, ey = q.ey;
+        const float w_tl = q.w_tl, w_tr = q.w_tr, w_bl = q.w_bl, w_br = q.w_br;
+        const float gam_x = q.gam_x, gam_y = q.gam_y, ax = q.ax, ay = q.ay, bx = q.bx, by = q.by, gmx = q.gmx, gmy = q.gmy;
 
         float gfx = 0.f, gfy = 0.f;
         if (NEED_FLOW) {
@@ -200,6 +216,15 @@ __global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_cons
     }
 }
 
+template <int MODE, int CT, bool NEED_IMG, bool NEED_FLOW>
+__global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_constant__ WarpBwdArgs a)
+{
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
+    if (y0 >= a.H) return;                            // uniform per warp (a warp never spans two rows)
+    warp_rows_bwd_body<MODE, CT, NEED_IMG, NEED_FLOW>(a, blockIdx.x * blockDim.x + threadIdx.x, y0, min(y0 + a.rows, a.H),
+                                                      threadIdx.x & 31, blockIdx.z);
+}
+
 template <int MODE, bool NEED_IMG, bool NEED_FLOW>
 static inline void launch_warp_rows_bwd(WarpBwdArgs a, cudaStream_t st)
 {
@@ -213,6 +238,14 @@ static inline void launch_warp_rows_bwd(WarpBwdArgs a, cudaStream_t st)
         if (a.gflow) c.gflow = a.gflow + (size_t)b0 * 2 * hw;
         dim3 grid, block;
         warp_rows_shape(c.B, c.H, c.W, c.rows, grid, block);
+        if (const char *e = getenv("FLOWOPS_TUNE_BWD_GEOM")) {          // "bx,by,rows": A/B timing of the CTA footprint
+            int bx = 0, by = 0, rows = 0;
+            if (sscanf(e, "%d,%d,%d", &bx, &by, &rows) == 3 && bx >= 32 && bx % 32 == 0 && by >= 1 && bx * by <= 256 && rows >= 1) {
+                c.rows = rows;
+                block = dim3(bx, by, 1);
+                grid = dim3((c.W + bx - 1) / bx, (c.H + by * rows - 1) / (by * rows), c.B);
+            }
+        }
         if (a.C == 3) warp_rows_bwd_kernel<MODE, 3, NEED_IMG, NEED_FLOW><<<grid, block, 0, st>>>(c);
         else if (a.C == 2) warp_rows_bwd_kernel<MODE, 2, NEED_IMG, NEED_FLOW><<<grid, block, 0, st>>>(c);
         else warp_rows_bwd_kernel<MODE, 1, NEED_IMG, NEED_FLOW><<<grid, block, 0, st>>>(c);

@@ -586,6 +586,52 @@ def test_warp_backward_window_kernel_matches_direct_reductions(flowops_lib, c_or
         assert maxrel(gi_w, gi_o) <= BWD_TOL
 
 
+@pytest.mark.parametrize("case", [(2, 3, 40, 56, 3.0), (1, 2, 33, 70, 0.0), (2, 3, 64, 96, 40.0), (1, 1, 7, 5, 2.0), (2, 3, 128, 160, 1.0),
+                                  (1, 3, 96, 64, "nan"), (1, 3, 64, 64, "huge"), (1, 3, 64, 64, "tiny")])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_warp_backward_fixed_point_kernel_matches_direct_reductions(flowops_lib, c_oracle, case, mode):
+    """The fixed-point shared-memory image gradient (warp_fx_bwd.cuh, flowops_warp_set_impl(4)) against the direct-reduction
+    kernel and, on the small cases, the C oracle: tiles that fit the window (small flows), tiles that fall back (40-pixel
+    noise), ragged edges, NaN flows and Inf gradients (must propagate exactly as in the direct kernel), gradients of 1e30 and
+    1e-25 (the scaling is relative to the tile's largest gradient)."""
+    from ir2rgb_b200 import functional as F
+    B, C, H, W, amp = case
+    torch.manual_seed(23)
+    img = torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, C, H, W, device="cuda")
+    if isinstance(amp, str):
+        flow = (2.0 * torch.randn(B, 2, H, W, device="cuda")).contiguous()
+        if amp == "nan":
+            flow[0, 0, 10, 12] = float("nan")
+            flow[0, 1, 50, 3] = float("inf")
+            go[0, 1, 70, 40] = float("inf")
+        elif amp == "huge":
+            go *= 1e30
+        else:
+            go *= 1e-25
+    else:
+        flow = (amp * torch.randn(B, 2, H, W, device="cuda")).contiguous()
+    prev = flowops_lib.flowops_warp_get_impl()
+    try:
+        flowops_lib.flowops_warp_set_impl(0)
+        gi_d, gf_d = F.warp_backward(img, flow, go, True, True, mode)
+        flowops_lib.flowops_warp_set_impl(4)
+        gi_f, gf_f = F.warp_backward(img, flow, go, True, True, mode)
+        gi_f2, _ = F.warp_backward(img, flow, go, True, False, mode)
+    finally:
+        flowops_lib.flowops_warp_set_impl(prev)
+    assert torch.equal(gf_f, gf_d, ) or torch.equal(torch.nan_to_num(gf_f, nan=7.0), torch.nan_to_num(gf_d, nan=7.0))     # same gather
+    if amp == "nan":
+        assert torch.equal(torch.isnan(gi_f), torch.isnan(gi_d)) and torch.equal(torch.isinf(gi_f), torch.isinf(gi_d))
+        ok = torch.isfinite(gi_d)
+        assert maxrel(gi_f[ok], gi_d[ok]) <= 1e-5
+    else:
+        assert maxrel(gi_f, gi_d) <= 1e-5 and maxrel(gi_f2, gi_d) <= 1e-5
+    if mode == 0 and H * W <= 4096 and not isinstance(amp, str):
+        gi_o, _ = c_oracle.resample2d_bwd(img.cpu().numpy(), flow.cpu().numpy(), go.cpu().numpy())
+        assert maxrel(gi_f, gi_o) <= BWD_TOL
+
+
 @pytest.mark.parametrize("flavour", ["randn", "smooth", "border"])
 def test_resample2d_tolerance_mode_vs_reference_ext(ops, ref, flavour):
     """fp32-weight blend (functional.warp_tolerance_mode, what FlowNet runs): within 1e-6 of the reference's kernel --

@@ -216,8 +216,13 @@ __device__ __forceinline__ void warp_rows_bwd_body(const WarpBwdArgs &a, int xr,
     }
 }
 
+// Tuning macro (variant builds, tools/ab_ops.py): resident CTAs per SM the register allocation of the backward aims at
+#ifndef FLOWOPS_TUNE_BWD_MINB
+#define FLOWOPS_TUNE_BWD_MINB 3
+#endif
+
 template <int MODE, int CT, bool NEED_IMG, bool NEED_FLOW>
-__global__ void __launch_bounds__(256, 3) warp_rows_bwd_kernel(const __grid_constant__ WarpBwdArgs a)
+__global__ void __launch_bounds__(256, FLOWOPS_TUNE_BWD_MINB) warp_rows_bwd_kernel(const __grid_constant__ WarpBwdArgs a)
 {
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * a.rows;
     if (y0 >= a.H) return;                            // uniform per warp (a warp never spans two rows)

@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="layout of the FlowNet2 conv body in the native arm (the reference arm keeps the stock NCHW)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="native arm: launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--sd-overlap", action="store_true", help="native arm: run FlowNetSD on a second stream beside FlowNetC -> S -> S (A/B; no gain measured)")
+    ap.add_argument("--no-sd-pad16", action="store_true", help="native arm: FlowNetSD.conv0 reads the 8-channel frame stack instead of the 16-channel one (A/B)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="keep cuDNN autotuning launches out of ncu launch lists")
     return ap.parse_args()
 
@@ -170,7 +172,7 @@ class Launches:
         F.bias_lrelu_ = epi
 
 
-def build_native(device, memory_format="channels_last"):
+def build_native(device, memory_format="channels_last", overlap_sd=False, sd_pad16=True):
     import torch
     from ir2rgb_b200.models.flownet import FlowNet
     net = FlowNet(fp16=False, flownet_checkpoint_path=None, gpu_ids=[device.index], checkpoints_dir=".", name="bench")
@@ -178,6 +180,8 @@ def build_native(device, memory_format="channels_last"):
         # conv body tuning: NHWC weights/activations let cuDNN run its tensor-op kernels
         # without the NCHW<->NHWC transposes that take ~30 % of the stock forward (profiles/launches_r01_*)
         net.flowNet = net.flowNet.to(memory_format=torch.channels_last)
+    net.flowNet.overlap_sd = overlap_sd
+    net.flowNet.sd_pad16 = sd_pad16
     return net.eval()
 
 
@@ -326,7 +330,7 @@ def main():
         ffma_idle = F0.ffma_peak_tflops()            # FP32-FMA pipe peak on the idle, cool GPU (before any step has run)
         launches.install()
         torch.manual_seed(0)
-        net = build_native(device, args.memory_format)
+        net = build_native(device, args.memory_format, args.sd_overlap, not args.no_sd_pad16)
         if not args.no_cuda_graph:
             from ir2rgb_b200.runtime import GraphedFlowNet
             net = GraphedFlowNet(net)
@@ -361,10 +365,13 @@ def main():
     n_launch, corr_events, ms_eager = 0, [], None
     if args.impl == "native":
         eager = getattr(net, "net", net)
+        overlap = eager.flowNet.overlap_sd
+        eager.flowNet.overlap_sd = False         # per-kernel timings: no second stream running beside the timed kernels
         run_step(eager, im1, im2, mb)
         launches.enabled = True
         ms_eager = timed(lambda: run_step(eager, im1, im2, mb), 1, 0, None, device)
         launches.enabled = False
+        eager.flowNet.overlap_sd = overlap
         n_launch = launches.count * args.steps
         corr_events = launches.corr_events
 
@@ -382,6 +389,7 @@ def main():
                        "conv_math": "cudnn fp32 with TF32 allowed (torch default, same in the reference arm)",
                        "conv_layout": args.memory_format if args.impl == "native" else "contiguous",
                        "cuda_graph": bool(args.impl == "native" and not args.no_cuda_graph),
+                       "sd_branch_on_second_stream": bool(args.impl == "native" and args.sd_overlap),
                        "l2": "inputs larger than L2 (per-rank frames %.0f MB, activations several GB per micro-batch)"
                              % (2 * B_local * 3 * H * W * 4 / 1e6),
                        "parallelism": "batch-sharded x%d, no collective on the data path" % world},
@@ -415,7 +423,7 @@ def main():
                       "share_of_step": sum(us) / (ms_eager * 1e3), "traffic": traffic, "traffic_source": traffic_src,
                       "fp32_peak": {"idle": ffma_idle, "after_steps": ffma, "nominal": FP32_NOMINAL_TFLOPS,
                                     "source": "flowops_bench_ffma in this process, before the first step and after the timed steps"},
-                      "timed_in": "one eagerly launched step of the same workload (the timed steps replay these kernels from a CUDA graph)"}
+                      "timed_in": "one eagerly launched single-stream step of the same workload (the timed steps replay these kernels from a CUDA graph)"}
             if tc_on:
                 # tcgen05 kernel (csrc/corr_tc.cu).  `achieved` counts ALGORITHMIC flops; the tensor pipe executes
                 # 3 (3xTF32) x 1024/441 (dense 128 x 256 UMMA tiles around a banded contraction) = 6.97x as many.

@@ -229,6 +229,15 @@ int flowops_flownet2_prep_s2d(const float *inputs, const float *rgb_mean, float 
                               float *x_planar, float *xa_s2d, float *xb_s2d, float *x_nhwc8,
                               int B, int H, int W, void *stream);
 
+/* Either of the two above (s2d = 0 / 1) with the both-frames tensor at a wider channel pitch: x_packed is channels-last
+ * [B,H,W,packed_channels] (a multiple of 4, >= 8); the kernel writes channels 0..7 (six frame channels + two zeros) of
+ * every pixel and never touches the rest, which the CALLER zeroes once.  cuDNN's fused conv + bias + LeakyReLU engine
+ * for FlowNetSD's conv0 (FlowNetSD.py:18, 3x3, 6 -> 64) is 1.4x faster on a 16-channel input than on the 8-channel one
+ * (tools/conv_pad_probe.py: 678 vs 967 us per 16 pairs at 512 x 1024). */
+int flowops_flownet2_prep_pitched(const float *inputs, const float *rgb_mean, float rgb_max,
+                                  float *x_planar, float *xa, float *xb, float *x_packed, int packed_channels, int s2d,
+                                  int B, int H, int W, void *stream);
+
 /* ---- 16-bit storage variants (fp16 / bf16 in HBM, fp32 arithmetic) ----------------------------------------
  * The reference's fp16 mode is "fp16 storage, fp32 math" (flownet2_pytorch/main.py:59).  As run it reaches the
  * operators in three ways, and each entry point below reproduces exactly one of them in a single pass, with half the
@@ -303,9 +312,11 @@ int flowops_concat_nhwc(const float *src, float *dst, size_t n_pixels, int c_src
  * 2-channel flow [B, h, w, 2] (FlowNetS.py:46-49 `upsampled_flow6_to_5` ...; weight [2, 2, 4, 4] contiguous, bias [2] or
  * NULL) -- written into channels [c_off, c_off + 2) of the channels-last concat buffer dst [B, 2h, 2w, c_dst] (c_off, c_dst
  * even).  Replaces cuDNN's strided-dgrad launch with its channel-padding kernels, the bias pass and the copy into the
- * buffer. */
+ * buffer.  tail_zero (0, 2 or 6; needs c_off, c_dst multiples of 4): that many channels behind the flow are written as
+ * zeros in the same 16-byte stores -- the zero pad channels that end the buffer's pixel record, so that its last 32-byte
+ * sector is written whole instead of receiving an 8-byte partial write. */
 int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const float *bias, float *dst,
-                                int B, int h, int w, int c_dst, int c_off, void *stream);
+                                int B, int h, int w, int c_dst, int c_off, int tail_zero, void *stream);
 
 /* Epilogue of a ConvTranspose2d(kernel 4, stride 2, padding 1) + LeakyReLU (submodules.py:28-31 `deconv`) whose sums were
  * formed by a 3x3 convolution with 4*C output channels at the input resolution, one group of C per output parity
@@ -320,10 +331,12 @@ int flowops_bias_lrelu_d2s_nhwc_to(const float *y4, const float *bias, float *ds
  * torch.cat((skip, deconv(x), upsampled_flow(flow)), 1)): channels [c_off, c_off + C) as above and channels
  * [c_off + C, c_off + C + 2) = ConvTranspose2d(2, 2, 4, 2, 1)(flow) + flow_bias for the dense channels-last flow
  * [B, h, w, 2] at the input resolution, flow_weight [2, 2, 4, 4] contiguous, flow_bias [2] or NULL -- the arithmetic of
- * flowops_flow_deconv_nhwc_to, bit for bit. */
+ * flowops_flow_deconv_nhwc_to, bit for bit.  tail_zero (0, 2 or 6): that many channels behind the flow are written as
+ * zeros in the same 16-byte stores -- for the zero pad channels that end a concat buffer's pixel record, so that the
+ * record's last 32-byte sector is written whole (an 8-byte store into it costs a DRAM read-modify-write). */
 int flowops_bias_lrelu_d2s_flowup_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
                                           int c_dst, int c_off, float slope, const float *flow, const float *flow_weight,
-                                          const float *flow_bias, void *stream);
+                                          const float *flow_bias, int tail_zero, void *stream);
 
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 

@@ -231,7 +231,7 @@ __device__ __forceinline__ float2 flow_deconv_pixel(const float2 *__restrict__ i
 
 __global__ void __launch_bounds__(256) flow_deconv_nhwc_kernel(const float2 *__restrict__ in, const float *__restrict__ wgt,
                                                                const float *__restrict__ bias, float *__restrict__ dst,
-                                                               int B, int h, int w, unsigned c_dst, unsigned c_off)
+                                                               int B, int h, int w, unsigned c_dst, unsigned c_off, unsigned tail_zero)
 {
     __shared__ float sw[64];                      // [ci][co][ky][kx]
     if (threadIdx.x < 64) sw[threadIdx.x] = wgt[threadIdx.x];
@@ -243,25 +243,36 @@ __global__ void __launch_bounds__(256) flow_deconv_nhwc_kernel(const float2 *__r
         const int ox = (int)(i % W2);
         const size_t r = i / W2;
         const int oy = (int)(r % H2), b = (int)(r / H2);
-        *reinterpret_cast<float2 *>(dst + i * c_dst + c_off) = flow_deconv_pixel(in, sw, b0, b1, b, oy, ox, h, w);
+        const float2 f = flow_deconv_pixel(in, sw, b0, b1, b, oy, ox, h, w);
+        float *d = dst + i * c_dst + c_off;
+        if (tail_zero == 0) {
+            *reinterpret_cast<float2 *>(d) = f;
+        } else {                                  // whole sectors: see bias_lrelu_d2s_flowup_kernel
+            *reinterpret_cast<float4 *>(d) = make_float4(f.x, f.y, 0.f, 0.f);
+            if (tail_zero == 6) *reinterpret_cast<float4 *>(d + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
 }  // namespace flowops
 
 extern "C" int flowops_flow_deconv_nhwc_to(const float *flow, const float *weight, const float *bias, float *dst,
-                                           int B, int h, int w, int c_dst, int c_off, void *stream)
+                                           int B, int h, int w, int c_dst, int c_off, int tail_zero, void *stream)
 {
     FLOWOPS_REQUIRE(flow && weight && dst, FLOWOPS_EINVAL, "flow_deconv_nhwc_to: null pointer");
     FLOWOPS_REQUIRE(B > 0 && h > 0 && w > 0 && c_off >= 0 && c_off + 2 <= c_dst && ((c_off | c_dst) & 1) == 0, FLOWOPS_EINVAL,
                     "flow_deconv_nhwc_to: bad shape / channel range (%d, %d x %d, channels %d + 2 of %d; offsets must be even)", B, h, w, c_off, c_dst);
     FLOWOPS_REQUIRE((((uintptr_t)flow | (uintptr_t)dst) & 7) == 0, FLOWOPS_EINVAL, "flow_deconv_nhwc_to: 8-byte alignment required");
+    FLOWOPS_REQUIRE(tail_zero == 0 || ((tail_zero == 2 || tail_zero == 6) && c_off + 2 + tail_zero <= c_dst && ((c_off | c_dst) & 3) == 0 &&
+                                       aligned16(dst)), FLOWOPS_EINVAL,
+                    "flow_deconv_nhwc_to: tail_zero %d (0, or 2 / 6 zero channels behind the flow inside the %d channels, with c_off, c_dst "
+                    "multiples of 4 and a 16-byte aligned dst)", tail_zero, c_dst);
     const size_t total = (size_t)B * 4 * h * w;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)kNumSMs * 8 * 8;
     if (blocks > cap) blocks = cap;
     flow_deconv_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(flow), weight, bias, dst,
-                                                                                  B, h, w, (unsigned)c_dst, (unsigned)c_off);
+                                                                                  B, h, w, (unsigned)c_dst, (unsigned)c_off, (unsigned)tail_zero);
     return check_launch("flow_deconv_nhwc_to");
 }
 
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(256) bias_lrelu_d2s_flowup_kernel(const float4
                                                                     float *__restrict__ dst, size_t total_q, unsigned h, unsigned w,
                                                                     unsigned cq, unsigned c_dst, unsigned c_off, float slope,
                                                                     const float2 *__restrict__ flow, const float *__restrict__ fwgt,
-                                                                    const float *__restrict__ fbias)
+                                                                    const float *__restrict__ fbias, unsigned tail_zero)
 {
     __shared__ float sw[64];
     if (threadIdx.x < 64) sw[threadIdx.x] = fwgt[threadIdx.x];
@@ -357,7 +368,17 @@ __global__ void __launch_bounds__(256) bias_lrelu_d2s_flowup_kernel(const float4
             o.w = __fadd_rn(v.w, bb.w); o.w = o.w > 0.f ? o.w : __fmul_rn(o.w, slope);
             *reinterpret_cast<float4 *>(dst + pix * c_dst + c_off + 4 * q) = o;
         } else {
-            *reinterpret_cast<float2 *>(dst + pix * c_dst + c_off + 4 * cq) = flow_deconv_pixel(flow, sw, fb0, fb1, (int)b, (int)oy, (int)ox, (int)h, (int)w);
+            const float2 f = flow_deconv_pixel(flow, sw, fb0, fb1, (int)b, (int)oy, (int)ox, (int)h, (int)w);
+            float *d = dst + pix * c_dst + c_off + 4 * cq;
+            if (tail_zero == 0) {
+                *reinterpret_cast<float2 *>(d) = f;
+            } else {
+                // the zero pad channels behind the flow are (re)written with it: 16-byte stores that complete the pixel's last
+                // 32-byte sector instead of an 8-byte store into it -- L2 answers a partially written sector with a DRAM
+                // read-modify-write, which made the two flow channels cost as much as the 16 deconvolution channels
+                *reinterpret_cast<float4 *>(d) = make_float4(f.x, f.y, 0.f, 0.f);
+                if (tail_zero == 6) *reinterpret_cast<float4 *>(d + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
 }
@@ -366,19 +387,21 @@ __global__ void __launch_bounds__(256) bias_lrelu_d2s_flowup_kernel(const float4
 
 extern "C" int flowops_bias_lrelu_d2s_flowup_nhwc_to(const float *y4, const float *bias, float *dst, int B, int h, int w, int C,
                                                      int c_dst, int c_off, float slope, const float *flow, const float *flow_weight,
-                                                     const float *flow_bias, void *stream)
+                                                     const float *flow_bias, int tail_zero, void *stream)
 {
     FLOWOPS_REQUIRE(y4 && bias && dst && flow && flow_weight, FLOWOPS_EINVAL, "bias_lrelu_d2s_flowup_nhwc_to: null pointer");
     FLOWOPS_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && (C & 3) == 0 && c_off >= 0 && c_off + C + 2 <= c_dst && ((c_off | c_dst) & 3) == 0,
                     FLOWOPS_EINVAL, "bias_lrelu_d2s_flowup_nhwc_to: bad shape / channel range (C %d + 2, channels from %d of %d; multiples of 4)", C, c_off, c_dst);
     FLOWOPS_REQUIRE(aligned16(y4) && aligned16(dst) && aligned16(bias) && (((uintptr_t)flow) & 7) == 0, FLOWOPS_EINVAL,
                     "bias_lrelu_d2s_flowup_nhwc_to: 16-byte alignment required (8 for the flow)");
+    FLOWOPS_REQUIRE((tail_zero == 0 || tail_zero == 2 || tail_zero == 6) && c_off + C + 2 + tail_zero <= c_dst, FLOWOPS_EINVAL,
+                    "bias_lrelu_d2s_flowup_nhwc_to: tail_zero %d (0, 2 or 6 zero channels behind the flow, inside the %d channels)", tail_zero, c_dst);
     const size_t total_q = (size_t)B * h * w * 4 * (C / 4 + 1);
     size_t blocks = (total_q + 255) / 256;
     const size_t cap = (size_t)kNumSMs * 8 * 16;
     if (blocks > cap) blocks = cap;
     bias_lrelu_d2s_flowup_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(y4), bias, dst, total_q, (unsigned)h, (unsigned)w, (unsigned)(C / 4), (unsigned)c_dst, (unsigned)c_off,
-        slope, reinterpret_cast<const float2 *>(flow), flow_weight, flow_bias);
+        slope, reinterpret_cast<const float2 *>(flow), flow_weight, flow_bias, (unsigned)tail_zero);
     return check_launch("bias_lrelu_d2s_flowup_nhwc_to");
 }

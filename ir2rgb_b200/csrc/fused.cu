@@ -348,7 +348,7 @@ namespace flowops {
 template <bool S2D>
 __global__ void __launch_bounds__(256) flownet2_prep_kernel(const float *__restrict__ in, const float *__restrict__ mean, float inv_rgb_max,
                                                             float *__restrict__ xp, float4 *__restrict__ xa, float4 *__restrict__ xb,
-                                                            float4 *__restrict__ x8, unsigned hw, size_t total, unsigned W)
+                                                            float4 *__restrict__ x8, unsigned x8_quads, unsigned hw, size_t total, unsigned W)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / hw;
@@ -372,45 +372,59 @@ __global__ void __launch_bounds__(256) flownet2_prep_kernel(const float *__restr
         }
         if (xa) xa[ia] = make_float4(v[0], v[1], v[2], 0.f);
         if (xb) xb[ia] = make_float4(v[3], v[4], v[5], 0.f);
-        if (x8) { x8[2 * i] = make_float4(v[0], v[1], v[2], v[3]); x8[2 * i + 1] = make_float4(v[4], v[5], 0.f, 0.f); }
+        // x8_quads float4s per pixel: 2 = a dense 8-channel tensor; more = the first 8 channels of a wider, pre-zeroed one
+        if (x8) { x8[x8_quads * i] = make_float4(v[0], v[1], v[2], v[3]); x8[x8_quads * i + 1] = make_float4(v[4], v[5], 0.f, 0.f); }
     }
 }
 
 }  // namespace flowops
 
-extern "C" int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_max,
-                                     float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
-                                     int B, int H, int W, void *stream)
+static int flownet2_prep_launch(const char *what, bool s2d, const float *inputs, const float *rgb_mean, float rgb_max,
+                                float *x_planar, float *xa, float *xb, float *x_packed, int packed_channels,
+                                int B, int H, int W, void *stream)
 {
-    FLOWOPS_REQUIRE(inputs && rgb_mean, FLOWOPS_EINVAL, "flownet2_prep: null pointer");
-    FLOWOPS_REQUIRE(x_planar || xa_nhwc4 || xb_nhwc4 || x_nhwc8, FLOWOPS_EINVAL, "flownet2_prep: no output requested");
-    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (size_t)H * W < (1ull << 31), FLOWOPS_EINVAL, "flownet2_prep: bad shape %dx%dx%d", B, H, W);
-    FLOWOPS_REQUIRE(aligned16(xa_nhwc4) && aligned16(xb_nhwc4) && aligned16(x_nhwc8), FLOWOPS_EINVAL, "flownet2_prep: outputs must be 16-byte aligned");
+    FLOWOPS_REQUIRE(inputs && rgb_mean, FLOWOPS_EINVAL, "%s: null pointer", what);
+    FLOWOPS_REQUIRE(x_planar || xa || xb || x_packed, FLOWOPS_EINVAL, "%s: no output requested", what);
+    FLOWOPS_REQUIRE(!s2d || (xa && xb), FLOWOPS_EINVAL, "%s: null pointer", what);
+    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (size_t)H * W < (1ull << 31), FLOWOPS_EINVAL, "%s: bad shape %dx%dx%d", what, B, H, W);
+    FLOWOPS_REQUIRE(!s2d || ((H & 1) == 0 && (W & 1) == 0), FLOWOPS_EINVAL, "%s: bad shape %dx%dx%d (H, W must be even)", what, B, H, W);
+    FLOWOPS_REQUIRE(packed_channels >= 8 && packed_channels % 4 == 0, FLOWOPS_EINVAL, "%s: packed_channels %d (a multiple of 4, >= 8)",
+                    what, packed_channels);
+    FLOWOPS_REQUIRE(aligned16(xa) && aligned16(xb) && aligned16(x_packed), FLOWOPS_EINVAL, "%s: outputs must be 16-byte aligned", what);
     const size_t total = (size_t)B * H * W;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)kNumSMs * 8 * 16;
     if (blocks > cap) blocks = cap;
     // tensor / python-scalar on CUDA is tensor * (1.0f / scalar) in ATen; reproduced so that x matches models.py:98 bit for bit
-    flownet2_prep_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
-        reinterpret_cast<float4 *>(xa_nhwc4), reinterpret_cast<float4 *>(xb_nhwc4), reinterpret_cast<float4 *>(x_nhwc8),
-        (unsigned)((size_t)H * W), total, (unsigned)W);
-    return check_launch("flownet2_prep");
+    if (s2d)
+        flownet2_prep_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
+            reinterpret_cast<float4 *>(xa), reinterpret_cast<float4 *>(xb), reinterpret_cast<float4 *>(x_packed),
+            (unsigned)packed_channels / 4, (unsigned)((size_t)H * W), total, (unsigned)W);
+    else
+        flownet2_prep_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
+            reinterpret_cast<float4 *>(xa), reinterpret_cast<float4 *>(xb), reinterpret_cast<float4 *>(x_packed),
+            (unsigned)packed_channels / 4, (unsigned)((size_t)H * W), total, (unsigned)W);
+    return check_launch(what);
+}
+
+extern "C" int flowops_flownet2_prep(const float *inputs, const float *rgb_mean, float rgb_max,
+                                     float *x_planar, float *xa_nhwc4, float *xb_nhwc4, float *x_nhwc8,
+                                     int B, int H, int W, void *stream)
+{
+    return flownet2_prep_launch("flownet2_prep", false, inputs, rgb_mean, rgb_max, x_planar, xa_nhwc4, xb_nhwc4, x_nhwc8, 8, B, H, W, stream);
 }
 
 extern "C" int flowops_flownet2_prep_s2d(const float *inputs, const float *rgb_mean, float rgb_max,
                                          float *x_planar, float *xa_s2d, float *xb_s2d, float *x_nhwc8,
                                          int B, int H, int W, void *stream)
 {
-    FLOWOPS_REQUIRE(inputs && rgb_mean && xa_s2d && xb_s2d, FLOWOPS_EINVAL, "flownet2_prep_s2d: null pointer");
-    FLOWOPS_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0 && (size_t)H * W < (1ull << 31), FLOWOPS_EINVAL,
-                    "flownet2_prep_s2d: bad shape %dx%dx%d (H, W must be even)", B, H, W);
-    FLOWOPS_REQUIRE(aligned16(xa_s2d) && aligned16(xb_s2d) && aligned16(x_nhwc8), FLOWOPS_EINVAL, "flownet2_prep_s2d: outputs must be 16-byte aligned");
-    const size_t total = (size_t)B * H * W;
-    size_t blocks = (total + 255) / 256;
-    const size_t cap = (size_t)kNumSMs * 8 * 16;
-    if (blocks > cap) blocks = cap;
-    flownet2_prep_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inputs, rgb_mean, 1.0f / rgb_max, x_planar,
-        reinterpret_cast<float4 *>(xa_s2d), reinterpret_cast<float4 *>(xb_s2d), reinterpret_cast<float4 *>(x_nhwc8),
-        (unsigned)((size_t)H * W), total, (unsigned)W);
-    return check_launch("flownet2_prep_s2d");
+    return flownet2_prep_launch("flownet2_prep_s2d", true, inputs, rgb_mean, rgb_max, x_planar, xa_s2d, xb_s2d, x_nhwc8, 8, B, H, W, stream);
+}
+
+extern "C" int flowops_flownet2_prep_pitched(const float *inputs, const float *rgb_mean, float rgb_max,
+                                             float *x_planar, float *xa, float *xb, float *x_packed, int packed_channels, int s2d,
+                                             int B, int H, int W, void *stream)
+{
+    return flownet2_prep_launch("flownet2_prep_pitched", s2d != 0, inputs, rgb_mean, rgb_max, x_planar, xa, xb, x_packed, packed_channels,
+                                B, H, W, stream);
 }

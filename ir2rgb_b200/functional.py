@@ -7,6 +7,7 @@ fp16 / bf16 tensors and then run the library's "16-bit storage, fp32 math" entry
 reproduce what the reference's fp16 mode computes (include/flowops.h).
 """
 import ctypes
+import os
 
 import torch
 
@@ -272,10 +273,26 @@ def flownet2_fusion_input(x, flow2_s2, flow2_sd, div_flow, c_pad=16):
     return out
 
 
-def flownet2_prep(inputs, rgb_mean, rgb_max):
+_PREP_CACHE = {}
+
+
+def _prep_packed(B, H, W, device, channels):
+    """The both-frames channels_last tensor FlowNetSD's conv0 reads.  8 channels: a fresh dense tensor, written whole by
+    the kernel.  More: the kernel writes channels 0..7 only, so the tensor is allocated and zeroed once per shape and
+    device and REUSED by later calls (like the space-to-depth frames below)."""
+    cl = dict(device=device, dtype=torch.float32, memory_format=torch.channels_last)
+    if channels == 8:
+        return torch.empty((B, 8, H, W), **cl)
+    key = ("packed", B, H, W, device, channels)
+    if key not in _PREP_CACHE:
+        _PREP_CACHE[key] = torch.empty((B, channels, H, W), **cl).zero_()
+    return _PREP_CACHE[key]
+
+
+def flownet2_prep(inputs, rgb_mean, rgb_max, sd_channels=8):
     """x = (inputs - rgb_mean) / rgb_max for inputs [B,3,2,H,W] (models.py:97-101), in the four layouts its consumers
-    read: (x planar [B,6,H,W], frame 0 and frame 1 as channels_last [B,4,H,W], both frames as channels_last [B,8,H,W]);
-    the extra channels are zero."""
+    read: (x planar [B,6,H,W], frame 0 and frame 1 as channels_last [B,4,H,W], both frames as channels_last
+    [B,sd_channels,H,W]); the extra channels are zero.  sd_channels > 8: see _prep_packed (a cached, reused tensor)."""
     inputs = _require(inputs, "inputs", ndim=5).contiguous()
     B, C, F2, H, W = inputs.shape
     if C != 3 or F2 != 2:
@@ -284,17 +301,15 @@ def flownet2_prep(inputs, rgb_mean, rgb_max):
     with torch.cuda.device_of(inputs):
         cl = dict(device=inputs.device, dtype=torch.float32, memory_format=torch.channels_last)
         x = torch.empty((B, 6, H, W), device=inputs.device, dtype=torch.float32)
-        xa, xb, x8 = torch.empty((B, 4, H, W), **cl), torch.empty((B, 4, H, W), **cl), torch.empty((B, 8, H, W), **cl)
+        xa, xb = torch.empty((B, 4, H, W), **cl), torch.empty((B, 4, H, W), **cl)
+        x8 = _prep_packed(B, H, W, inputs.device, sd_channels)
         if inputs.numel():
-            check(_lib.load().flowops_flownet2_prep(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb), _p(x8),
-                                                    B, H, W, _stream()), "flownet2_prep")
+            check(_lib.load().flowops_flownet2_prep_pitched(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb),
+                                                            _p(x8), sd_channels, 0, B, H, W, _stream()), "flownet2_prep")
     return x, xa, xb, x8
 
 
-_S2D_CACHE = {}
-
-
-def flownet2_prep_s2d(inputs, rgb_mean, rgb_max):
+def flownet2_prep_s2d(inputs, rgb_mean, rgb_max, sd_channels=8):
     """flownet2_prep with the two frames in the space-to-depth layout FlowNetC's first layer reads on the fast path
     (include/flowops.h): returns (x planar, xa_s2d, xb_s2d, x8).  The s2d tensors are [B, 16, H/2+1, W/2+1] channels_last
     with a zero first row / column; they are allocated (and zeroed) once per shape and device and REUSED by later calls."""
@@ -305,14 +320,14 @@ def flownet2_prep_s2d(inputs, rgb_mean, rgb_max):
     rgb_mean = rgb_mean.reshape(B, 3).contiguous()
     with torch.cuda.device_of(inputs):
         cl = dict(device=inputs.device, dtype=torch.float32, memory_format=torch.channels_last)
-        key = (B, H, W, inputs.device)
-        if key not in _S2D_CACHE:
-            _S2D_CACHE[key] = tuple(torch.empty((B, 16, H // 2 + 1, W // 2 + 1), **cl).zero_() for _ in range(2))
-        xa, xb = _S2D_CACHE[key]
+        key = ("s2d", B, H, W, inputs.device)
+        if key not in _PREP_CACHE:
+            _PREP_CACHE[key] = tuple(torch.empty((B, 16, H // 2 + 1, W // 2 + 1), **cl).zero_() for _ in range(2))
+        xa, xb = _PREP_CACHE[key]
         x = torch.empty((B, 6, H, W), device=inputs.device, dtype=torch.float32)
-        x8 = torch.empty((B, 8, H, W), **cl)
-        check(_lib.load().flowops_flownet2_prep_s2d(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb), _p(x8),
-                                                    B, H, W, _stream()), "flownet2_prep_s2d")
+        x8 = _prep_packed(B, H, W, inputs.device, sd_channels)
+        check(_lib.load().flowops_flownet2_prep_pitched(_p(inputs), _p(rgb_mean), ctypes.c_float(rgb_max), _p(x), _p(xa), _p(xb),
+                                                        _p(x8), sd_channels, 1, B, H, W, _stream()), "flownet2_prep_s2d")
     return x, xa, xb, x8
 
 
@@ -357,6 +372,9 @@ def _cat_fast(tensors):
             all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4
                 and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:] and t.device == t0.device and _is_nhwc(t)
                 for t in tensors))
+
+
+D2S_WRITE_PAD = os.environ.get("FLOWOPS_D2S_WRITE_PAD", "1") != "0"      # A/B switch of ConcatBuffer.bias_lrelu_d2s_in's tail write
 
 
 class ConcatBuffer:
@@ -410,8 +428,14 @@ class ConcatBuffer:
         B, _, h, w = flow.shape
         with torch.cuda.device_of(flow):
             check(_lib.load().flowops_flow_deconv_nhwc_to(_p(flow), _p(weight), _p(bias), _p(self.tensor), B, h, w, self.c_pad, c_off,
-                                                          _stream()), "flow_deconv_nhwc_to")
+                                                          self._pad_tail(c_off + 2, c_off), _stream()), "flow_deconv_nhwc_to")
         return c_off + 2
+
+    def _pad_tail(self, c_end, c_off):
+        """How many of the buffer's zero pad channels a 2-channel flow slice ending at channel c_end rewrites with it (2 or 6:
+        whole 16-byte stores that complete the pixel record's last sector, include/flowops.h), or 0."""
+        tail = self.c_pad - self.c_total if (D2S_WRITE_PAD and c_end == self.c_total and c_off % 4 == 0 and self.c_pad % 4 == 0) else 0
+        return tail if tail in (2, 6) else 0
 
     def bias_lrelu_d2s_in(self, y4, bias, slope, c_off, flow_up=None):
         """dst[b, 2m+py, 2n+px, c_off + co] = LeakyReLU(y4[b, m, n, (py*2+px)*C + co] + bias[co]): the epilogue of a k4 s2 p1
@@ -428,8 +452,11 @@ class ConcatBuffer:
             flow, fw, fb = flow_up
             if tuple(flow.shape) != (B, 2, h, w):
                 raise ValueError("bias_lrelu_d2s_in: the flow must be [B, 2, h, w] at the deconvolution's input resolution")
+            # the slice ends the buffer's real channels: its zero pad channels are rewritten together with the flow, which
+            # completes the pixel record's last sector (include/flowops.h)
+            tail = self._pad_tail(c_off + C4 // 4 + 2, c_off)
             check(_lib.load().flowops_bias_lrelu_d2s_flowup_nhwc_to(_p(y4), _p(bias), _p(self.tensor), B, h, w, C4 // 4, self.c_pad, c_off,
-                                                                    ctypes.c_float(slope), _p(flow), _p(fw), _p(fb), _stream()),
+                                                                    ctypes.c_float(slope), _p(flow), _p(fw), _p(fb), tail, _stream()),
                   "bias_lrelu_d2s_flowup_nhwc_to")
         return c_off + C4 // 4 + 2
 

@@ -30,6 +30,9 @@ class MyDict(dict):
     pass
 
 
+_SD_STREAMS = {}      # device index -> the stream FlowNetSD runs on beside FlowNetC -> S -> S (FlowNet2._forward_fused)
+
+
 class fp16_resample2d(nn.Module):
     def __init__(self):
         super(fp16_resample2d, self).__init__()
@@ -61,6 +64,10 @@ class FlowNet2(nn.Module):
         self.fuse_fusion_input = True  # channels_last body: concat3 (models.py:129-152) from one kernel
         self.fuse_upsample = True      # channels_last body: the x4 bilinear upsamplings folded into the concat kernels
         self.s2d_conv1 = True          # channels_last body, TF32 convolutions: FlowNetC.conv1 on space-to-depth frames
+        self.sd_pad16 = True           # channels_last body, TF32 convolutions: FlowNetSD.conv0 reads a 16-channel tensor
+        self.overlap_sd = False        # channels_last body: FlowNetSD (models.py:141-142) on a second stream beside C -> S -> S
+                                       # (optional: measured, no gain on one B200 -- 639 pairs/s either way)
+        self._sd_warm = set()          # (device, shape) pairs whose first (serial, plan-building) forward has run
 
         self.channelnorm = ChannelNorm()
         self.flownetc = FlowNetC.FlowNetC(args, batchNorm=self.batchNorm)
@@ -94,15 +101,38 @@ class FlowNet2(nn.Module):
         tensors between the sub-networks produced directly in the layout and channel count their consumers read --
         no torch.cat, no slice copies, no NCHW<->NHWC conversions, no cuDNN channel re-padding."""
         rgb_mean = inputs.contiguous().view(inputs.size()[:2] + (-1,)).mean(dim=-1)
+        # FlowNetSD.conv0 (3x3, 6 -> 64 at full resolution): cuDNN's fused conv + bias + LeakyReLU engine takes 967 us per 16
+        # pairs on the frame stack padded to 8 channels and 678 us on the same stack padded to 16 (tools/conv_pad_probe.py);
+        # the extra zero channels add exact zeros.  Only with TF32 convolutions, where the fused engines run at all.
+        sd_c = 16 if self.sd_pad16 and torch.backends.cudnn.allow_tf32 else 8
         if self.s2d_conv1 and torch.backends.cudnn.allow_tf32 and inputs.shape[3] % 2 == 0 and inputs.shape[4] % 2 == 0:
             # FlowNetC's first layer on the space-to-depth frames: a 16-channel 4x4 convolution instead of a 3(4)-channel
             # 7x7 stride-2 one, which cuDNN runs on a pre-Blackwell kernel without shared-memory staging (4.8 % of the
             # step).  Same sums in another order: on when TF32 convolutions are (the bit-exact path otherwise).
-            x, xa, xb, x8 = _F.flownet2_prep_s2d(inputs, rgb_mean, float(self.rgb_max))
+            x, xa, xb, x8 = _F.flownet2_prep_s2d(inputs, rgb_mean, float(self.rgb_max), sd_c)
             frames = (xa, xb, "s2d")
         else:
-            x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max))
+            x, xa, xb, x8 = _F.flownet2_prep(inputs, rgb_mean, float(self.rgb_max), sd_c)
             frames = (xa, xb)
+
+        # FlowNetSD reads only the frame stack (models.py:141-142), so it can run beside FlowNetC -> S1 -> S2: forked onto a
+        # second stream here, joined in front of the fusion-network input.  Inside a CUDA graph the two chains become
+        # parallel branches, and the sub-networks' low-resolution layers (grids of 32 .. 256 CTAs on 148 SMs) can fill each
+        # other's idle SMs.  Off by default (no measurable gain: the step is power- and bandwidth-bound, not occupancy-bound).
+        # The first forward of a shape stays serial: cuDNN autotuning and the fused-plan timings of
+        # networks/submodules.py run there and must not be disturbed by a concurrent stream.
+        key = (x.device.index, tuple(inputs.shape), bool(torch.backends.cudnn.allow_tf32), bool(torch.backends.cudnn.benchmark))
+        fork = self.overlap_sd and key in self._sd_warm
+        self._sd_warm.add(key)
+        main = torch.cuda.current_stream(x.device)
+        if fork:
+            side = _SD_STREAMS.get(x.device.index)
+            if side is None:
+                side = _SD_STREAMS[x.device.index] = torch.cuda.Stream(device=x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                flow2_sd = self.flownets_d(x8)[0]
+            x8.record_stream(side)
 
         flow2_c = self.flownetc(x, frames=frames)[0]
         if self.fuse_upsample and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
@@ -114,7 +144,11 @@ class FlowNet2(nn.Module):
             flownets1_flow = self.upsample2(self.flownets_1(concat1)[0] * self.div_flow)
             concat2 = _F.warp_diff_norm_concat(x, flownets1_flow, self.div_flow)
         flow2_s2 = self.flownets_2(concat2)[0]
-        flow2_sd = self.flownets_d(x8)[0]
+        if fork:
+            main.wait_stream(side)
+            flow2_sd.record_stream(main)
+        else:
+            flow2_sd = self.flownets_d(x8)[0]
         if self.fuse_fusion_input and _sm.PAD_CHANNELS > 1 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
             # scalings, nearest upsamplings, both ChannelNorms, both warp-error chains and the concat of models.py:129-152
             # as one kernel writing the 16-channel channels-last tensor conv0 of the fusion network reads

@@ -54,6 +54,8 @@ def reset_padded_weights(net):
     for m in net.modules():
         for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
             m.__dict__.pop(k, None)
+        if isinstance(m.__dict__.get("_sd_warm"), set):
+            m._sd_warm.clear()
 
 
 CACHE_CONCAT_BUFFERS = True      # inference: one concat buffer per place and shape, reused across forwards

@@ -50,6 +50,8 @@ class GraphedFlowNet(torch.nn.Module):
         for m in self.net.modules():
             for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
                 m.__dict__.pop(k, None)
+            if isinstance(m.__dict__.get("_sd_warm"), set):
+                m._sd_warm.clear()                     # FlowNet2: the next forward builds its plans serially again
 
     @torch.no_grad()
     def forward(self, input_A, input_B):

@@ -129,3 +129,38 @@ def test_reference_class_arm_makes_no_libflowops_call():
     finally:
         _lib.launch_hook = prev
     assert calls == [], calls
+
+
+def test_sd_branch_on_second_stream_changes_nothing(bench_net):
+    """FlowNetSD forked onto a second stream beside FlowNetC -> S -> S (FlowNet2.overlap_sd; reference models.py:141-142
+    is independent of :104-137): the same kernels in another schedule, so flow and confidence must be bit-identical to
+    the in-line order -- launched eagerly and replayed from the CUDA graph.  (Only the captured graphs are dropped
+    between the two settings: the per-layer plan choices made by timing must stay the same on both sides.)"""
+    eager, graphed = bench_net
+    fn = eager.flowNet
+    im1, im2 = _frames(2, 13)
+    prev = fn.overlap_sd
+    try:
+        graphed.reset()
+        fn.overlap_sd = False
+        with torch.no_grad():
+            eager(im1, im2)                               # builds every plan of this shape
+            f_serial, c_serial = eager(im1, im2)
+            f_serial_g, c_serial_g = graphed(im1, im2)
+        fn.overlap_sd = True
+        graphed._graphs.clear()
+        with torch.no_grad():
+            assert any(k[:2] == (im1.device.index, (2, 3, 2, H, W)) for k in fn._sd_warm)     # so the next forward forks
+            f_fork, c_fork = eager(im1, im2)
+            f_fork_g, c_fork_g = graphed(im1, im2)        # parallel branches inside the graph
+            im1b, im2b = _frames(2, 14)
+            f_fork_g2, c_fork_g2 = graphed(im1b, im2b)    # replay with other contents
+            f_fork_2, c_fork_2 = eager(im1b, im2b)
+        torch.cuda.synchronize()
+    finally:
+        fn.overlap_sd = prev
+        graphed.reset()
+    assert torch.isfinite(f_fork).all()
+    assert torch.equal(f_serial, f_fork) and torch.equal(c_serial, c_fork)
+    assert torch.equal(f_serial_g, f_fork_g) and torch.equal(c_serial_g, c_fork_g)
+    assert torch.equal(f_fork_g2, f_fork_2) and torch.equal(c_fork_g2, c_fork_2)

@@ -125,6 +125,30 @@ def test_input_prep_and_concat_assembly_are_bit_identical(nets):
     assert torch.equal(cat[:, :12], want) and (cat[:, 12:] == 0).all()
 
 
+@pytest.mark.parametrize("s2d", [False, True])
+def test_input_prep_at_a_16_channel_pitch(nets, s2d):
+    """flowops_flownet2_prep_pitched: the both-frames tensor FlowNetSD.conv0 reads, as the first 8 channels of a cached,
+    pre-zeroed 16-channel channels_last tensor (the rest is never written) -- same values as the dense 8-channel form,
+    also on the second call, which reuses the tensor."""
+    from ir2rgb_b200 import functional as F
+    prep = F.flownet2_prep_s2d if s2d else F.flownet2_prep
+    B, H, W = 2, 64, 96
+    ptr = None
+    for seed in (1, 2):
+        torch.manual_seed(seed)
+        inputs = 2 * torch.rand(B, 3, 2, H, W, device="cuda") - 1
+        mean = inputs.view(B, 3, -1).mean(dim=-1)
+        x, xa, xb, x8 = prep(inputs, mean, 255.0, 8)
+        x2, xa2, xb2, x16 = prep(inputs, mean, 255.0, 16)
+        assert x16.shape == (B, 16, H, W) and x16.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(x, x2) and torch.equal(xa, xa2) and torch.equal(xb, xb2)
+        assert torch.equal(x16[:, :8], x8) and (x16[:, 8:] == 0).all()
+        assert ptr in (None, x16.data_ptr())              # one tensor per shape and device
+        ptr = x16.data_ptr()
+    with pytest.raises(Exception):
+        prep(inputs, mean, 255.0, 6)                      # a multiple of 4, >= 8
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 128, 320), (3, 8, 12)])
 def test_fusion_input_is_bit_identical_to_operator_chain(nets, shape):
     """flowops_flownet2_fusion_input_nhwc against models.py:129-152 spelled out with the separate operators."""
@@ -473,3 +497,43 @@ def test_depth_to_space_epilogue_with_the_flow_upsampler_folded_in(flowops_lib, 
     assert torch.equal(one.tensor, sep.tensor)
     assert ((one.tensor[:, 8 + cout:10 + cout] - want_up).abs().max() / want_up.abs().max()).item() <= 1e-6
     assert (one.tensor[:, :8] == 5.0).all() and (one.tensor[:, 10 + cout:] == 5.0).all()
+
+
+@pytest.mark.parametrize("cout,tail", [(16, 6), (20, 2), (8, 6)])
+def test_flow_slice_that_ends_the_record_rewrites_the_pad_channels(flowops_lib, cout, tail):
+    """A 2-channel flow slice that ends a concat buffer's real channels is written together with the buffer's zero pad
+    channels (tail_zero of flowops_flow_deconv_nhwc_to / flowops_bias_lrelu_d2s_flowup_nhwc_to: whole 16-byte stores, whole
+    sectors): every real channel is bit-identical to the 8-byte-store form, the pad channels are (still) zero, and the
+    channels in front of the slice are untouched."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(43)
+    h, w, cin = 12, 20, 24
+    conv = torch.nn.ConvTranspose2d(cin, cout, 4, 2, 1).cuda().to(memory_format=torch.channels_last)
+    up = torch.nn.ConvTranspose2d(2, 2, 4, 2, 1).cuda()
+    x = torch.randn(2, cin, h, w, device="cuda").contiguous(memory_format=torch.channels_last)
+    flow = (3 * torch.randn(2, 2, h, w, device="cuda")).contiguous(memory_format=torch.channels_last)
+    c_total = 8 + cout + 2
+    results = {}
+    prev = F.D2S_WRITE_PAD
+    try:
+        with torch.no_grad():
+            y4 = torch.nn.functional.conv2d(x, sm.deconv_as_conv3_weight(conv, conv.weight), None, 1, 1)
+            fw = up.weight.detach().contiguous()
+            for mode in (False, True):
+                F.D2S_WRITE_PAD = mode
+                one = F.ConcatBuffer(x, c_total, 8, shape=(2, 2 * h, 2 * w))
+                assert one.c_pad - one.c_total == tail and one._pad_tail(c_total, 8 + cout) == (tail if mode else 0)
+                one.tensor[:, :8] = 5.0
+                one.bias_lrelu_d2s_in(y4, conv.bias, 0.1, 8, (flow, fw, up.bias))
+                two = F.ConcatBuffer(x, c_total, 8, shape=(2, 2 * h, 2 * w))
+                two.tensor[:, :8] = 5.0
+                two.bias_lrelu_d2s_in(y4, conv.bias, 0.1, 8)
+                two.flow_deconv_in(flow, fw, up.bias, 8 + cout)
+                results[mode] = (one.tensor.clone(), two.tensor.clone())
+    finally:
+        F.D2S_WRITE_PAD = prev
+    ref = results[False][0]
+    assert (ref[:, :8] == 5.0).all() and (ref[:, c_total:] == 0).all()
+    for t in (results[False][1], results[True][0], results[True][1]):
+        assert torch.equal(t, ref)

@@ -338,6 +338,17 @@ int flowops_bias_lrelu_d2s_flowup_nhwc_to(const float *y4, const float *bias, fl
                                           int c_dst, int c_off, float slope, const float *flow, const float *flow_weight,
                                           const float *flow_bias, int tail_zero, void *stream);
 
+/* The decoders' flow heads -- predict_flow = nn.Conv2d(C, 2, kernel_size 3, stride 1, padding 1) (networks/submodules.py:40-41;
+ * FlowNetS.py:36-40, FlowNetFusion.py:32-34, ...) -- as one direct FP32 convolution with the bias included:
+ *   out[b, y, x, co] = bias[co] + sum_{dy, dx, c < cin} x[b, y+dy-1, x+dx-1, c] * w[co, c, dy, dx]        (zero padding)
+ * x: channels-last [B, H, W, c_pitch], of which the first cin channels are read (cin, c_pitch multiples of 4; the weights of
+ * zero pad channels are zero); out: channels-last [B, H, W, 2], dense; bias [2] or NULL.  w_packed: the filter in the order the
+ * kernel reads it, [ceil(cin / 16)][dy * 3 + dx][(c % 16) / 4][c % 4][co], zero beyond the layer's real channels
+ * (ir2rgb_b200.functional.pack_flow_head_weight).  FP32 multiply-adds (FFMA2), i.e. more exact than the TF32 convolution it
+ * stands in for; replaces cuDNN's convolution + its two filter / output channel-padding kernels + the bias pass. */
+int flowops_flow_head_nhwc(const float *x, int c_pitch, int cin, const float *w_packed, const float *bias, float *out,
+                           int B, int H, int W, void *stream);
+
 /* ---- Measurement helper (not part of the reference surface) -------------------------------- */
 
 /* Launches a register-resident FFMA chain kernel on every SM: `iters` loop trips of 64 independent

@@ -57,6 +57,7 @@ SIGNATURES = {
     "flowops_fill_channels_nhwc": (_int, [_vp, _sz, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_bias_lrelu_d2s_nhwc_to": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, ctypes.c_float, _vp]),
     "flowops_bias_lrelu_d2s_flowup_nhwc_to": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, ctypes.c_float, _vp, _vp, _vp, _int, _vp]),
+    "flowops_flow_head_nhwc": (_int, [_vp, _int, _int, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "flowops_flow_deconv_nhwc_to": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _vp]),
     "flowops_concat_nhwc": (_int, [_vp, _vp, _sz, _int, _int, _int, _vp]),
     "flowops_bench_ffma": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), _vp]),

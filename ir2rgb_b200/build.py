@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libflowops.so")
-SOURCES = ["api.cu", "cnorm.cu", "warp.cu", "warp16.cu", "corr.cu", "corr_generic.cu", "corr_fast.cu", "corr_tc.cu", "corr_tc_bwd.cu", "corr_bwd.cu", "fused.cu", "epilogue.cu"]
+SOURCES = ["api.cu", "cnorm.cu", "warp.cu", "warp16.cu", "corr.cu", "corr_generic.cu", "corr_fast.cu", "corr_tc.cu", "corr_tc_bwd.cu", "corr_bwd.cu", "fused.cu", "epilogue.cu", "flowhead.cu"]
 HEADERS = ["common.cuh", "io16.cuh", "corr.cuh", "warp.cuh", "warp_rows.cuh", "warp_rows_bwd.cuh", "warp_win_bwd.cuh", "warp_fx_bwd.cuh", "tma.cuh", "tc.cuh", os.path.join("..", "..", "include", "flowops.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

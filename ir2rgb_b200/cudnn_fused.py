@@ -20,6 +20,8 @@ ENABLED = True
 MIN_OUT_ELEMENTS = 1 << 22      # smaller layers: the epilogue pass is launch-latency sized and plan building is not worth it
 _handles = {}
 _cache = {}
+_errors = {}         # key -> why no fused plan could be built
+_rejected = {}       # key -> (ms fused, ms two kernels) of the layers where the fused plan lost
 
 
 def available():
@@ -135,9 +137,11 @@ def conv_bias_lrelu(conv, x, w, slope, out=None, unfused=None, after=None):
         try:
             plan = _Plan(x, w, conv.bias, y, conv.stride, conv.padding, conv.dilation, slope, handle, unfused, after)
             if not plan.wins:
+                _rejected[key] = (plan.ms, plan.ms_unfused)
                 plan = False
-        except Exception:
+        except Exception as e:
             plan = False                               # no engine for this layer: remember, use the unfused path
+            _errors[key] = repr(e)[:200]
         _cache[key] = plan
     if plan is False:
         return NotImplemented
@@ -145,6 +149,25 @@ def conv_bias_lrelu(conv, x, w, slope, out=None, unfused=None, after=None):
     return y
 
 
+def report():
+    """One record per layer seen so far: shapes, the best fused plan's time, the two-kernel time it was measured against, and
+    which of the two runs (tools/step_probe.py prints it)."""
+    out = []
+    for key, plan in _cache.items():
+        rec = {"x": list(key[1]), "w": list(key[3]), "y": list(key[5]), "stride": list(key[7]), "slope": key[10],
+               "fused": bool(plan)}
+        if key in _rejected:
+            rec.update(us_fused=round(_rejected[key][0] / 3 * 1e3, 1), us_two_kernels=round(_rejected[key][1] / 3 * 1e3, 1))
+        if key in _errors:
+            rec["error"] = _errors[key]
+        if plan:
+            rec.update(us_fused=round(plan.ms / 3 * 1e3, 1), us_two_kernels=None if plan.ms_unfused is None else round(plan.ms_unfused / 3 * 1e3, 1))
+        out.append(rec)
+    return out
+
+
 def reset():
     _cache.clear()
+    _rejected.clear()
+    _errors.clear()
 

@@ -347,6 +347,35 @@ def warp_conf_forward(im1, im2, flow, thresh=0.02, mode=WARP_GRIDSAMPLE):
     return conf
 
 
+def pack_flow_head_weight(weight, cin):
+    """The [2, C, 3, 3] filter of a flow head (C <= cin) in the order flowops_flow_head_nhwc reads it:
+    [ceil(cin / 16)][dy * 3 + dx][(c % 16) / 4][c % 4][co], zero for c >= C (include/flowops.h)."""
+    co, c, kh, kw = weight.shape
+    if co != 2 or kh != 3 or kw != 3 or c > cin:
+        raise ValueError("pack_flow_head_weight: expected a [2, C <= %d, 3, 3] filter, got %s" % (cin, tuple(weight.shape)))
+    n_chunks = -(-cin // 16)
+    wp = weight.new_zeros(n_chunks * 16, 9, 2)                       # [c][tap][co]
+    wp[:c] = weight.detach().float().reshape(2, c, 9).permute(1, 2, 0)
+    return wp.view(n_chunks, 4, 4, 9, 2).permute(0, 3, 1, 2, 4).contiguous()      # [chunk][tap][quad][ch][co]
+
+
+def flow_head(x, w_packed, bias):
+    """conv2d(x, w, bias, stride 1, padding 1) for a 2-filter 3x3 layer on a channels_last (view) x, as one FP32 kernel
+    (flowops_flow_head_nhwc); w_packed from pack_flow_head_weight(w, C_x).  Returns channels_last [B, 2, H, W]."""
+    x = _require(x, "x")
+    if not (_is_nhwc_view(x) or (x.dim() == 4 and x.shape[1] == 1 and x.is_contiguous())):
+        raise ValueError("flow_head: x must be channels_last (or a channel slice of a channels_last tensor)")
+    B, C, H, W = x.shape
+    if C % 4 or x.stride(3) % 4 or w_packed.numel() != -(-C // 16) * 288:
+        raise ValueError("flow_head: channel count %d / pitch %d must be multiples of 4 and match the packed filter" % (C, x.stride(3)))
+    with torch.cuda.device_of(x):
+        out = torch.empty((B, 2, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if out.numel():
+            check(_lib.load().flowops_flow_head_nhwc(_p(x), x.stride(3), C, _p(w_packed), _p(bias), _p(out), B, H, W, _stream()),
+                  "flow_head_nhwc")
+    return out
+
+
 def bias_lrelu_(y, bias, slope):
     """In-place per-channel bias add + LeakyReLU on a conv output (NCHW- or channels_last-contiguous)."""
     y = _require(y, "y")

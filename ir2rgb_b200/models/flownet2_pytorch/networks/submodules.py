@@ -5,6 +5,8 @@ restated here only because BASELINE config 4 (FlowNet2 frame pairs/s) needs the 
 three custom operators.  nn.Sequential indices are kept (``conv1.0.weight`` ...) so that a FlowNet2
 checkpoint of the reference loads unchanged.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -48,11 +50,41 @@ def padded_weight(conv, cin):
     return cache[1]
 
 
+FLOW_HEAD_KERNEL = os.environ.get("FLOWOPS_FLOW_HEAD", "1") != "0"      # inference, TF32 convolutions allowed: predict_flow layers
+                                                                      # through flowops_flow_head_nhwc (the variable: A/B timing)
+
+
+# The kernel wins where the head is bandwidth-bound -- the fusion network's full- and half-resolution heads (16 / 32 channels:
+# 200 vs 387 us and 108 vs 131 us per 16 pairs) -- and loses on the wide, low-resolution decoder levels, where it is bound by
+# the shared-memory reads of its weights and cuDNN's tensor-op kernels are not (194 channels: 222 vs 160 us;
+# profiles/step_probe_flow_heads_r02.json, profiles/ncu_flow_head_c16_r02.txt).
+FLOW_HEAD_MAX_CHANNELS = 32
+
+
+def _flow_head_ok(conv, x):
+    return (isinstance(conv, nn.Conv2d) and conv.out_channels == 2 and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1)
+            and tuple(conv.padding) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+            and x.shape[1] % 4 == 0 and conv.in_channels <= x.shape[1] <= FLOW_HEAD_MAX_CHANNELS and _F._is_nhwc_view(x) and x.stride(3) % 4 == 0
+            and x.data_ptr() % 16 == 0 and x.shape[0] <= 65535)
+
+
+def flow_head_weight(conv, cin):
+    """conv.weight of a flow head packed for flowops_flow_head_nhwc (zero for the pad channels of a `cin`-channel input),
+    cached on the module under the same key -- and with the same `.data` caveat -- as padded_weight."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version, cin)
+    cache = conv.__dict__.get("_flowops_whead")
+    if cache is None or cache[0] != key:
+        cache = (key, _F.pack_flow_head_weight(w, cin))
+        conv.__dict__["_flowops_whead"] = cache
+    return cache[1]
+
+
 def reset_padded_weights(net):
     """Drop every cached tensor derived from the weights of `net` (needed after weight updates made through `.data`)
     and the cached concat buffers."""
     for m in net.modules():
-        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
+        for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3", "_flowops_whead"):
             m.__dict__.pop(k, None)
         if isinstance(m.__dict__.get("_sd_warm"), set):
             m._sd_warm.clear()
@@ -90,12 +122,20 @@ def apply_conv(mod, x):
             and isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)) and not conv.__dict__.get("_flowops_stock", False)):
         # a bare convolution with bias (the 2-channel flow heads, the flow upsamplers, inter_conv): ATen adds the bias
         # with a generic strided elementwise kernel after cuDNN's bias-free convolution; the library's epilogue with
-        # slope 1 (t > 0 ? t : t * 1 == t) is the same add, bit for bit, in one vectorised pass
-        y = _raw_conv(conv, x, None)
-        if y.is_contiguous() or _F._is_nhwc(y):
-            _F.bias_lrelu_(y, conv.bias, 1.0)
+        # slope 1 (t > 0 ? t : t * 1 == t) is the same add, bit for bit, in one vectorised pass.  (cuDNN's fused
+        # conv -> bias engines lose on every one of these layers -- narrow outputs, wide inputs: the fusion network's inter_conv0
+        # 3059 us fused vs 961 us, its flow head 592 vs 382; profiles/step_probe_r02.json -- so they are not tried here.)
+        if FLOW_HEAD_KERNEL and torch.backends.cudnn.allow_tf32 and _flow_head_ok(conv, x):
+            # the 2-channel flow heads as one direct FP32 convolution with the bias included (csrc/flowhead.cu) instead of
+            # cuDNN's convolution between two channel-padding kernels + the bias pass.  Exact FP32 sums, so it stands in for
+            # the TF32 convolution only; with TF32 off the cuDNN fp32 convolution below keeps the round-1 summation order
+            y = _F.flow_head(x, flow_head_weight(conv, x.shape[1]), conv.bias)
         else:
-            y += conv.bias.view(1, -1, 1, 1)
+            y = _raw_conv(conv, x, None)
+            if y.is_contiguous() or _F._is_nhwc(y):
+                _F.bias_lrelu_(y, conv.bias, 1.0)
+            else:
+                y += conv.bias.view(1, -1, 1, 1)
     elif x.shape[1] == cin:
         return mod(x)
     else:

@@ -48,7 +48,7 @@ class GraphedFlowNet(torch.nn.Module):
         """Drop the captured graphs (and the padded-weight caches they point into); the next call captures again."""
         self._graphs.clear()
         for m in self.net.modules():
-            for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3"):
+            for k in ("_flowops_wpad", "_flowops_wdense", "_flowops_cbuf", "_flowops_conv1_s2d", "_flowops_wconv3", "_flowops_whead"):
                 m.__dict__.pop(k, None)
             if isinstance(m.__dict__.get("_sd_warm"), set):
                 m._sd_warm.clear()                     # FlowNet2: the next forward builds its plans serially again

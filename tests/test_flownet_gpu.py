@@ -537,3 +537,38 @@ def test_flow_slice_that_ends_the_record_rewrites_the_pad_channels(flowops_lib, 
     assert (ref[:, :8] == 5.0).all() and (ref[:, c_total:] == 0).all()
     for t in (results[False][1], results[True][0], results[True][1]):
         assert torch.equal(t, ref)
+
+
+@pytest.mark.parametrize("B,c_real,c_pad,H,W,bias", [(2, 16, 16, 33, 70, True), (1, 194, 200, 17, 45, True), (3, 22, 24, 5, 3, False),
+                                                     (2, 1026, 1032, 4, 9, True), (1, 32, 32, 64, 129, True), (2, 8, 8, 2, 3, True), (1, 16, 16, 70, 40, True)])
+def test_flow_head_kernel_matches_fp32_convolution(flowops_lib, B, c_real, c_pad, H, W, bias):
+    """flowops_flow_head_nhwc (predict_flow: nn.Conv2d(C, 2, 3, 1, 1), networks/submodules.py:40-41) against cuDNN's fp32
+    convolution: FP32 sums in another order (<= 1e-5 of the largest output); zero pad channels, ragged widths, one-pixel
+    frames, a channel-slice view as the input, with and without bias."""
+    from ir2rgb_b200 import functional as F
+    from ir2rgb_b200.models.flownet2_pytorch.networks import submodules as sm
+    torch.manual_seed(c_real + W)
+    conv = torch.nn.Conv2d(c_real, 2, 3, 1, 1, bias=bias).cuda()
+    x = torch.zeros(B, c_pad, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    x[:, :c_real] = torch.randn(B, c_real, H, W, device="cuda")
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = conv(x[:, :c_real])
+            got = F.flow_head(x, F.pack_flow_head_weight(conv.weight, c_pad), conv.bias)
+            assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+            assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+            # NaN / Inf in a pad channel must not leak (the kernel never reads beyond the layer's channel quads ...)
+            if c_pad - c_real >= 4:
+                x2 = x.clone()
+                x2[:, -4:] = float("nan")
+                got2 = F.flow_head(x2[:, :c_pad - 4], F.pack_flow_head_weight(conv.weight, c_pad - 4), conv.bias)    # a channel-slice view
+                assert torch.equal(got2, got) or ((got2 - want).abs().max() / want.abs().max()).item() <= 1e-5
+            # ... and through the layer dispatch of the conv body (TF32 convolutions allowed: the kernel runs)
+            torch.backends.cudnn.allow_tf32 = True
+            assert sm._flow_head_ok(conv, x) == (c_pad <= sm.FLOW_HEAD_MAX_CHANNELS)
+            if bias and sm._flow_head_ok(conv, x):
+                assert torch.equal(sm.apply_conv(conv, x), got)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

@@ -27,6 +27,13 @@ elif op in ("corr_fwd_nhwc_b16", "corr_fwd_nhwc_b32"):    # what the FlowNet2 st
     planes.fill_from_conv_(b, zb, 1.0, 1, write_act=False)
     buf = F.ConcatBuffer(a, 473, 8)
     fn = lambda: F.correlation_planes_forward_into(planes, buf, 32, 0.1)
+elif op in ("flow_head_c16", "flow_head_c194"):       # predict_flow of the fusion network (full resolution) / of a decoder level 2
+    c_real, hh, ww = (16, 512, 1024) if op == "flow_head_c16" else (194, 128, 256)
+    c_pad = -(-c_real // 8) * 8
+    xh = torch.randn(16, c_pad, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
+    wp = F.pack_flow_head_weight(torch.randn(2, c_real, 3, 3, device="cuda"), c_pad)
+    hb = torch.randn(2, device="cuda")
+    fn = lambda: F.flow_head(xh, wp, hb)
 elif op == "corr_fwd_c4b16":       # the shape bench.py's FlowNet2 step runs per micro-batch of 16 pairs
     a, b = torch.randn(16, 256, 64, 128, device="cuda"), torch.randn(16, 256, 64, 128, device="cuda")
     fn = lambda: F.correlation_forward(a, b, *P)

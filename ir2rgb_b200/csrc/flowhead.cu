@@ -13,8 +13,8 @@
 //     chunk with one 128-bit load each (16 fully used sectors per request) -- and feeds the three output rows it touches,
 //     whose partial sums live in registers (3 rows x 4 pixels x 2 outputs); a finished row is summed over the quads with two
 //     xor-shuffles and stored, and the accumulators rotate.
-//   * The loads of step s + 1 (next chunk, or the next row's first chunk) are issued before the multiply-adds of step s:
-//     there is no barrier in the loop, so a warp always has a row segment in flight.  (A first version that synchronised
+//   * The loads of step s + 1 (next chunk, or the next row's first chunk) are issued before the multiply-adds of step s
+//     into the other of two register buffers: there is no barrier in the loop, so a warp always has a row segment in flight.  (A first version that synchronised
 //     the CTA per chunk and had no prefetch ran at 415 us on the full-resolution head -- latency-bound at 16 warps per SM.)
 //   * All weights sit in shared memory for the whole CTA (72 x 16 bytes per chunk) and are read as 128-bit words shared by
 //     the four pixels of a thread; the arithmetic is packed FFMA2 on (out0, out1) pairs.
@@ -32,10 +32,54 @@ struct HeadRowLoad {
     float4 v[6];
 };
 
+// One input row's worth of multiply-adds of one 16-channel chunk: acc[k] is output row (r - 1 + k), which sees input row r
+// through tap row dy = 2 - k.  W(tap, half) yields the thread's 8 weights of a tap as two float4s.
+template <typename WF>
+__device__ __forceinline__ void head_row_fma(const HeadRowLoad &cur, float2 (&acc)[3][4], WF W)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4 wa = W((2 - k) * 3 + dx, 0), wb = W((2 - k) * 3 + dx, 1);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float4 t = cur.v[p + dx];
+                acc[k][p] = fma2(make_float2(t.x, t.x), make_float2(wa.x, wa.y), acc[k][p]);
+                acc[k][p] = fma2(make_float2(t.y, t.y), make_float2(wa.z, wa.w), acc[k][p]);
+                acc[k][p] = fma2(make_float2(t.z, t.z), make_float2(wb.x, wb.y), acc[k][p]);
+                acc[k][p] = fma2(make_float2(t.w, t.w), make_float2(wb.z, wb.w), acc[k][p]);
+            }
+        }
+    }
+}
+
+// Input row r is consumed: output row r - 1 has received its last contribution -- and, if r is the image's last row, so has
+// row r.  Sum over the four channel quads, add the bias, lane q stores pixel q of its group; then the accumulators rotate.
+__device__ __forceinline__ void head_finish_row(float2 (&acc)[3][4], int r, int H, int y0, int y1, int x0, int q, int W,
+                                                float b0, float b1, float2 *ob)
+{
+#pragma unroll
+    for (int fin = 0; fin < 2; ++fin) {
+        const int yo = r - 1 + fin;
+        if (fin == 1 && r != H - 1) break;
+        float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float sx = acc[fin][p].x, sy = acc[fin][p].y;
+            sx += __shfl_xor_sync(0xffffffffu, sx, 1); sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+            sx += __shfl_xor_sync(0xffffffffu, sx, 2); sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+            if (p == q) mine = make_float2(sx + b0, sy + b1);
+        }
+        if (yo >= y0 && yo < y1 && x0 + q < W) ob[(size_t)yo * W + x0 + q] = mine;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[0][p] = acc[1][p]; acc[1][p] = acc[2][p]; acc[2][p] = make_float2(0.f, 0.f); }
+}
+
 // wp: [n_chunks][tap = dy*3+dx][quad][channel in quad][out] (zero beyond the layer's real channels)
-// MINB: resident CTAs per SM the register allocation aims at (2: 110 registers, no spills; 3: 80 registers, 72 bytes spilled)
-template <int MINB>
-__global__ void __launch_bounds__(32 * kHeadWarps, MINB) flow_head_kernel(const float *__restrict__ x, const float *__restrict__ wp,
+// 120 registers, two CTAs per SM (a build aimed at three spills and runs at half the speed)
+__global__ void __launch_bounds__(32 * kHeadWarps, 2) flow_head_kernel(const float *__restrict__ x, const float *__restrict__ wp,
                                                                        const float *__restrict__ bias, float2 *__restrict__ out,
                                                                        int H, int W, unsigned c_pitch, int cin, int n_chunks, int rows)
 {
@@ -75,49 +119,24 @@ __global__ void __launch_bounds__(32 * kHeadWarps, MINB) flow_head_kernel(const 
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[k][p] = make_float2(0.f, 0.f);
 
-    HeadRowLoad cur, nxt;
-    load(r_first, 0, cur);
-    for (int r = r_first; r <= r_last; ++r) {
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
-            // prefetch the next step
-            const bool last_chunk = chunk + 1 == n_chunks;
-            const int rn = last_chunk ? r + 1 : r, cn = last_chunk ? 0 : chunk + 1;
-            if (rn <= r_last) load(rn, cn, nxt);
-            const float4 *w = sw + chunk * kHeadChunkQuads + q * 2;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {                  // tap row dy = 2 - k
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float4 wa = w[((2 - k) * 3 + dx) * 8], wb = w[((2 - k) * 3 + dx) * 8 + 1];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float4 t = cur.v[p + dx];
-                        acc[k][p] = fma2(make_float2(t.x, t.x), make_float2(wa.x, wa.y), acc[k][p]);
-                        acc[k][p] = fma2(make_float2(t.y, t.y), make_float2(wa.z, wa.w), acc[k][p]);
-                        acc[k][p] = fma2(make_float2(t.z, t.z), make_float2(wb.x, wb.y), acc[k][p]);
-                        acc[k][p] = fma2(make_float2(t.w, t.w), make_float2(wb.z, wb.w), acc[k][p]);
-                    }
-                }
-            }
-            cur = nxt;
-        }
-        // output row r - 1 has received its last contribution -- unless r is the image's last row, then r is complete too
-#pragma unroll
-        for (int fin = 0; fin < 2; ++fin) {
-            const int yo = r - 1 + fin;
-            if (fin == 1 && r != H - 1) break;
-            float2 mine = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                float sx = acc[fin][p].x, sy = acc[fin][p].y;
-                sx += __shfl_xor_sync(0xffffffffu, sx, 1); sy += __shfl_xor_sync(0xffffffffu, sy, 1);
-                sx += __shfl_xor_sync(0xffffffffu, sx, 2); sy += __shfl_xor_sync(0xffffffffu, sy, 2);
-                if (p == q) mine = make_float2(sx + b0, sy + b1);
-            }
-            if (yo >= y0 && yo < y1 && x0 + q < W) ob[(size_t)yo * W + x0 + q] = mine;
-        }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) { acc[0][p] = acc[1][p]; acc[1][p] = acc[2][p]; acc[2][p] = make_float2(0.f, 0.f); }
+    // steps (r, chunk) in order; two register buffers used alternately, so the loads of step s + 1 are in flight while step s
+    // is multiplied and nothing waits for them before step s + 1 starts (a `cur = nxt` copy would)
+    HeadRowLoad bufA, bufB;
+    int r = r_first, chunk = 0;
+    load(r, 0, bufA);
+    auto step = [&](const HeadRowLoad &cur, HeadRowLoad &nxt) -> bool {
+        const bool last_chunk = chunk + 1 == n_chunks;
+        const int rn = last_chunk ? r + 1 : r, cn = last_chunk ? 0 : chunk + 1;
+        const bool more = rn <= r_last;
+        if (more) load(rn, cn, nxt);
+        const float4 *w = sw + chunk * kHeadChunkQuads + q * 2;
+        head_row_fma(cur, acc, [&](int tap, int half) { return w[tap * 8 + half]; });
+        if (last_chunk) head_finish_row(acc, r, H, y0, y1, x0, q, W, b0, b1, ob);
+        r = rn;
+        chunk = cn;
+        return more;
+    };
+    while (step(bufA, bufB) && step(bufB, bufA)) {
     }
 }
 
@@ -147,11 +166,9 @@ extern "C" int flowops_flow_head_nhwc(const float *x, int c_pitch, int cin, cons
     const dim3 grid((unsigned)strips_x, (unsigned)((H + rows * kHeadWarps - 1) / (rows * kHeadWarps)), (unsigned)B);
     FLOWOPS_REQUIRE(grid.y <= 65535, FLOWOPS_EINVAL, "flow_head_nhwc: H %d too large", H);
     // per device, cheap, legal during stream capture: set on every call rather than caching a per-process flag
-    const char *tune = getenv("FLOWOPS_TUNE_HEAD_MINB");           // A/B timing only
-    auto kernel = (tune && tune[0] == '3') ? flow_head_kernel<3> : flow_head_kernel<2>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(flow_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FLOWOPS_REQUIRE(e == cudaSuccess, (int)e, "flow_head_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    kernel<<<grid, 32 * kHeadWarps, smem, (cudaStream_t)stream>>>(x, w_packed, bias, reinterpret_cast<float2 *>(out), H, W,
-                                                                  (unsigned)c_pitch, cin, n_chunks, rows);
+    flow_head_kernel<<<grid, 32 * kHeadWarps, smem, (cudaStream_t)stream>>>(x, w_packed, bias, reinterpret_cast<float2 *>(out), H, W,
+                                                                            (unsigned)c_pitch, cin, n_chunks, rows);
     return check_launch("flow_head_nhwc");
 }

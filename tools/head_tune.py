@@ -1,5 +1,5 @@
-"""A/B timing of flowops_flow_head_nhwc's tuning knobs (resident CTAs per SM the register allocation aims at, rows per
-strip) at the flow-head shapes of FlowNet2 (16 pairs, 512 x 1024)."""
+"""A/B timing of flowops_flow_head_nhwc's rows-per-strip knob (FLOWOPS_TUNE_HEAD_ROWS) at the flow-head shapes of FlowNet2
+(16 pairs, 512 x 1024)."""
 import json
 import os
 import sys
@@ -27,7 +27,7 @@ def time_us(fn, n=20):
 def main():
     B = 16
     res = []
-    for c_real, hh, ww in ((16, 512, 1024), (32, 256, 512), (194, 128, 256), (386, 64, 128), (770, 32, 64)):
+    for c_real, hh, ww in ((16, 512, 1024), (32, 256, 512), (194, 128, 256)):
         c_pad = -(-c_real // 8) * 8
         torch.manual_seed(c_real)
         x = torch.randn(B, c_pad, hh, ww, device="cuda").contiguous(memory_format=torch.channels_last)
@@ -35,18 +35,15 @@ def main():
         bias = torch.randn(2, device="cuda")
         wp = F.pack_flow_head_weight(w, c_pad)
         rec = {"cin": c_real, "hw": [hh, ww]}
-        for minb in ("2", "3"):
-            for rows in ("auto", "4", "8", "16", "32", "64"):
-                os.environ["FLOWOPS_TUNE_HEAD_MINB"] = minb
-                if rows == "auto":
-                    os.environ.pop("FLOWOPS_TUNE_HEAD_ROWS", None)
-                else:
-                    os.environ["FLOWOPS_TUNE_HEAD_ROWS"] = rows
-                rec["minb%s_rows%s" % (minb, rows)] = round(time_us(lambda: F.flow_head(x, wp, bias)), 1)
+        for rows in ("auto", "4", "8", "16", "32", "64"):
+            if rows == "auto":
+                os.environ.pop("FLOWOPS_TUNE_HEAD_ROWS", None)
+            else:
+                os.environ["FLOWOPS_TUNE_HEAD_ROWS"] = rows
+            rec["rows_" + rows] = round(time_us(lambda: F.flow_head(x, wp, bias)), 1)
         print(json.dumps(rec), flush=True)
         res.append(rec)
     os.environ.pop("FLOWOPS_TUNE_HEAD_ROWS", None)
-    os.environ.pop("FLOWOPS_TUNE_HEAD_MINB", None)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "head_tune.json"), "w"), indent=1)
 
 

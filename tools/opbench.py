@@ -257,6 +257,22 @@ def run(iters=20, skip_ref=False, small=False, quiet=False, ffma=None, only=None
     add("gridsample_fwd_smooth_f16", lambda i, f: F.warp_forward(i, f, GS), (img16, flows["smooth"].half()), _chain16,
         alg_bytes=4 * plane)
     del img16, gout16, y16, gy16
+    # ---- FlowNet2 glue of the fusion network at 16 pairs: the full-resolution flow head and the
+    # depth-to-space epilogue of deconv0 with the flow upsampler folded in ----
+    if not small:
+        xh = torch.randn(16, 16, 512, 1024, device="cuda").contiguous(memory_format=torch.channels_last)
+        wh = F.pack_flow_head_weight(torch.randn(2, 16, 3, 3, device="cuda"), 16)
+        bh = torch.randn(2, device="cuda")
+        add("flow_head_c16_fullres", lambda x, w, b: F.flow_head(x, w, b), (xh, wh, bh), None, alg_bytes=xh.numel() * 4 + 16 * 512 * 1024 * 8)
+        del xh
+        y4 = torch.randn(16, 64, 256, 512, device="cuda").contiguous(memory_format=torch.channels_last)
+        fl = torch.randn(16, 2, 256, 512, device="cuda").contiguous(memory_format=torch.channels_last)
+        cb = F.ConcatBuffer(y4, 82, 8, shape=(16, 512, 1024))
+        b16c, fw, fb = torch.randn(16, device="cuda"), torch.randn(2, 2, 4, 4, device="cuda"), torch.randn(2, device="cuda")
+        # bytes: y4 read + 16 + 2 (+ 6 pad) channels written per output pixel + the low-resolution flow
+        add("d2s_flowup_deconv0", lambda y, f: cb.bias_lrelu_d2s_in(y, b16c, 0.1, 64, (f, fw, fb)), (y4, fl), None,
+            alg_bytes=y4.numel() * 4 + 16 * 512 * 1024 * 24 * 4 + fl.numel() * 4)
+        del y4, fl, cb
     B, C, H, W = (2, 64, 24, 32) if small else (8, 256, 48, 64)
     a16, b16 = torch.randn(B, C, H, W, device="cuda").half(), torch.randn(B, C, H, W, device="cuda").half()
     add("corr_fwd_c2_f16", lambda a, b: F.correlation_forward(a, b, *P), (a16, b16),

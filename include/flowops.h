@@ -89,6 +89,10 @@ int flowops_warp_bwd(const float *img, const float *flow, const float *gout,
  *                      in fp64 by accident of a `1.` literal (resample2d_kernel.cu:55-58); the default path reproduces
  *                      that bit for bit at the price of 20 fp64 conversions per pixel.  The fp32 blend differs from it
  *                      by ~1e-7 max-relative (tolerance 1e-5).
+ *   bit 2 (default 0)  flowops_warp_bwd accumulates the image gradient per tile in shared memory in fixed point (exact to
+ *                      2^-28 of the tile's largest gradient); faster on per-pixel-random flows only.
+ *   bit 3 (default 0)  GRIDSAMPLE forward of frames with C <= 3: use the row-walking kernel instead of the variant that keeps
+ *                      two rows of corner gathers in flight per thread (bit-identical results; A/B timing only).
  * No reference counterpart. */
 int flowops_warp_set_impl(int flags);
 int flowops_warp_get_impl(void);

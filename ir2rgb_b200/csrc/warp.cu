@@ -32,7 +32,9 @@ namespace flowops {
 // process-wide switches of the warp kernels (flowops_warp_set_impl): bit 0 = image gradient by owned accumulation in
 // per-warp shared-memory windows (warp_win_bwd.cuh; default OFF: measured on B200 it cuts the L2 reduction sector
 // operations 4x but only wins on incoherent flows), bit 1 = forward blend with fp32 weights instead of the
-// reference's accidental fp64 weight products (tolerance mode, see flowops.h; default off)
+// reference's accidental fp64 weight products (tolerance mode, see flowops.h; default off), bit 2 = fixed-point shared-memory
+// image gradient (warp_fx_bwd.cuh; default off), bit 3 = GRIDSAMPLE forward on the row-walking kernel instead of
+// warp_rows_mlp_kernel (A/B timing; default off)
 static int g_warp_impl = -1;
 int warp_impl_flags()
 {
@@ -263,6 +265,36 @@ static int launch_fwd(const float *img, const float *flow, float *out, int B, in
         a.B = B; a.C = C; a.H = H; a.W = W; a.rows = warp_rows_pick(B, H, W);
         a.wm1 = (float)(W - 1); a.hm1 = (float)(H - 1);
         a.lin_x = lx; a.lin_y = ly; a.invx = invx; a.invy = invy;
+#ifdef FLOWOPS_TUNE_WARP_MLP
+        // variant build (python -m ir2rgb_b200.build --out ... -DFLOWOPS_TUNE_WARP_MLP): flag bits 3..5 pick rows per thread /
+        // rows of gathers in flight / resident CTAs of warp_rows_mlp_kernel in every mode (tools/warp_mlp_probe.py)
+        const int variant = (warp_impl_flags() >> 3) & 7;
+        if (variant && C == 3 && a.rows == 4) {
+            switch (variant) {
+            case 1: launch_warp_rows_mlp<MODE, 3, 4, 2, 4>(a, st); break;
+            case 2: launch_warp_rows_mlp<MODE, 3, 4, 2, 3>(a, st); break;
+            case 3: launch_warp_rows_mlp<MODE, 3, 4, 4, 2>(a, st); break;
+            case 4: launch_warp_rows_mlp<MODE, 3, 8, 2, 4>(a, st); break;
+            case 5: launch_warp_rows_mlp<MODE, 3, 8, 3, 3>(a, st); break;
+            case 6: launch_warp_rows_mlp<MODE, 3, 4, 4, 3>(a, st); break;
+            default: launch_warp_rows_mlp<MODE, 3, 4, 2, 5>(a, st); break;
+            }
+            return check_launch("warp_fwd");
+        }
+#else
+        if constexpr (MODE == FLOWOPS_WARP_GRIDSAMPLE) if (a.rows == 4 && !(warp_impl_flags() & 8)) {
+            // frames large enough for 4-row strips, grid_sample arithmetic: two rows of corner gathers in flight per thread
+            // (4 rows per thread, 4 CTAs per SM).  Bit-identical to the row-walking kernel; measured at config 3
+            // (profiles/warp_fwd_mlp_probe_r02.json): 76.5 -> 72.4 us on the smooth flow, 166.5 -> 148.1 us on the bilinear-
+            // upsampled noise flow, 101.6 -> 94.0 us on per-pixel noise, equal on a zero flow.  The same variant LOSES in
+            // both Resample2d modes (nearest 78.8 -> 88.6 us), which therefore keep the row-walking kernel; flag bit 3 of
+            // flowops_warp_set_impl switches it off (A/B timing).
+            if (C == 3) launch_warp_rows_mlp<MODE, 3, 4, 2, 4>(a, st);
+            else if (C == 2) launch_warp_rows_mlp<MODE, 2, 4, 2, 4>(a, st);
+            else launch_warp_rows_mlp<MODE, 1, 4, 2, 4>(a, st);
+            return check_launch("warp_fwd");
+        }
+#endif
         launch_warp_rows<MODE, EPI_STORE, true>(a, st);
         return check_launch("warp_fwd");
     }

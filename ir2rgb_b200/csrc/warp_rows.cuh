@@ -360,6 +360,77 @@ __global__ void __launch_bounds__(256, 5) warp_rows_kernel(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The forward store with more loads in flight per thread (plain warps only: EPI_STORE, full-resolution flow).
+// tools/warp_flow_sweep.py showed that the row-walking kernel above needs 70 us at config 3 even for a ZERO flow (0.59 of
+// the HBM roofline, perfectly coalesced gathers): its time is set by the dependent chain flow -> gather -> blend of one row
+// at a time, not by the access pattern of the flow.  Here a thread owns R rows of its column, loads the flow of all R rows
+// at once (2R independent loads), and keeps the corner gathers of DEPTH rows in flight (12 * DEPTH loads for 3 channels)
+// while it blends and stores the oldest one.  Fully unrolled: every buffer index is a compile-time constant.  Same
+// pix_prep / pix_gather / pix_finish as above, so the results are bit-identical to the row-walking kernel in every mode.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int CT, int R, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) warp_rows_mlp_kernel(const __grid_constant__ WarpArgs a)
+{
+    static_assert(DEPTH >= 2 && DEPTH <= R, "DEPTH rows of gathers in flight out of R rows per thread");
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
+    if (x >= a.W || y0 >= a.H) return;
+    const unsigned hw = (unsigned)a.H * a.W, W = (unsigned)a.W;
+    const size_t b = blockIdx.z;
+    const float *src = a.img + b * a.img_bs;
+    asm("" : "+l"(src));
+    const unsigned p0 = (unsigned)y0 * W + (unsigned)x;
+    const float *fl = a.flow + b * 2 * hw + p0;
+    float *out = a.out + b * a.out_bs + p0;
+    const float xfl = small_int_as_float(x);
+    float dx[R], dy[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned o = (y0 + r < a.H ? (unsigned)r : 0u) * W;          // rows below the image redo row y0 (never stored)
+        dx[r] = ldg_stream(fl + o); dy[r] = ldg_stream(fl + o + hw);
+    }
+    PixPrep<MODE> q[DEPTH];
+    PixVals<CT> v[DEPTH];
+#pragma unroll
+    for (int r = 0; r < DEPTH - 1; ++r) {
+        const int yr = y0 + r < a.H ? y0 + r : y0;
+        pix_prep(q[r], a, xfl, small_int_as_float(yr), x, yr, dx[r], dy[r]);
+        pix_gather<CT, false, false>(v[r], q[r], src, src, src, hw);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        constexpr int D1 = DEPTH - 1;
+        if (r + D1 < R) {
+            const int yr = y0 + r + D1 < a.H ? y0 + r + D1 : y0;
+            pix_prep(q[(r + D1) % DEPTH], a, xfl, small_int_as_float(yr), x, yr, dx[r + D1], dy[r + D1]);
+            pix_gather<CT, false, false>(v[(r + D1) % DEPTH], q[(r + D1) % DEPTH], src, src, src, hw);
+        }
+        if (y0 + r < a.H)
+            pix_finish<MODE, CT, EPI_STORE, true>(a, q[r % DEPTH], v[r % DEPTH], out + (unsigned)r * W, nullptr, hw, dx[r], dy[r]);
+    }
+}
+
+template <int MODE, int CT, int R, int DEPTH, int MINB>
+static inline void launch_warp_rows_mlp(WarpArgs a, cudaStream_t st)
+{
+    const int B = a.B;
+    const size_t hw = (size_t)a.H * a.W;
+    a.rows = R;
+    for (int b0 = 0; b0 < B; b0 += 65535) {            // gridDim.z limit
+        WarpArgs c = a;
+        c.B = B - b0 < 65535 ? B - b0 : 65535;
+        c.img = a.img + (size_t)b0 * a.img_bs;
+        c.flow = a.flow + (size_t)b0 * 2 * hw;
+        c.out = a.out + (size_t)b0 * a.out_bs;
+        const int bx = c.W >= 256 ? 256 : (c.W > 64 ? 128 : (c.W > 32 ? 64 : 32));
+        const dim3 block(bx, 256 / bx, 1);
+        const int strip = (int)block.y * R;
+        const dim3 grid((c.W + bx - 1) / bx, (c.H + strip - 1) / strip, c.B);
+        warp_rows_mlp_kernel<MODE, CT, R, DEPTH, MINB><<<grid, block, 0, st>>>(c);
+    }
+}
+
 // 256-thread blocks shaped to the image width: whole warps lie along x (coalescing), the block's rows
 // are `rows` apart so that each thread walks its own strip
 static inline void warp_rows_shape(int B, int H, int W, int rows, dim3 &grid, dim3 &block)

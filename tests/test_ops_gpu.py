@@ -656,3 +656,27 @@ def test_resample2d_tolerance_mode_vs_reference_ext(ops, ref, flavour):
     assert maxrel(fast, want) <= 1e-6
     warped_e, norm_e = F.warp_diff_norm_forward(x6, flow)
     assert maxrel(warped_f, warped_e) <= 1e-6 and maxrel(norm_f, norm_e) <= 1e-6
+
+
+@pytest.mark.parametrize("C", [1, 2, 3])
+def test_gridsample_forward_two_rows_in_flight_kernel_is_bit_identical(flowops_lib, C):
+    """Large frames take warp_rows_mlp_kernel in GRIDSAMPLE mode (two rows of corner gathers in flight per thread); flag bit 3
+    forces the row-walking kernel, which the goldens and the ATen comparisons above pin.  Ragged frame (neither dimension a
+    multiple of the block shape, bottom strip shorter than 4 rows), NaN / Inf / huge flow values."""
+    from ir2rgb_b200 import functional as F
+    B, H, W = 3, 1021, 1531                                   # > 3.03 M pixels: 4-row strips
+    torch.manual_seed(31)
+    img = 2 * torch.rand(B, C, H, W, device="cuda") - 1
+    flow = torch.nn.functional.interpolate(30 * torch.randn(B, 2, 16, 24, device="cuda"), size=(H, W), mode="bicubic",
+                                           align_corners=False).contiguous()
+    flow[0, 0, 5, 7] = float("nan"); flow[1, 1, 100, 200] = float("inf"); flow[2, 0, 0, 0] = -3e38
+    flow[2, 1, H - 1, W - 1] = 5e6; flow[1, :, H - 2:, :] = 4 * torch.randn(2, 2, W, device="cuda")
+    prev = flowops_lib.flowops_warp_get_impl()
+    try:
+        flowops_lib.flowops_warp_set_impl(prev & ~8)
+        new = F.warp_forward(img, flow, F.WARP_GRIDSAMPLE)
+        flowops_lib.flowops_warp_set_impl(prev | 8)
+        old = F.warp_forward(img, flow, F.WARP_GRIDSAMPLE)
+    finally:
+        flowops_lib.flowops_warp_set_impl(prev)
+    assert torch.equal(new.view(torch.int32), old.view(torch.int32))

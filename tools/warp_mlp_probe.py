@@ -1,7 +1,9 @@
 """Forward warp at the config-3 shape: the row-walking kernel (variant 0) against the variants of warp_rows_mlp_kernel that keep
 more loads in flight per thread (flowops_warp_set_impl bits 3..5), in all three arithmetic modes, on flows of increasing
 roughness; bit-identity of every variant with the row-walking kernel, also on a ragged frame.
-    python tools/warp_mlp_probe.py [out.json]"""
+Needs a variant build with every variant compiled in:
+    python -m ir2rgb_b200.build --out tools/_exp/libflowops_mlp.so -DFLOWOPS_TUNE_WARP_MLP
+    FLOWOPS_LIB=tools/_exp/libflowops_mlp.so python tools/warp_mlp_probe.py [out.json]"""
 import json
 import os
 import sys

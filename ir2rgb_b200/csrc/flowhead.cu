@@ -153,7 +153,8 @@ extern "C" int flowops_flow_head_nhwc(const float *x, int c_pitch, int cin, cons
                     "flow_head_nhwc: x and w_packed must be 16-byte aligned, out 8-byte aligned");
     const int n_chunks = (cin + 15) / 16;
     const size_t smem = (size_t)n_chunks * kHeadChunkQuads * sizeof(float4);
-    FLOWOPS_REQUIRE(smem <= 200 * 1024, FLOWOPS_EUNSUPPORTED, "flow_head_nhwc: %d input channels need %zu bytes of shared memory", cin, smem);
+    constexpr size_t kHeadMaxSmem = 200 * 1024;
+    FLOWOPS_REQUIRE(smem <= kHeadMaxSmem, FLOWOPS_EUNSUPPORTED, "flow_head_nhwc: %d input channels need %zu bytes of shared memory", cin, smem);
     // rows per strip: tall strips re-read fewer halo rows, short ones give the small decoder levels enough warps (1.5 x the
     // 148 SMs x 16 resident ones)
     const long strips_x = (W + 31) / 32;
@@ -165,8 +166,10 @@ extern "C" int flowops_flow_head_nhwc(const float *x, int c_pitch, int cin, cons
     }
     const dim3 grid((unsigned)strips_x, (unsigned)((H + rows * kHeadWarps - 1) / (rows * kHeadWarps)), (unsigned)B);
     FLOWOPS_REQUIRE(grid.y <= 65535, FLOWOPS_EINVAL, "flow_head_nhwc: H %d too large", H);
-    // per device, cheap, legal during stream capture: set on every call rather than caching a per-process flag
-    cudaError_t e = cudaFuncSetAttribute(flow_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // per device, cheap, legal during stream capture: set on every call rather than caching a per-process flag -- and always
+    // to the same ceiling, not to this call's size, so that two host threads launching heads of different widths cannot
+    // lower the limit under each other between this call and the launch
+    cudaError_t e = cudaFuncSetAttribute(flow_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadMaxSmem);
     FLOWOPS_REQUIRE(e == cudaSuccess, (int)e, "flow_head_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     flow_head_kernel<<<grid, 32 * kHeadWarps, smem, (cudaStream_t)stream>>>(x, w_packed, bias, reinterpret_cast<float2 *>(out), H, W,
                                                                             (unsigned)c_pitch, cin, n_chunks, rows);

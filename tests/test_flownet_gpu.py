@@ -3,6 +3,7 @@
 import json
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -70,7 +71,7 @@ def test_oracle_network_never_calls_libflowops(nets):
         _lib.launch_hook = prev
 
 
-def test_fused_glue_is_bit_identical_to_operator_chain(nets):
+def test_fused_glue_is_bit_identical_to_operator_chain(nets, c_oracle):
     from ir2rgb_b200 import functional as F
     from ir2rgb_b200.models.flownet2_pytorch.networks.channelnorm_package.channelnorm import ChannelNorm
     from ir2rgb_b200.models.flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d
@@ -81,6 +82,11 @@ def test_fused_glue_is_bit_identical_to_operator_chain(nets):
     w_ref = Resample2d()(x[:, 3:], flow)
     n_ref = ChannelNorm()((x[:, :3] - w_ref).contiguous())
     assert torch.equal(warped, w_ref) and torch.equal(norm, n_ref)
+    # ... and directly against the C restatement of the reference kernels (resample2d_kernel.cu:16-64, channelnorm_kernel.cu:19-60)
+    xn, fn = x.cpu().numpy(), flow.cpu().numpy()
+    w_o = c_oracle.resample2d_fwd(np.ascontiguousarray(xn[:, 3:]), fn)
+    n_o = c_oracle.cnorm_fwd(np.ascontiguousarray(xn[:, :3] - w_o))
+    assert np.array_equal(warped.cpu().numpy(), w_o) and np.array_equal(norm.cpu().numpy(), n_o)
     # writing straight into a concat buffer
     buf = torch.zeros(2, 12, 64, 96, device="cuda")
     F.warp_diff_norm_forward(x, flow, out=(buf, 6, 11))
